@@ -1,0 +1,190 @@
+/*
+ * iid_b200.h -- C ABI of the B200-native elastic-scattering (Debye sum) hot path.
+ *
+ * This is the drop-in boundary for the three callables that pyIID's
+ * ElasticScatter.set_processor binds (reference:
+ * pyiid/experiments/elasticscatter/__init__.py:206-292 -> self.fq, self.grad,
+ * self.grad_pdf) and for the Rw / chi^2 energy+forces that pyiid.calc.Calc1D
+ * derives from them (pyiid/calc/calc_1d.py:78-95, pyiid/calc/__init__.py:10-105).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types.
+ *  - every function returns int: 0 = ok, negative = IID_E_* below, positive =
+ *    a cudaError_t.  iid_last_error() returns a thread-local message.
+ *  - "dev" pointers are device pointers on the handle's device; "host"
+ *    pointers are ordinary host memory.  `stream` is a cudaStream_t passed as
+ *    void* (NULL = the handle's own stream).  Device-pointer calls only
+ *    ENQUEUE work; host-pointer calls (suffix _host) copy in, run, copy out
+ *    and synchronise before returning.
+ *  - precision: IID_FP32 computes the pair sums in float32 arithmetic the way
+ *    the reference does (float32-rounded positions, float32 accumulators,
+ *    float64 for the F(Q) reduction); IID_FP64 computes everything in float64.
+ *  - a handle is used by one thread at a time.
+ *  - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef IID_B200_H
+#define IID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IID_FP32 0
+#define IID_FP64 1
+
+#define IID_POT_RW 0      /* master_kernel.get_rw      (:206-236) */
+#define IID_POT_CHI_SQ 1  /* master_kernel.get_chi_sq  (:239-266) */
+
+#define IID_E_BADARG (-1)
+#define IID_E_NOSTRUCT (-2)   /* iid_set_structure not called yet      */
+#define IID_E_NOTRANSFORM (-3)/* iid_set_transform not called yet      */
+#define IID_E_NOMEM (-4)
+#define IID_E_NODEVICE (-5)   /* no CUDA device / wrong architecture   */
+
+typedef struct iid_handle iid_handle;
+
+/* library / device ------------------------------------------------------- */
+int iid_version(void);
+const char *iid_last_error(void);
+int iid_device_count(int *count);
+/* sm count, clock (kHz), compute capability major*10+minor */
+int iid_device_info(int device, int *sm_count, int *clock_khz, int *cc);
+
+/* handle ------------------------------------------------------------------ */
+/* Owns one stream, the staged (element-sorted) atom arrays, the work-item
+ * lists and all scratch for one GPU.  Replaces the per-call allocation done
+ * by atomics/gpu_atomics.py:89-280 and the thread-per-GPU farm of
+ * gpu_wrappers/gpu_wrap.py:287-314. */
+int iid_create(int device, int precision, iid_handle **out);
+int iid_destroy(iid_handle *h);
+int iid_get_stream(iid_handle *h, void **stream);
+int iid_synchronize(iid_handle *h);
+
+/* Which slice of the pair-tile work list this handle computes: items
+ * rank, rank+world, ... (one process per GPU; the caller all-reduces the
+ * partial outputs).  Default (0, 1).  Replaces gpu_wrap.gpu_multithreading. */
+int iid_set_shard(iid_handle *h, int rank, int world);
+
+/* Structure = what stays fixed while positions move: per-atom element index
+ * type_index[n] in [0, n_types) and the per-ELEMENT form-factor table
+ * ftable[n_types][nq] sampled at Q_m = m*qbin.  Replaces the per-atom
+ * `atoms.arrays['F(Q) scatter' | 'PDF scatter']` [n, nq] float32 arrays that
+ * wrap_fq / wrap_fq_grad pull from the Atoms object
+ * (cpu_wrappers/flat_multi_cpu_wrap.py:11-19) and re-upload per chunk
+ * (atomics/gpu_atomics.py:143,248).  The normaliser
+ * na[m] = N * mean_pairs(f_i f_j) (flat_multi_cpu_wrap.py:52-55) is computed
+ * here in float64 from its closed form.  Host pointers. */
+int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
+                      int64_t n_types, const double *ftable, int64_t nq,
+                      double qbin);
+
+/* F(Q) -> G(r) as a dense real matrix T[nr][nq] (float64, host) reproducing
+ * master_kernel.get_pdf_at_qmin :39-104 (zero below qmin, zero-pad, odd
+ * extension, inverse FFT, linear re-binning onto rgrid, factor 2); the host
+ * layer builds it once per experiment.  Needed by iid_fq_to_gr, iid_potential,
+ * iid_energy_forces*. */
+int iid_set_transform(iid_handle *h, int64_t nr, int64_t nq, const double *T);
+
+/* sizes ------------------------------------------------------------------- */
+int iid_get_sizes(iid_handle *h, int64_t *n, int64_t *nq, int64_t *nr,
+                  int64_t *n_items_fq, int64_t *n_items_grad);
+
+/* pair sums (device pointers; enqueue only) ------------------------------- */
+/* pos_dev: [n,3] float64 in the caller's atom order (rounded to float32
+ * inside when the handle is IID_FP32, as wrap_fq does :11-12).
+ *
+ * iid_fq_partial: S[m] = sum over this shard's unordered pairs of
+ *   f_i f_j sin(Q_m r_ij)/r_ij  -> S_dev[nq] float64 (overwritten).
+ *   Replaces atomic_fq (atomics/cpu_atomics.py:60-78, gpu_atomics.py:89-189).
+ * iid_fq_finish: F[m] = 2 S[m] / na[m], 0 where na == 0
+ *   (flat_multi_cpu_wrap.py:49-60) -> F_dev[nq] float64. */
+int iid_fq_partial(iid_handle *h, const double *pos_dev, double *S_dev,
+                   void *stream);
+int iid_fq_finish(iid_handle *h, const double *S_dev, double *F_dev,
+                  void *stream);
+
+/* iid_grad_fq_partial: this shard's rows/terms of the NORMALISED gradient in
+ * the reference's convention (SURVEY.md section 8a note 1)
+ *   G[i,w,m] = (1/na[m]) sum_j f_i f_j a_ij(m) (q_j - q_i)_w,
+ *   a = (Q cos(Q r) - sin(Q r)/r) / r^2
+ * accumulated into G_dev[n][3][nq] (float32 for IID_FP32, float64 for
+ * IID_FP64; the call zeroes it first), plus the same S[m] partial as
+ * iid_fq_partial in S_dev (may be NULL).  Replaces atomic_grad_fq
+ * (cpu_atomics.py:81-102, gpu_atomics.py:192-280) + the /na of
+ * flat_multi_cpu_wrap.py:93-102. */
+int iid_grad_fq_partial(iid_handle *h, const double *pos_dev, void *G_dev,
+                        double *S_dev, void *stream);
+
+/* iid_force_partial: force[i,w] = sum_m wq[m] * G[i,w,m] without forming G:
+ * one scalar per pair, sum_m wq[m] f_i f_j a_ij(m) / na[m], walked over the
+ * pair triangle.  wq_dev[nq] float64, force_dev[n][3] float64 (overwritten
+ * with this shard's partial).  Replaces get_grad_pdf + get_grad_rw's
+ * contraction (master_kernel.py:276-347) without the N x 3 x R array. */
+int iid_force_partial(iid_handle *h, const double *pos_dev,
+                      const double *wq_dev, double *force_dev, void *stream);
+
+/* float64 small stages (device pointers; enqueue only) -------------------- */
+/* G[nr] = T F  (master_kernel.get_pdf_at_qmin) */
+int iid_fq_to_gr(iid_handle *h, const double *F_dev, double *G_dev,
+                 void *stream);
+/* Rw or chi^2 of gcalc against target (get_rw / get_chi_sq), the scale, and
+ * the chain-rule weight vector wq[m] = conv * sum_r c_r T[r][m] with c from
+ * get_grad_rw / get_grad_chi_sq (master_kernel.py:293-375).
+ * out_dev[4] = {energy = value*conv, scale, raw value, 0}. */
+int iid_potential(iid_handle *h, const double *G_dev, const double *target_dev,
+                  int potential, double conv, double *out_dev, double *wq_dev,
+                  void *stream);
+/* grad_pdf[rows][nr] = grad_fq[rows][nq] . T^T  (master_kernel.grad_pdf
+ * :276-290 / gpu_wrap.grad_pdf :197-284): one row per (atom, direction).
+ * grad_fq_dev is float32 (IID_FP32) or float64; output float64. */
+int iid_grad_pdf(iid_handle *h, const void *grad_fq_dev, int64_t rows,
+                 double *grad_pdf_dev, void *stream);
+
+/* host-buffer entry points (copy in, compute, copy out, synchronise) ------ */
+/* These are what a ctypes/numpy caller binds; single shard or partial
+ * results when a shard is set.  F_host[nq], G_host[n*3*nq] (float32 or
+ * float64 by precision), pdf_host[nr], forces_host[n*3] are float64 unless
+ * noted. */
+int iid_fq_host(iid_handle *h, const double *pos_host, double *F_host);
+int iid_grad_fq_host(iid_handle *h, const double *pos_host, void *G_host,
+                     double *F_host);
+int iid_pdf_host(iid_handle *h, const double *pos_host, double *pdf_host,
+                 double *F_host);
+/* One call per HMC leapfrog: energy = potential(G(r), target)*conv and
+ * forces = grad(...)*conv exactly as Calc1D.calculate_energy/forces
+ * (calc/calc_1d.py:78-95) with exp_function = get_pdf and
+ * exp_grad_function = get_grad_pdf.  out_host[4] as iid_potential. */
+int iid_energy_forces_host(iid_handle *h, const double *pos_host,
+                           const double *target_host, int potential,
+                           double conv, double *out_host,
+                           double *forces_host, double *pdf_host);
+
+/* Rw / chi^2 of two host vectors (calc/__init__.py wrap_rw :10-31,
+ * wrap_chi_sq :33-54) plus the chain-rule vector c[len] with
+ * grad[i,w] = sum_k c[k] dcalc[i,w,k] (wrap_grad_rw :56-79, wrap_grad_chi_sq
+ * :82-105; master_kernel.py:293-375).  out_host[4] as iid_potential. */
+int iid_rw_host(iid_handle *h, const double *gcalc_host, const double *gobs_host,
+                int64_t len, int potential, double conv, double *out_host,
+                double *c_host);
+/* out[row] = sum_k A[row][k] c[k], A float32 (a_is_f32) or float64, host. */
+int iid_contract_host(iid_handle *h, const void *A_host, int a_is_f32,
+                      int64_t rows, int64_t len, const double *c_host,
+                      double *out_host);
+/* G(r) = T F for a host F(Q) (get_pdf's noise branch,
+ * elasticscatter/__init__.py:371-390). */
+int iid_fq_to_gr_host(iid_handle *h, const double *F_host, double *pdf_host);
+
+/* instrumentation ---------------------------------------------------------- */
+/* number of kernels this handle has launched since creation */
+int iid_launch_count(iid_handle *h, int64_t *count);
+/* device time (ms, CUDA events on the launching stream) of the last pair-sum
+ * kernel launched by this handle, and its algorithmic pair*Q count */
+int iid_last_kernel_ms(iid_handle *h, float *ms, double *pairq);
+int iid_set_timing(iid_handle *h, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IID_B200_H */

@@ -1,0 +1,402 @@
+"""Host side of the B200 processor: owns the native handle and the caches.
+
+Replaces the reference's processor wrappers
+(``pyiid/experiments/elasticscatter/gpu_wrappers/gpu_wrap.py:119-314`` and the
+chunk workers ``atomics/gpu_atomics.py:89-280``): instead of chunking the pair
+list by free memory and farming chunks to one Python thread per GPU, one
+process drives one GPU through the C ABI (``include/iid_b200.h``), and with
+``torch.distributed`` initialised each rank computes its slice of the
+pair-tile work list and the partial F(Q) / force / gradient arrays are
+all-reduced over NCCL.
+
+PyTorch is used only when world_size > 1 (device buffers for the collective);
+the single-GPU path talks to the library with numpy host buffers.
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import IID_FP32, IID_FP64, IID_POT_RW, IID_POT_CHI_SQ, check
+
+POTENTIALS = {'rw': IID_POT_RW, 'chi_sq': IID_POT_CHI_SQ}
+
+
+def _dist_state():
+    """(rank, world) of an initialised torch.distributed group, else (0, 1)."""
+    try:
+        import torch.distributed as dist
+    except ImportError:  # pragma: no cover
+        return 0, 1
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def pdf_matrix(nq, rstep, qstep, rgrid, qmin):
+    """Dense T[R, Q] with ``G = T @ F`` equal to the reference's
+    ``get_pdf_at_qmin(F, rstep, qstep, rgrid, qmin)``
+    (``kernels/master_kernel.py:39-104`` with ``fft_fq_to_gr :108-128`` and
+    ``fft_gr_to_fq :131-203``).
+
+    The reference zeroes F below ceil(qmin/qstep), zero-pads it to
+    L = max(len F, ceil(pi/rstep/qstep)), odd-extends it into a 4*npad2 real
+    array on the even slots, takes ``np.fft.ifft`` and keeps
+    ``imag[::2]*npad2*qstep*2/pi``, i.e.
+    ``g[i] = (qstep/pi) * sum_k F[k] sin(2 pi k i / npad2)``; it then
+    interpolates linearly at ``rgrid/(2 drpad)``, ``drpad = pi/(npad2 qstep)``,
+    and doubles.  The phases k*i mod npad2 are reduced in integers, so the
+    matrix is exact to float64 rounding.
+    """
+    rgrid = np.asarray(rgrid, dtype=np.float64)
+    kmin = int(math.ceil(qmin / qstep))
+    nfromdr = int(math.ceil(math.pi / rstep / qstep))
+    length = max(int(nq), nfromdr)
+    padrmin = int(round(qmin / qstep))
+    npad1 = padrmin + length
+    npad2 = (1 << int(math.ceil(math.log(npad1, 2)))) * 2
+    drpad = math.pi / (npad2 * qstep)
+    axdrp = rgrid / drpad / 2
+    ilo = axdrp.astype(int)
+    whi = axdrp - ilo
+    wlo = 1.0 - whi
+    if len(ilo) and ilo.max() + 1 >= npad2:
+        raise IndexError('rgrid reaches beyond the padded transform length')
+    k = np.arange(int(nq), dtype=np.int64)
+    ph_lo = (ilo[:, None].astype(np.int64) * k[None, :]) % npad2
+    ph_hi = ((ilo[:, None].astype(np.int64) + 1) * k[None, :]) % npad2
+    w = 2.0 * np.pi / npad2
+    t = wlo[:, None] * np.sin(w * ph_lo) + whi[:, None] * np.sin(w * ph_hi)
+    t *= 2.0 * qstep / math.pi
+    t[:, :kmin] = 0.0
+    return np.ascontiguousarray(t)
+
+
+def element_table(scatter_array, numbers=None):
+    """Split a per-atom scatter-factor array [N, Q] into a per-element table
+    [E, Q] and an index [N].  Rows are grouped by atomic number when that is
+    consistent (the usual case: ``_wrap_atoms`` broadcasts one row per
+    element), otherwise by unique rows."""
+    scat = np.asarray(scatter_array)
+    n = scat.shape[0]
+    if numbers is not None and len(numbers) == n:
+        numbers = np.asarray(numbers)
+        zs, first, inv = np.unique(numbers, return_index=True, return_inverse=True)
+        table = scat[first]
+        if np.array_equal(table[inv], scat):
+            return (np.ascontiguousarray(table, dtype=np.float64),
+                    np.ascontiguousarray(inv, dtype=np.int32))
+    table, inv = np.unique(scat, axis=0, return_inverse=True)
+    return (np.ascontiguousarray(table, dtype=np.float64),
+            np.ascontiguousarray(inv.reshape(-1), dtype=np.int32))
+
+
+class Backend(object):
+    """One native handle on one GPU for one precision."""
+    _instances = {}
+
+    @classmethod
+    def get(cls, precision='fp32', device=None, slot='fq'):
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', '0'))
+            try:
+                lib = _lib.load()
+                cnt = ctypes.c_int(0)
+                if lib.iid_device_count(ctypes.byref(cnt)) == 0 and cnt.value:
+                    device %= cnt.value
+            except _lib.IIDError:
+                raise
+        # one handle per Q grid in use ('fq' / 'pdf'), so that alternating
+        # get_fq / get_pdf calls do not re-upload the structure
+        key = (precision, int(device), slot)
+        inst = cls._instances.get(key)
+        if inst is None:
+            inst = cls(precision, int(device))
+            cls._instances[key] = inst
+        return inst
+
+    def __init__(self, precision='fp32', device=0):
+        if precision not in ('fp32', 'fp64'):
+            raise ValueError("precision must be 'fp32' or 'fp64'")
+        self.lib = _lib.load()
+        self.precision = precision
+        self.device = device
+        self.h = ctypes.c_void_p()
+        check(self.lib.iid_create(device, IID_FP32 if precision == 'fp32'
+                                  else IID_FP64, ctypes.byref(self.h)))
+        self.gdtype = np.float32 if precision == 'fp32' else np.float64
+        self._skey = None
+        self._tkey = None
+        self._target_key = None
+        self.n = self.nq = self.nr = 0
+        self.rank, self.world = 0, 1
+        self._tensors = {}
+        self._ext = None
+        self.sync_shard()
+
+    # -- sharding -----------------------------------------------------------
+    def sync_shard(self):
+        rank, world = _dist_state()
+        if (rank, world) != (self.rank, self.world):
+            check(self.lib.iid_set_shard(self.h, rank, world))
+            self.rank, self.world = rank, world
+
+    # -- cached state -------------------------------------------------------
+    def set_structure(self, scatter_array, numbers, qbin):
+        scat = np.asarray(scatter_array)
+        table, idx = element_table(scat, numbers)
+        key = (scat.shape, float(qbin), idx.tobytes(), table.tobytes())
+        if key == self._skey:
+            return
+        n, nq = scat.shape
+        check(self.lib.iid_set_structure(
+            self.h, n, idx.ctypes.data, table.shape[0], table.ctypes.data, nq,
+            float(qbin)))
+        if nq != self.nq:
+            self._tkey = None
+            self.nr = 0
+        self._skey = key
+        self._target_key = None
+        self.n, self.nq = n, nq
+        self._tensors = {}
+
+    def set_transform(self, rstep, qstep, rgrid, qmin):
+        rgrid = np.asarray(rgrid, dtype=np.float64)
+        key = (self.nq, float(rstep), float(qstep), float(qmin), rgrid.tobytes())
+        if key == self._tkey:
+            return
+        t = pdf_matrix(self.nq, rstep, qstep, rgrid, qmin)
+        check(self.lib.iid_set_transform(self.h, t.shape[0], t.shape[1],
+                                         t.ctypes.data))
+        self._tkey = key
+        self._target_key = None
+        self.nr = t.shape[0]
+        self._tensors = {}
+
+    @staticmethod
+    def _pos(positions):
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        if pos.ndim != 2 or pos.shape[1] != 3:
+            raise ValueError('positions must be [N, 3]')
+        return pos
+
+    # -- torch plumbing for world > 1 ----------------------------------------
+    def _t(self, name, shape, dtype):
+        import torch
+        t = self._tensors.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.zeros(shape, dtype=dtype, device='cuda:%d' % self.device)
+            self._tensors[name] = t
+        return t
+
+    def _stream(self):
+        """NULL = the handle's own stream (see _on_stream)."""
+        return None
+
+    def _on_stream(self):
+        """Context that makes the handle's stream torch's current stream, so
+        torch copies / NCCL collectives and our kernels are ordered on ONE
+        stream (torch's default stream 0 does not order with it)."""
+        import torch
+        if self._ext is None:
+            sp = ctypes.c_void_p()
+            check(self.lib.iid_get_stream(self.h, ctypes.byref(sp)))
+            self._ext = torch.cuda.ExternalStream(sp.value, device=self.device)
+        return torch.cuda.stream(self._ext)
+
+    def _upload(self, pos):
+        import torch
+        t = self._t('pos', (self.n, 3), torch.float64)
+        t.copy_(torch.from_numpy(pos))
+        return t
+
+    # -- the three bound callables + fused paths ------------------------------
+    def fq(self, positions):
+        """F(Q) [nq] float64 (flat_multi_cpu_wrap.wrap_fq :22-60)."""
+        pos = self._pos(positions)
+        self.sync_shard()
+        out = np.empty(self.nq, np.float64)
+        if self.world == 1:
+            check(self.lib.iid_fq_host(self.h, pos.ctypes.data, out.ctypes.data))
+            return out
+        import torch
+        import torch.distributed as dist
+        with torch.cuda.device(self.device), self._on_stream():
+            p = self._upload(pos)
+            s = self._t('S', (self.nq,), torch.float64)
+            f = self._t('F', (self.nq,), torch.float64)
+            st = self._stream()
+            check(self.lib.iid_fq_partial(self.h, p.data_ptr(), s.data_ptr(), st))
+            dist.all_reduce(s)
+            check(self.lib.iid_fq_finish(self.h, s.data_ptr(), f.data_ptr(), st))
+            return f.cpu().numpy()
+
+    def grad_fq(self, positions, with_fq=False):
+        """grad F(Q) [N,3,nq] in the kernel precision
+        (flat_multi_cpu_wrap.wrap_fq_grad :63-102)."""
+        pos = self._pos(positions)
+        self.sync_shard()
+        g = np.empty((self.n, 3, self.nq), self.gdtype)
+        f = np.empty(self.nq, np.float64)
+        if self.world == 1:
+            check(self.lib.iid_grad_fq_host(self.h, pos.ctypes.data, g.ctypes.data,
+                                            f.ctypes.data))
+            return (g, f) if with_fq else g
+        import torch
+        import torch.distributed as dist
+        tdt = torch.float32 if self.precision == 'fp32' else torch.float64
+        with torch.cuda.device(self.device), self._on_stream():
+            p = self._upload(pos)
+            gt = self._t('G', (self.n, 3, self.nq), tdt)
+            s = self._t('S', (self.nq,), torch.float64)
+            ft = self._t('F', (self.nq,), torch.float64)
+            st = self._stream()
+            check(self.lib.iid_grad_fq_partial(self.h, p.data_ptr(), gt.data_ptr(),
+                                               s.data_ptr(), st))
+            dist.all_reduce(s)
+            dist.all_reduce(gt)
+            check(self.lib.iid_fq_finish(self.h, s.data_ptr(), ft.data_ptr(), st))
+            g = gt.cpu().numpy()
+            f = ft.cpu().numpy()
+        return (g, f) if with_fq else g
+
+    def pdf(self, positions, with_fq=False):
+        """G(r) [nr] float64 = get_pdf_at_qmin(F(Q)) (master_kernel.py:39-104)."""
+        pos = self._pos(positions)
+        self.sync_shard()
+        if self.nr == 0:
+            raise _lib.IIDError('set_transform has not been called')
+        g = np.empty(self.nr, np.float64)
+        f = np.empty(self.nq, np.float64)
+        if self.world == 1:
+            check(self.lib.iid_pdf_host(self.h, pos.ctypes.data, g.ctypes.data,
+                                        f.ctypes.data))
+            return (g, f) if with_fq else g
+        import torch
+        import torch.distributed as dist
+        with torch.cuda.device(self.device), self._on_stream():
+            p = self._upload(pos)
+            s = self._t('S', (self.nq,), torch.float64)
+            ft = self._t('F', (self.nq,), torch.float64)
+            gr = self._t('Gr', (self.nr,), torch.float64)
+            st = self._stream()
+            check(self.lib.iid_fq_partial(self.h, p.data_ptr(), s.data_ptr(), st))
+            dist.all_reduce(s)
+            check(self.lib.iid_fq_finish(self.h, s.data_ptr(), ft.data_ptr(), st))
+            check(self.lib.iid_fq_to_gr(self.h, ft.data_ptr(), gr.data_ptr(), st))
+            g = gr.cpu().numpy()
+            f = ft.cpu().numpy()
+        return (g, f) if with_fq else g
+
+    def energy_forces(self, positions, target, potential='rw', conv=1.,
+                      want_forces=True, want_pdf=False):
+        """Fused Calc1D evaluation (calc/calc_1d.py:78-95 with
+        exp_function=get_pdf, exp_grad_function=get_grad_pdf): returns
+        (energy, scale, forces[N,3] or None, pdf or None) from ONE F(Q) pass
+        and ONE force pass, never forming the N x 3 x Q / N x 3 x R arrays."""
+        if potential not in POTENTIALS:
+            raise NotImplementedError('Potential not implemented')
+        pos = self._pos(positions)
+        self.sync_shard()
+        if self.nr == 0:
+            raise _lib.IIDError('set_transform has not been called')
+        target = np.ascontiguousarray(target, dtype=np.float64)
+        if target.shape != (self.nr,):
+            raise ValueError('target must have the r-grid length %d' % self.nr)
+        out = np.zeros(4, np.float64)
+        forces = np.empty((self.n, 3), np.float64) if want_forces else None
+        pdf = np.empty(self.nr, np.float64) if want_pdf else None
+        pot = POTENTIALS[potential]
+        if self.world == 1:
+            tkey = target.tobytes()
+            tptr = target.ctypes.data
+            if tkey == self._target_key:
+                tptr = None  # already resident on the device
+            check(self.lib.iid_energy_forces_host(
+                self.h, pos.ctypes.data, tptr, pot, float(conv), out.ctypes.data,
+                forces.ctypes.data if want_forces else None,
+                pdf.ctypes.data if want_pdf else None))
+            self._target_key = tkey
+            return out[0], out[1], forces, pdf
+        import torch
+        import torch.distributed as dist
+        with torch.cuda.device(self.device), self._on_stream():
+            p = self._upload(pos)
+            s = self._t('S', (self.nq,), torch.float64)
+            ft = self._t('F', (self.nq,), torch.float64)
+            gr = self._t('Gr', (self.nr,), torch.float64)
+            tg = self._t('target', (self.nr,), torch.float64)
+            o4 = self._t('out4', (4,), torch.float64)
+            wq = self._t('wq', (self.nq,), torch.float64)
+            fo = self._t('force', (self.n, 3), torch.float64)
+            tg.copy_(torch.from_numpy(target))
+            st = self._stream()
+            check(self.lib.iid_fq_partial(self.h, p.data_ptr(), s.data_ptr(), st))
+            dist.all_reduce(s)
+            check(self.lib.iid_fq_finish(self.h, s.data_ptr(), ft.data_ptr(), st))
+            check(self.lib.iid_fq_to_gr(self.h, ft.data_ptr(), gr.data_ptr(), st))
+            check(self.lib.iid_potential(self.h, gr.data_ptr(), tg.data_ptr(), pot,
+                                         float(conv), o4.data_ptr(),
+                                         wq.data_ptr() if want_forces else None, st))
+            if want_forces:
+                check(self.lib.iid_force_partial(self.h, p.data_ptr(), wq.data_ptr(),
+                                                 fo.data_ptr(), st))
+                dist.all_reduce(fo)
+                forces = fo.cpu().numpy()
+            out = o4.cpu().numpy()
+            if want_pdf:
+                pdf = gr.cpu().numpy()
+        return out[0], out[1], forces, pdf
+
+    def grad_pdf(self, grad_fq):
+        """[rows.., R] = grad_fq[rows.., Q] . T^T on the device
+        (master_kernel.grad_pdf :276-290)."""
+        import torch
+        if self.nr == 0:
+            raise _lib.IIDError('set_transform has not been called')
+        g = np.ascontiguousarray(grad_fq, dtype=self.gdtype)
+        if g.shape[-1] != self.nq:
+            raise ValueError('grad_fq last axis must be %d' % self.nq)
+        rows = int(np.prod(g.shape[:-1]))
+        with torch.cuda.device(self.device), self._on_stream():
+            gin = torch.from_numpy(g.reshape(rows, self.nq)).to('cuda:%d' % self.device)
+            out = torch.empty((rows, self.nr), dtype=torch.float64,
+                              device='cuda:%d' % self.device)
+            check(self.lib.iid_grad_pdf(self.h, gin.data_ptr(), rows, out.data_ptr(),
+                                        self._stream()))
+            res = out.cpu().numpy()
+        return res.reshape(g.shape[:-1] + (self.nr,))
+
+    def gr_from_fq(self, fq):
+        """G(r) = T F for a host F(Q) (get_pdf's noise branch)."""
+        if self.nr == 0:
+            raise _lib.IIDError('set_transform has not been called')
+        f = np.ascontiguousarray(fq, dtype=np.float64)
+        if f.shape != (self.nq,):
+            raise ValueError('F(Q) must have %d bins' % self.nq)
+        g = np.empty(self.nr, np.float64)
+        check(self.lib.iid_fq_to_gr_host(self.h, f.ctypes.data, g.ctypes.data))
+        return g
+
+    # -- instrumentation ------------------------------------------------------
+    def launch_count(self):
+        c = ctypes.c_int64(0)
+        check(self.lib.iid_launch_count(self.h, ctypes.byref(c)))
+        return c.value
+
+    def set_timing(self, on):
+        check(self.lib.iid_set_timing(self.h, int(bool(on))))
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_float(0)
+        pq = ctypes.c_double(0)
+        check(self.lib.iid_last_kernel_ms(self.h, ctypes.byref(ms), ctypes.byref(pq)))
+        return ms.value, pq.value
+
+    def sizes(self):
+        v = [ctypes.c_int64(0) for _ in range(5)]
+        check(self.lib.iid_get_sizes(self.h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(('n', 'nq', 'nr', 'items_fq', 'items_grad'),
+                        [x.value for x in v]))

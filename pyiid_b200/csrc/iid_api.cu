@@ -1,0 +1,822 @@
+// iid_api.cu -- C ABI (include/iid_b200.h) over the sm_100a kernels.
+// Host-side bookkeeping only: element sort + padding, work-item lists, the
+// closed-form normaliser, launch geometry, staging buffers.  No CPU compute
+// path exists behind any entry point.
+#include "../../include/iid_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "iid_debye.cuh"
+#include "iid_small.cuh"
+
+using namespace iid;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                              \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) {                                              \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);       \
+            return (int)e_;                                                   \
+        }                                                                     \
+    } while (0)
+
+#define NEED(h)                                                               \
+    do {                                                                      \
+        if (!(h)) return fail(IID_E_BADARG, "null handle");                   \
+        CU(cudaSetDevice((h)->device));                                       \
+    } while (0)
+
+template <typename X>
+static int dev_alloc(X **p, size_t count)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    CU(cudaMalloc((void **)p, count * sizeof(X)));
+    return 0;
+}
+
+struct iid_handle {
+    int device = 0;
+    int precision = IID_FP32;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    int rank = 0, world = 1;
+    // structure
+    int64_t n = 0, np = 0, nq = 0, qp = 0, ntypes = 0;
+    double qbin = 0.0;
+    double *x = nullptr, *y = nullptr, *z = nullptr;
+    float *valid = nullptr;
+    int *orig = nullptr, *tile_type = nullptr;
+    void *ftab = nullptr, *inv_na = nullptr;
+    double *inv_na_d = nullptr;
+    WorkItem *items_tri = nullptr, *items_sq = nullptr;
+    int64_t n_items_tri = 0, n_items_sq = 0;
+    // transform
+    int64_t nr = 0;
+    double *T = nullptr;
+    // scratch (device)
+    double *pos = nullptr, *S = nullptr, *F = nullptr, *Gr = nullptr,
+           *cr = nullptr, *wq = nullptr, *out4 = nullptr, *force = nullptr,
+           *target = nullptr;
+    void *Gfull = nullptr;
+    size_t Gfull_bytes = 0;
+    // pinned host staging
+    double *pin = nullptr;
+    size_t pin_count = 0;
+    // tunables
+    int nw_max = 8;
+    int slab_override = 0;
+    // instrumentation
+    int64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_pending = false;
+    double last_pairq = 0.0;
+};
+
+// ---------------------------------------------------------------------------
+extern "C" int iid_version(void) { return 100; }
+extern "C" const char *iid_last_error(void) { return g_err.c_str(); }
+
+extern "C" int iid_device_count(int *count)
+{
+    if (!count) return fail(IID_E_BADARG, "null count");
+    CU(cudaGetDeviceCount(count));
+    return 0;
+}
+
+extern "C" int iid_device_info(int device, int *sm_count, int *clock_khz, int *cc)
+{
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (clock_khz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+        *clock_khz = khz;
+    }
+    if (cc) *cc = prop.major * 10 + prop.minor;
+    return 0;
+}
+
+extern "C" int iid_create(int device, int precision, iid_handle **out)
+{
+    if (!out) return fail(IID_E_BADARG, "null out");
+    if (precision != IID_FP32 && precision != IID_FP64)
+        return fail(IID_E_BADARG, "precision must be IID_FP32 or IID_FP64");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(IID_E_NODEVICE, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= count) return fail(IID_E_BADARG, "bad device index");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(IID_E_NODEVICE,
+                    "device is not sm_100-class; kernels are built for sm_100a only");
+    iid_handle *h = new iid_handle();
+    h->device = device;
+    h->precision = precision;
+    h->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    CU(cudaMalloc((void **)&h->out4, 4 * sizeof(double)));
+    if (const char *s = getenv("IID_NW")) h->nw_max = std::max(1, std::min(12, atoi(s)));
+    h->nw_max = std::min(h->nw_max, 12);
+    if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
+    *out = h;
+    return 0;
+}
+
+extern "C" int iid_destroy(iid_handle *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
+                    h->inv_na, h->inv_na_d, h->items_tri, h->items_sq, h->T,
+                    h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
+                    h->target, h->Gfull};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int iid_get_stream(iid_handle *h, void **stream)
+{
+    if (!h || !stream) return fail(IID_E_BADARG, "null argument");
+    *stream = (void *)h->stream;
+    return 0;
+}
+
+extern "C" int iid_synchronize(iid_handle *h)
+{
+    NEED(h);
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int iid_set_shard(iid_handle *h, int rank, int world)
+{
+    if (!h) return fail(IID_E_BADARG, "null handle");
+    if (world < 1 || rank < 0 || rank >= world)
+        return fail(IID_E_BADARG, "need 0 <= rank < world");
+    h->rank = rank;
+    h->world = world;
+    return 0;
+}
+
+// Work items: (i-tile, j-slab) with one element type per slab.  Triangle
+// lists (F(Q), force) take the j tiles strictly below the i-tile plus one
+// diagonal item; square lists (full gradient) take every j.
+static void build_items(const std::vector<int> &run_begin,
+                        const std::vector<int> &run_end, int np, int slab,
+                        bool triangle, std::vector<WorkItem> &out)
+{
+    const int ntile = np / TILE_I;
+    out.clear();
+    for (int it = 0; it < ntile; ++it) {
+        const int jlimit = triangle ? it * TILE_I : np;
+        for (size_t b = 0; b < run_begin.size(); ++b) {
+            const int rb = run_begin[b], re = std::min(run_end[b], jlimit);
+            if (re <= rb) continue;
+            // equal slabs of at most `slab` atoms, multiples of 32
+            const int len = re - rb;
+            const int nsl = (len + slab - 1) / slab;
+            const int per = ((len + nsl - 1) / nsl + TILE_I - 1) / TILE_I * TILE_I;
+            for (int j0 = rb; j0 < re; j0 += per)
+                out.push_back({it, j0, std::min(re, j0 + per), (int)b});
+        }
+        if (triangle) {
+            // the i-tile against itself: both orders present, F counts 1/2
+            int b = 0;
+            for (size_t k = 0; k < run_begin.size(); ++k)
+                if (it * TILE_I >= run_begin[k] && it * TILE_I < run_end[k]) b = (int)k;
+            out.push_back({it, it * TILE_I, (it + 1) * TILE_I, b | ITEM_DIAG});
+        }
+    }
+    // longest first: the hardware block scheduler then fills the tail with
+    // short items
+    std::stable_sort(out.begin(), out.end(), [](const WorkItem &a, const WorkItem &b) {
+        return (a.jend - a.jbegin) > (b.jend - b.jbegin);
+    });
+}
+
+extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
+                                 int64_t n_types, const double *ftable, int64_t nq,
+                                 double qbin)
+{
+    NEED(h);
+    if (n < 1 || n_types < 1 || nq < 1 || !type_index || !ftable)
+        return fail(IID_E_BADARG, "bad structure arguments");
+    if (n_types > 65535) return fail(IID_E_BADARG, "more than 65535 element types");
+    if (n > (int64_t)1 << 30) return fail(IID_E_BADARG, "too many atoms");
+    CU(cudaStreamSynchronize(h->stream));
+    // element-sorted, per-element padded layout
+    std::vector<int64_t> count(n_types, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        if (type_index[i] < 0 || type_index[i] >= n_types)
+            return fail(IID_E_BADARG, "type_index out of range");
+        ++count[type_index[i]];
+    }
+    std::vector<int> run_begin, run_end, run_type;
+    int64_t np = 0;
+    std::vector<int64_t> start(n_types, 0);
+    for (int64_t e = 0; e < n_types; ++e) {
+        start[e] = np;
+        if (count[e] == 0) continue;
+        const int64_t padded = (count[e] + TILE_I - 1) / TILE_I * TILE_I;
+        run_begin.push_back((int)np);
+        run_end.push_back((int)(np + padded));
+        run_type.push_back((int)e);
+        np += padded;
+    }
+    std::vector<int> orig(np, -1), tile_type(np / TILE_I, 0);
+    {
+        std::vector<int64_t> fill(start);
+        for (int64_t i = 0; i < n; ++i) orig[fill[type_index[i]]++] = (int)i;
+        for (size_t b = 0; b < run_begin.size(); ++b)
+            for (int t = run_begin[b] / TILE_I; t < run_end[b] / TILE_I; ++t)
+                tile_type[t] = run_type[b];
+    }
+    const int64_t qp = (nq + 31) / 32 * 32;
+    // normaliser, closed form of N * mean_pairs(f_i f_j):
+    //   na = ((sum_i f_i)^2 - sum_i f_i^2) / (N - 1)
+    std::vector<double> inv_na(qp, 0.0);
+    for (int64_t m = 0; m < nq; ++m) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int64_t e = 0; e < n_types; ++e) {
+            const double f = ftable[e * nq + m];
+            s1 += (double)count[e] * f;
+            s2 += (double)count[e] * f * f;
+        }
+        const double na = n > 1 ? (s1 * s1 - s2) / (double)(n - 1) : 0.0;
+        inv_na[m] = (na != 0.0 && std::isfinite(na)) ? 1.0 / na : 0.0;
+    }
+    // the item info field stores the RUN's element type
+    std::vector<WorkItem> tri, sq;
+    {
+        // slab length: enough items to fill the machine ~12x over
+        const int64_t ntile = np / TILE_I;
+        const int64_t want = (int64_t)h->sm_count * 12;
+        auto pick = [&](int64_t total_j) {
+            int64_t s = total_j / std::max<int64_t>(1, want);
+            s = (s + TILE_I - 1) / TILE_I * TILE_I;
+            s = std::max<int64_t>(TILE_I, std::min<int64_t>(4096, s));
+            if (h->slab_override > 0) s = (h->slab_override + TILE_I - 1) / TILE_I * TILE_I;
+            return (int)s;
+        };
+        build_items(run_begin, run_end, (int)np, pick(ntile * np), false, sq);
+        build_items(run_begin, run_end, (int)np, pick(ntile * np / 2), true, tri);
+        for (auto *v : {&tri, &sq})
+            for (auto &w : *v) {
+                const int b = w.info & 0xffff;
+                w.info = (w.info & ITEM_DIAG) | run_type[b];
+            }
+    }
+    if (nq != h->nq) h->nr = 0;  // a transform built for another Q grid is void
+    h->n = n; h->np = np; h->nq = nq; h->qp = qp; h->ntypes = n_types; h->qbin = qbin;
+    int rc;
+    if ((rc = dev_alloc(&h->x, np)) || (rc = dev_alloc(&h->y, np)) ||
+        (rc = dev_alloc(&h->z, np)) || (rc = dev_alloc(&h->valid, np)) ||
+        (rc = dev_alloc(&h->orig, np)) || (rc = dev_alloc(&h->tile_type, np / TILE_I)) ||
+        (rc = dev_alloc(&h->inv_na_d, qp)) || (rc = dev_alloc(&h->items_tri, tri.size())) ||
+        (rc = dev_alloc(&h->items_sq, sq.size())) || (rc = dev_alloc(&h->pos, 3 * n)) ||
+        (rc = dev_alloc(&h->S, qp)) || (rc = dev_alloc(&h->F, qp)) ||
+        (rc = dev_alloc(&h->wq, qp)) || (rc = dev_alloc(&h->force, 3 * n)))
+        return rc;
+    h->n_items_tri = (int64_t)tri.size();
+    h->n_items_sq = (int64_t)sq.size();
+    CU(cudaMemcpy(h->orig, orig.data(), np * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->tile_type, tile_type.data(), tile_type.size() * sizeof(int),
+                  cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->inv_na_d, inv_na.data(), qp * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->items_tri, tri.data(), tri.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->items_sq, sq.data(), sq.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    CU(cudaMemset(h->S, 0, qp * sizeof(double)));
+    CU(cudaMemset(h->F, 0, qp * sizeof(double)));
+    CU(cudaMemset(h->wq, 0, qp * sizeof(double)));
+    const size_t esz = h->precision == IID_FP32 ? sizeof(float) : sizeof(double);
+    if (h->ftab) { cudaFree(h->ftab); h->ftab = nullptr; }
+    if (h->inv_na) { cudaFree(h->inv_na); h->inv_na = nullptr; }
+    CU(cudaMalloc(&h->ftab, (size_t)n_types * qp * esz));
+    CU(cudaMalloc(&h->inv_na, (size_t)qp * esz));
+    if (h->precision == IID_FP32) {
+        std::vector<float> ft((size_t)n_types * qp, 0.f), in(qp, 0.f);
+        for (int64_t e = 0; e < n_types; ++e)
+            for (int64_t m = 0; m < nq; ++m) ft[e * qp + m] = (float)ftable[e * nq + m];
+        for (int64_t m = 0; m < qp; ++m) in[m] = (float)inv_na[m];
+        CU(cudaMemcpy(h->ftab, ft.data(), ft.size() * esz, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->inv_na, in.data(), in.size() * esz, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<double> ft((size_t)n_types * qp, 0.0);
+        for (int64_t e = 0; e < n_types; ++e)
+            for (int64_t m = 0; m < nq; ++m) ft[e * qp + m] = ftable[e * nq + m];
+        CU(cudaMemcpy(h->ftab, ft.data(), ft.size() * esz, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->inv_na, inv_na.data(), qp * esz, cudaMemcpyHostToDevice));
+    }
+    // pinned staging: positions / forces (3n), F (qp), G(r) (nr, grown later), 4
+    const size_t need = (size_t)6 * n + 2 * qp + 8 + 2 * (size_t)h->nr;
+    if (need > h->pin_count) {
+        if (h->pin) cudaFreeHost(h->pin);
+        h->pin = nullptr;
+        CU(cudaMallocHost((void **)&h->pin, need * sizeof(double)));
+        h->pin_count = need;
+    }
+    return 0;
+}
+
+extern "C" int iid_set_transform(iid_handle *h, int64_t nr, int64_t nq, const double *T)
+{
+    NEED(h);
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (nq != h->nq) return fail(IID_E_BADARG, "transform nq differs from structure nq");
+    if (nr < 1 || !T) return fail(IID_E_BADARG, "bad transform arguments");
+    CU(cudaStreamSynchronize(h->stream));
+    int rc;
+    if ((rc = dev_alloc(&h->T, (size_t)nr * h->qp)) || (rc = dev_alloc(&h->Gr, nr)) ||
+        (rc = dev_alloc(&h->cr, nr)) || (rc = dev_alloc(&h->target, nr)))
+        return rc;
+    CU(cudaMemset(h->T, 0, (size_t)nr * h->qp * sizeof(double)));
+    CU(cudaMemcpy2D(h->T, h->qp * sizeof(double), T, nq * sizeof(double),
+                    nq * sizeof(double), nr, cudaMemcpyHostToDevice));
+    h->nr = nr;
+    const size_t need = (size_t)6 * h->n + 2 * h->qp + 8 + 2 * (size_t)nr;
+    if (need > h->pin_count) {
+        if (h->pin) cudaFreeHost(h->pin);
+        h->pin = nullptr;
+        CU(cudaMallocHost((void **)&h->pin, need * sizeof(double)));
+        h->pin_count = need;
+    }
+    return 0;
+}
+
+extern "C" int iid_get_sizes(iid_handle *h, int64_t *n, int64_t *nq, int64_t *nr,
+                             int64_t *n_items_fq, int64_t *n_items_grad)
+{
+    if (!h) return fail(IID_E_BADARG, "null handle");
+    if (n) *n = h->n;
+    if (nq) *nq = h->nq;
+    if (nr) *nr = h->nr;
+    if (n_items_fq) *n_items_fq = h->n_items_tri;
+    if (n_items_grad) *n_items_grad = h->n_items_sq;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+static int stage_positions(iid_handle *h, const double *pos_dev, cudaStream_t st)
+{
+    const int np = (int)h->np;
+    prep_kernel<<<(np + 255) / 256, 256, 0, st>>>(pos_dev, h->orig, np,
+                                                  h->precision == IID_FP32, h->x, h->y,
+                                                  h->z, h->valid);
+    ++h->launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int C, int MODE>
+static int launch_debye_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
+                          cudaStream_t st)
+{
+    // warps per block = Q chunks per block.  Up to 8 warps a thread may use
+    // 255 registers (one block per SM); 9..12 warps compile to <= 168.
+    const int nchunk = (int)((h->nq + C - 1) / C);
+    const int gy = (nchunk + h->nw_max - 1) / h->nw_max;
+    const int nw = (nchunk + gy - 1) / gy;
+    dim3 grid((unsigned)nblocks, (unsigned)gy, 1), block(32 * nw, 1, 1);
+    if (h->timing) CU(cudaEventRecord(h->ev0, st));
+    if (nw <= 8)
+        debye_kernel<T, C, MODE, 256><<<grid, block, 0, st>>>(p);
+    else
+        debye_kernel<T, C, MODE, 384><<<grid, block, 0, st>>>(p);
+    ++h->launches;
+    CU(cudaGetLastError());
+    if (h->timing) {
+        CU(cudaEventRecord(h->ev1, st));
+        h->ev_pending = true;
+    }
+    return 0;
+}
+
+constexpr int C32 = 32;  // Q bins per warp, float32 kernels
+constexpr int C64 = 16;  // Q bins per warp, float64 kernels
+
+static int launch_debye(iid_handle *h, int mode, void *G, double *S, const double *wq,
+                        double *force, cudaStream_t st)
+{
+    DebyeParams p;
+    p.x = h->x; p.y = h->y; p.z = h->z; p.valid = h->valid; p.orig = h->orig;
+    p.tile_type = h->tile_type;
+    const bool square = mode == MODE_GRAD;
+    p.items = square ? h->items_sq : h->items_tri;
+    const int64_t nitems = square ? h->n_items_sq : h->n_items_tri;
+    p.item_begin = h->rank;
+    p.item_stride = h->world;
+    p.ftab = h->ftab; p.inv_na = h->inv_na; p.wq = wq;
+    p.nq = (int)h->nq; p.qp = (int)h->qp;
+    p.qbin = h->qbin;
+    p.qbin_turns = h->qbin / 6.283185307179586476925286766559;
+    p.G = G; p.S = S; p.force = force;
+    const int64_t mine = nitems > h->rank ? (nitems - h->rank + h->world - 1) / h->world : 0;
+    h->last_pairq = 0.5 * (double)h->n * (double)(h->n - 1) * (double)h->nq / h->world;
+    if (mine == 0) return 0;
+    if (h->precision == IID_FP32) {
+        if (mode == MODE_FQ) return launch_debye_t<float, C32, MODE_FQ>(h, p, mine, st);
+        if (mode == MODE_GRAD) return launch_debye_t<float, C32, MODE_GRAD>(h, p, mine, st);
+        return launch_debye_t<float, C32, MODE_FORCE>(h, p, mine, st);
+    }
+    if (mode == MODE_FQ) return launch_debye_t<double, C64, MODE_FQ>(h, p, mine, st);
+    if (mode == MODE_GRAD) return launch_debye_t<double, C64, MODE_GRAD>(h, p, mine, st);
+    return launch_debye_t<double, C64, MODE_FORCE>(h, p, mine, st);
+}
+
+static cudaStream_t pick(iid_handle *h, void *stream)
+{
+    return stream ? (cudaStream_t)stream : h->stream;
+}
+
+extern "C" int iid_fq_partial(iid_handle *h, const double *pos_dev, double *S_dev, void *stream)
+{
+    NEED(h);
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (!pos_dev || !S_dev) return fail(IID_E_BADARG, "null pointer");
+    cudaStream_t st = pick(h, stream);
+    int rc = stage_positions(h, pos_dev, st);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(S_dev, 0, h->nq * sizeof(double), st));
+    return launch_debye(h, MODE_FQ, nullptr, S_dev, nullptr, nullptr, st);
+}
+
+extern "C" int iid_fq_finish(iid_handle *h, const double *S_dev, double *F_dev, void *stream)
+{
+    NEED(h);
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (!S_dev || !F_dev) return fail(IID_E_BADARG, "null pointer");
+    cudaStream_t st = pick(h, stream);
+    finish_fq_kernel<<<(int)(h->nq + 127) / 128, 128, 0, st>>>(S_dev, h->inv_na_d, (int)h->nq, 0, F_dev);
+    ++h->launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iid_grad_fq_partial(iid_handle *h, const double *pos_dev, void *G_dev,
+                                   double *S_dev, void *stream)
+{
+    NEED(h);
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (!pos_dev || !G_dev) return fail(IID_E_BADARG, "null pointer");
+    cudaStream_t st = pick(h, stream);
+    int rc = stage_positions(h, pos_dev, st);
+    if (rc) return rc;
+    const size_t esz = h->precision == IID_FP32 ? sizeof(float) : sizeof(double);
+    CU(cudaMemsetAsync(G_dev, 0, (size_t)h->n * 3 * h->nq * esz, st));
+    if (S_dev) CU(cudaMemsetAsync(S_dev, 0, h->nq * sizeof(double), st));
+    return launch_debye(h, MODE_GRAD, G_dev, S_dev, nullptr, nullptr, st);
+}
+
+extern "C" int iid_force_partial(iid_handle *h, const double *pos_dev, const double *wq_dev,
+                                 double *force_dev, void *stream)
+{
+    NEED(h);
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (!pos_dev || !wq_dev || !force_dev) return fail(IID_E_BADARG, "null pointer");
+    cudaStream_t st = pick(h, stream);
+    int rc = stage_positions(h, pos_dev, st);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(force_dev, 0, (size_t)h->n * 3 * sizeof(double), st));
+    return launch_debye(h, MODE_FORCE, nullptr, nullptr, wq_dev, force_dev, st);
+}
+
+extern "C" int iid_fq_to_gr(iid_handle *h, const double *F_dev, double *G_dev, void *stream)
+{
+    NEED(h);
+    if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
+    if (!F_dev || !G_dev) return fail(IID_E_BADARG, "null pointer");
+    cudaStream_t st = pick(h, stream);
+    const int64_t threads = h->nr * 32;
+    gr_kernel<double><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(h->T, F_dev, h->nr,
+                                                                 (int)h->nq, (int)h->qp, G_dev);
+    ++h->launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iid_potential(iid_handle *h, const double *G_dev, const double *target_dev,
+                             int potential, double conv, double *out_dev, double *wq_dev,
+                             void *stream)
+{
+    NEED(h);
+    if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
+    if (!G_dev || !target_dev || !out_dev) return fail(IID_E_BADARG, "null pointer");
+    if (potential != IID_POT_RW && potential != IID_POT_CHI_SQ)
+        return fail(IID_E_BADARG, "unknown potential");
+    cudaStream_t st = pick(h, stream);
+    potential_kernel<<<1, 1024, 0, st>>>(G_dev, target_dev, (int)h->nr, potential, conv,
+                                         out_dev, h->cr);
+    ++h->launches;
+    CU(cudaGetLastError());
+    if (wq_dev) {
+        CU(cudaMemsetAsync(wq_dev, 0, h->nq * sizeof(double), st));
+        wq_kernel<<<(unsigned)((h->nr + WQ_ROWS - 1) / WQ_ROWS), 128, 0, st>>>(
+            h->T, h->cr, (int)h->nr, (int)h->nq, (int)h->qp, conv, wq_dev);
+        ++h->launches;
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int iid_grad_pdf(iid_handle *h, const void *grad_fq_dev, int64_t rows,
+                            double *grad_pdf_dev, void *stream)
+{
+    NEED(h);
+    if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
+    if (!grad_fq_dev || !grad_pdf_dev || rows < 0) return fail(IID_E_BADARG, "bad argument");
+    if (rows == 0) return 0;
+    cudaStream_t st = pick(h, stream);
+    dim3 grid((unsigned)((h->nr + GP_BN - 1) / GP_BN), (unsigned)((rows + GP_BM - 1) / GP_BM));
+    if (h->precision == IID_FP32)
+        grad_pdf_kernel<float><<<grid, 256, 0, st>>>((const float *)grad_fq_dev, h->T, rows,
+                                                     (int)h->nq, (int)h->qp, (int)h->nr,
+                                                     grad_pdf_dev);
+    else
+        grad_pdf_kernel<double><<<grid, 256, 0, st>>>((const double *)grad_fq_dev, h->T, rows,
+                                                      (int)h->nq, (int)h->qp, (int)h->nr,
+                                                      grad_pdf_dev);
+    ++h->launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// --- host-buffer entry points ------------------------------------------------
+// pinned layout: [0,3n) positions in, [3n,6n) forces out, then F (qp), out4 (8),
+// G(r) (nr), target (nr)
+static int upload_positions(iid_handle *h, const double *pos_host)
+{
+    memcpy(h->pin, pos_host, (size_t)3 * h->n * sizeof(double));
+    CU(cudaMemcpyAsync(h->pos, h->pin, (size_t)3 * h->n * sizeof(double),
+                       cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+extern "C" int iid_fq_host(iid_handle *h, const double *pos_host, double *F_host)
+{
+    NEED(h);
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (!pos_host || !F_host) return fail(IID_E_BADARG, "null pointer");
+    int rc;
+    if ((rc = upload_positions(h, pos_host))) return rc;
+    if ((rc = iid_fq_partial(h, h->pos, h->S, nullptr))) return rc;
+    if ((rc = iid_fq_finish(h, h->S, h->F, nullptr))) return rc;
+    double *pf = h->pin + 6 * h->n;
+    CU(cudaMemcpyAsync(pf, h->F, h->nq * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    memcpy(F_host, pf, h->nq * sizeof(double));
+    return 0;
+}
+
+extern "C" int iid_grad_fq_host(iid_handle *h, const double *pos_host, void *G_host,
+                                double *F_host)
+{
+    NEED(h);
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (!pos_host || !G_host) return fail(IID_E_BADARG, "null pointer");
+    const size_t esz = h->precision == IID_FP32 ? sizeof(float) : sizeof(double);
+    const size_t bytes = (size_t)h->n * 3 * h->nq * esz;
+    if (bytes > h->Gfull_bytes) {
+        if (h->Gfull) cudaFree(h->Gfull);
+        h->Gfull = nullptr;
+        h->Gfull_bytes = 0;
+        CU(cudaMalloc(&h->Gfull, bytes));
+        h->Gfull_bytes = bytes;
+    }
+    int rc;
+    if ((rc = upload_positions(h, pos_host))) return rc;
+    if ((rc = iid_grad_fq_partial(h, h->pos, h->Gfull, h->S, nullptr))) return rc;
+    if ((rc = iid_fq_finish(h, h->S, h->F, nullptr))) return rc;
+    double *pf = h->pin + 6 * h->n;
+    CU(cudaMemcpyAsync(pf, h->F, h->nq * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(G_host, h->Gfull, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (F_host) memcpy(F_host, pf, h->nq * sizeof(double));
+    return 0;
+}
+
+extern "C" int iid_pdf_host(iid_handle *h, const double *pos_host, double *pdf_host,
+                            double *F_host)
+{
+    NEED(h);
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
+    if (!pos_host || !pdf_host) return fail(IID_E_BADARG, "null pointer");
+    int rc;
+    if ((rc = upload_positions(h, pos_host))) return rc;
+    if ((rc = iid_fq_partial(h, h->pos, h->S, nullptr))) return rc;
+    if ((rc = iid_fq_finish(h, h->S, h->F, nullptr))) return rc;
+    if ((rc = iid_fq_to_gr(h, h->F, h->Gr, nullptr))) return rc;
+    double *pf = h->pin + 6 * h->n;
+    double *pg = pf + h->qp + 8;
+    CU(cudaMemcpyAsync(pf, h->F, h->nq * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(pg, h->Gr, h->nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    memcpy(pdf_host, pg, h->nr * sizeof(double));
+    if (F_host) memcpy(F_host, pf, h->nq * sizeof(double));
+    return 0;
+}
+
+extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
+                                      const double *target_host, int potential, double conv,
+                                      double *out_host, double *forces_host, double *pdf_host)
+{
+    NEED(h);
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
+    if (!pos_host || !out_host) return fail(IID_E_BADARG, "null pointer");
+    if (h->world != 1)
+        return fail(IID_E_BADARG, "iid_energy_forces_host needs the whole pair list (world == 1)");
+    int rc;
+    double *pfor = h->pin + 3 * h->n;
+    double *pf = h->pin + 6 * h->n;
+    double *po = pf + h->qp;
+    double *pg = po + 8;
+    double *pt = pg + h->nr;
+    if (target_host) {
+        memcpy(pt, target_host, h->nr * sizeof(double));
+        CU(cudaMemcpyAsync(h->target, pt, h->nr * sizeof(double), cudaMemcpyHostToDevice,
+                           h->stream));
+    }
+    if ((rc = upload_positions(h, pos_host))) return rc;
+    if ((rc = iid_fq_partial(h, h->pos, h->S, nullptr))) return rc;
+    if ((rc = iid_fq_finish(h, h->S, h->F, nullptr))) return rc;
+    if ((rc = iid_fq_to_gr(h, h->F, h->Gr, nullptr))) return rc;
+    if ((rc = iid_potential(h, h->Gr, h->target, potential, conv, h->out4,
+                            forces_host ? h->wq : nullptr, nullptr)))
+        return rc;
+    if (forces_host) {
+        // positions are already staged by iid_fq_partial; enqueue the force pass
+        CU(cudaMemsetAsync(h->force, 0, (size_t)h->n * 3 * sizeof(double), h->stream));
+        if ((rc = launch_debye(h, MODE_FORCE, nullptr, nullptr, h->wq, h->force, h->stream)))
+            return rc;
+        CU(cudaMemcpyAsync(pfor, h->force, (size_t)3 * h->n * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaMemcpyAsync(po, h->out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (pdf_host)
+        CU(cudaMemcpyAsync(pg, h->Gr, h->nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    memcpy(out_host, po, 4 * sizeof(double));
+    if (forces_host) memcpy(forces_host, pfor, (size_t)3 * h->n * sizeof(double));
+    if (pdf_host) memcpy(pdf_host, pg, h->nr * sizeof(double));
+    return 0;
+}
+
+// Rw / chi^2 of two host vectors and the chain-rule vector c (calc/__init__.py
+// wrap_rw / wrap_chi_sq :10-54 and the c of wrap_grad_* :56-105).
+extern "C" int iid_rw_host(iid_handle *h, const double *gcalc_host, const double *gobs_host,
+                           int64_t len, int potential, double conv, double *out_host,
+                           double *c_host)
+{
+    NEED(h);
+    if (!gcalc_host || !gobs_host || !out_host || len < 1)
+        return fail(IID_E_BADARG, "bad argument");
+    if (potential != IID_POT_RW && potential != IID_POT_CHI_SQ)
+        return fail(IID_E_BADARG, "unknown potential");
+    double *buf = nullptr;
+    CU(cudaMalloc((void **)&buf, (3 * len + 4) * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(buf, gcalc_host, len * sizeof(double),
+                                    cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(buf + len, gobs_host, len * sizeof(double),
+                            cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        potential_kernel<<<1, 1024, 0, h->stream>>>(buf, buf + len, (int)len, potential, conv,
+                                                    buf + 3 * len, buf + 2 * len);
+        ++h->launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(out_host, buf + 3 * len, 4 * sizeof(double),
+                            cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && c_host)
+        e = cudaMemcpyAsync(c_host, buf + 2 * len, len * sizeof(double),
+                            cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(buf);
+    if (e != cudaSuccess) {
+        g_err = std::string("iid_rw_host: ") + cudaGetErrorString(e);
+        return (int)e;
+    }
+    return 0;
+}
+
+// out[row] = sum_k A[row][k] c[k]: the contraction of wrap_grad_rw /
+// wrap_grad_chi_sq (master_kernel.py:334-347, 367-375) over a host array.
+extern "C" int iid_contract_host(iid_handle *h, const void *A_host, int a_is_f32,
+                                 int64_t rows, int64_t len, const double *c_host,
+                                 double *out_host)
+{
+    NEED(h);
+    if (!A_host || !c_host || !out_host || rows < 0 || len < 1)
+        return fail(IID_E_BADARG, "bad argument");
+    if (rows == 0) return 0;
+    const size_t esz = a_is_f32 ? sizeof(float) : sizeof(double);
+    void *A = nullptr;
+    double *cv = nullptr;
+    CU(cudaMalloc(&A, (size_t)rows * len * esz));
+    cudaError_t e = cudaMalloc((void **)&cv, (len + rows) * sizeof(double));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(A, A_host, (size_t)rows * len * esz, cudaMemcpyHostToDevice,
+                            h->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(cv, c_host, len * sizeof(double), cudaMemcpyHostToDevice,
+                            h->stream);
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((rows * 32 + 255) / 256);
+        if (a_is_f32)
+            gr_kernel<float><<<blocks, 256, 0, h->stream>>>((const float *)A, cv, rows, (int)len,
+                                                            (int)len, cv + len);
+        else
+            gr_kernel<double><<<blocks, 256, 0, h->stream>>>((const double *)A, cv, rows,
+                                                             (int)len, (int)len, cv + len);
+        ++h->launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(out_host, cv + len, rows * sizeof(double), cudaMemcpyDeviceToHost,
+                            h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(A);
+    if (cv) cudaFree(cv);
+    if (e != cudaSuccess) {
+        g_err = std::string("iid_contract_host: ") + cudaGetErrorString(e);
+        return (int)e;
+    }
+    return 0;
+}
+
+// G(r) from a host F(Q) (used when noise is added to F(Q) on the host,
+// elasticscatter/__init__.py:371-390)
+extern "C" int iid_fq_to_gr_host(iid_handle *h, const double *F_host, double *pdf_host)
+{
+    NEED(h);
+    if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
+    if (!F_host || !pdf_host) return fail(IID_E_BADARG, "null pointer");
+    double *pf = h->pin + 6 * h->n;
+    double *pg = pf + h->qp + 8;
+    memcpy(pf, F_host, h->nq * sizeof(double));
+    CU(cudaMemcpyAsync(h->F, pf, h->nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int rc = iid_fq_to_gr(h, h->F, h->Gr, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(pg, h->Gr, h->nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    memcpy(pdf_host, pg, h->nr * sizeof(double));
+    return 0;
+}
+
+// --- instrumentation -----------------------------------------------------------
+extern "C" int iid_launch_count(iid_handle *h, int64_t *count)
+{
+    if (!h || !count) return fail(IID_E_BADARG, "null argument");
+    *count = h->launches;
+    return 0;
+}
+
+extern "C" int iid_set_timing(iid_handle *h, int enabled)
+{
+    if (!h) return fail(IID_E_BADARG, "null handle");
+    h->timing = enabled != 0;
+    return 0;
+}
+
+extern "C" int iid_last_kernel_ms(iid_handle *h, float *ms, double *pairq)
+{
+    NEED(h);
+    if (!ms) return fail(IID_E_BADARG, "null argument");
+    *ms = 0.f;
+    if (h->ev_pending) {
+        CU(cudaEventSynchronize(h->ev1));
+        CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    }
+    if (pairq) *pairq = h->last_pairq;
+    return 0;
+}

@@ -1,0 +1,335 @@
+"""``ElasticScatter`` on the B200 processor.
+
+Mirror of the reference class
+``pyiid.experiments.elasticscatter.ElasticScatter``
+(``pyiid/experiments/elasticscatter/__init__.py:52-558``): same constructor,
+experiment dictionary and defaults, ``set_processor`` / ``update_experiment``,
+scatter-factor caching on the ``Atoms`` object and the same public methods
+(``get_fq``, ``get_pdf``, ``get_sq``, ``get_iq``, ``get_2d_scatter``,
+``get_grad_fq``, ``get_grad_pdf``, ``get_scatter_vector``, ``get_r``).
+
+What differs, deliberately (SURVEY.md section 8a notes):
+
+* there is one processor, the B200 CUDA path; ``set_processor('CPU', ...)``
+  raises -- no CPU fallback and no multi-backend dispatch;
+* the normaliser ``na`` is the float64 closed form, not the reference's naive
+  float32 ``np.mean`` over K rows (``cpu_wrappers/flat_multi_cpu_wrap.py:54``);
+* ``_wrap_atoms`` builds one form-factor row per unique element on the right
+  Q grid (the reference indexes the element table with the first atoms' Z and
+  samples the PDF table on the F(Q) grid, ``__init__.py:127-148`` -- both
+  no-ops for single-element structures);
+* the gradient keeps the reference's convention (= -1/2 dF/dq): forces and
+  sampler dynamics depend on it.
+"""
+import math
+
+import numpy as np
+
+from . import formfactors
+from .backend import Backend
+
+__all__ = ['ElasticScatter', 'wrap_atoms']
+
+PROCESSORS = ['B200', 'Multi-GPU', 'MPI-GPU']
+
+
+def _interp_std(iq_std, n):
+    iq_std = np.asarray(iq_std, dtype=float)
+    if iq_std.ndim == 0 or iq_std.shape == (n,):
+        return iq_std
+    return np.interp(np.linspace(0, len(iq_std) - 1, n),
+                     np.arange(len(iq_std)), iq_std)
+
+
+class ElasticScatter(object):
+    """Theoretical powder scattering F(Q), PDF and their gradients from an
+    atomic configuration, computed on a B200 (reference ``__init__.py:52``)."""
+
+    def __init__(self, exp_dict=None, verbose=False, seed=None,
+                 precision='fp32', device=None):
+        self.verbose = verbose
+        self.wrap_atoms_state = None
+        if seed is None:
+            self.seed = int(np.random.random() * 2 ** 32)
+        elif isinstance(seed, (int, np.integer)):
+            self.seed = int(seed)
+        else:
+            raise ValueError('Expected an integer!')
+        self.rs = np.random.RandomState(self.seed)
+        self.avail_pro = list(PROCESSORS)
+        self.exp_dict_keys = ['qmin', 'qmax', 'qbin', 'rmin', 'rmax', 'rstep',
+                              'sampling']
+        self.default_values = [0.0, 25, .1, 0.0, 40.0, .01, 'full']
+        self.alg = None
+        self.processor = None
+        self.exp = None
+        self.pdf_qbin = None
+        self.precision = precision
+        self.device = device
+        self._backends = {}
+        self.update_experiment(exp_dict)
+        self.fq = self._wrap_fq
+        self.grad = self._wrap_fq_grad
+        self.grad_pdf = self._grad_pdf
+        self.set_processor()
+
+    # The native handle is shared, never copied: leapfrog deep-copies the
+    # atoms, their calculator and through it this object on every step
+    # (pyiid/sim/__init__.py:29).
+    def __deepcopy__(self, memo):
+        memo[id(self)] = self
+        return self
+
+    def __copy__(self):
+        return self
+
+    # -- processor ----------------------------------------------------------
+    def _be(self, slot):
+        be = self._backends.get(slot)
+        if be is None:
+            be = Backend.get(self.precision, self.device, slot)
+            self._backends[slot] = be
+        return be
+
+    @property
+    def backend(self):
+        """The handle of the F(Q) grid (``pdf_backend`` for the PDF grid)."""
+        return self._be('fq')
+
+    @property
+    def pdf_backend(self):
+        return self._be('pdf')
+
+    def set_processor(self, processor=None, kernel_type='flat'):
+        """Bind ``self.fq``, ``self.grad``, ``self.grad_pdf`` (reference
+        ``__init__.py:206-292``).  Every GPU processor name maps onto the
+        B200 path; ``'CPU'`` is refused."""
+        if processor is not None and processor not in self.avail_pro:
+            if processor in ('CPU', 'Serial-CPU'):
+                raise NotImplementedError(
+                    'pyiid_b200 has no CPU processor: the elastic-scattering '
+                    'path runs on sm_100a CUDA only')
+            return None
+        self.fq = self._wrap_fq
+        self.grad = self._wrap_fq_grad
+        self.grad_pdf = self._grad_pdf
+        self.processor = 'B200'
+        self.alg = 'flat'
+        return True
+
+    def set_precision(self, precision):
+        if precision not in ('fp32', 'fp64'):
+            raise ValueError("precision must be 'fp32' or 'fp64'")
+        self.precision = precision
+        self._backends = {}
+
+    # -- experiment ---------------------------------------------------------
+    def update_experiment(self, exp_dict):
+        """Reference ``__init__.py:180-204``."""
+        if exp_dict is None or bool(exp_dict) is False:
+            exp_dict = {}
+        for key, dv in zip(self.exp_dict_keys, self.default_values):
+            if key not in exp_dict.keys():
+                exp_dict[key] = dv
+        if exp_dict['sampling'] == 'ns':
+            exp_dict['rstep'] = np.pi / exp_dict['qmax']
+        self.exp = exp_dict
+        self.pdf_qbin = np.pi / (self.exp['rmax'] + 6 * 2 * np.pi /
+                                 self.exp['qmax'])
+
+    def _wrap_atoms(self, atoms):
+        """Attach the per-atom scatter-factor arrays ``'F(Q) scatter'`` and
+        ``'PDF scatter'`` (float32 [N, Qbins]) and the cache keys
+        ``info['exp']``, ``info['scatter_atoms']`` (reference
+        ``__init__.py:110-151``)."""
+        if 'qbin' not in self.exp.keys():
+            self.exp['qbin'] = .1
+        n = len(atoms)
+        numbers = np.asarray(atoms.get_atomic_numbers())
+        zs, inv = np.unique(numbers, return_inverse=True)
+        for qbin, name in zip([self.exp['qbin'], self.pdf_qbin],
+                              ['F(Q) scatter', 'PDF scatter']):
+            qmax_bin = int(math.floor(self.exp['qmax'] / qbin))
+            table = np.zeros((len(zs), qmax_bin), dtype=np.float32)
+            formfactors.get_scatter_array(table, zs, qbin)
+            scatter_array = table[inv.reshape(-1)] if n else \
+                np.zeros((0, qmax_bin), np.float32)
+            if name in atoms.arrays.keys():
+                del atoms.arrays[name]
+            atoms.set_array(name, scatter_array)
+        atoms.info['exp'] = self.exp
+        atoms.info['scatter_atoms'] = n
+
+    def check_wrap_atoms_state(self, atoms):
+        """Reference ``__init__.py:294-302``."""
+        if self.wrap_atoms_state is None:
+            return False
+        if 'F(Q) scatter' not in atoms.arrays.keys():
+            return False
+        if atoms.info.get('exp') != self.exp or \
+                atoms.info.get('scatter_atoms') != len(atoms):
+            return False
+        return True
+
+    def _check_wrap_atoms_state(self, atoms):
+        """Reference ``__init__.py:153-178``: check, and re-wrap on a miss."""
+        t_value = self.check_wrap_atoms_state(atoms)
+        if not t_value:
+            if self.verbose:
+                print('calculating new scatter factors')
+            self._wrap_atoms(atoms)
+            self.wrap_atoms_state = True
+        return t_value
+
+    def _ensure_wrapped(self, atoms):
+        if self.check_wrap_atoms_state(atoms) is False:
+            if self.verbose:
+                print('calculating new scatter factors')
+            self._wrap_atoms(atoms)
+            self.wrap_atoms_state = True
+
+    # -- the three callables set_processor binds ------------------------------
+    def _load(self, atoms, qbin, sum_type):
+        name = 'F(Q) scatter' if sum_type == 'fq' else 'PDF scatter'
+        scat = atoms.get_array(name, copy=False) if hasattr(atoms, 'arrays') \
+            else atoms.get_array(name)
+        be = self._be('fq' if sum_type == 'fq' else 'pdf')
+        be.set_structure(scat, atoms.numbers, qbin)
+        return be
+
+    def _wrap_fq(self, atoms, qbin=.1, sum_type='fq'):
+        """``wrap_fq(atoms, qbin, sum_type) -> float32 [Qbins]``
+        (``cpu_wrappers/flat_multi_cpu_wrap.py:22-60``)."""
+        be = self._load(atoms, qbin, sum_type)
+        out = be.fq(atoms.get_positions())
+        return out.astype(np.float32) if self.precision == 'fp32' else out
+
+    def _wrap_fq_grad(self, atoms, qbin=.1, sum_type='fq'):
+        """``wrap_fq_grad(atoms, qbin, sum_type) -> [N, 3, Qbins]``
+        (``flat_multi_cpu_wrap.py:63-102``)."""
+        be = self._load(atoms, qbin, sum_type)
+        if len(atoms) < 2:
+            return np.zeros((len(atoms), 3, be.nq), be.gdtype)
+        return be.grad_fq(atoms.get_positions())
+
+    def _grad_pdf(self, grad_fq, rstep, qstep, rgrid, qmin):
+        """``grad_pdf(grad_fq, rstep, qstep, rgrid, qmin) -> float64
+        [N, 3, len(rgrid)]`` (``kernels/master_kernel.py:276-290``)."""
+        be = self.pdf_backend
+        if grad_fq.shape[-1] != be.nq:
+            raise ValueError('grad_fq does not match the loaded PDF-grid '
+                             'structure (%d bins)' % be.nq)
+        be.set_transform(rstep, qstep, rgrid, qmin)
+        return be.grad_pdf(grad_fq)
+
+    # -- public API -----------------------------------------------------------
+    def get_fq(self, atoms, iq_std=None, noise_distribution=None):
+        """Reduced structure function F(Q) (reference ``__init__.py:304-341``)."""
+        self._ensure_wrapped(atoms)
+        fq = self.fq(atoms, self.exp['qbin'])
+        lo = int(np.floor(self.exp['qmin'] / self.exp['qbin']))
+        fq = fq[lo:]
+        if iq_std is not None:
+            fq_std = iq_std * np.abs(self.get_scatter_vector()) / np.abs(
+                np.average(atoms.get_array('F(Q) scatter'), axis=0) ** 2)[lo:]
+            if fq_std[0] == 0.0:
+                fq_std[0] += 1e-9
+            fq = fq + self.rs.normal(0, fq_std)
+        return fq
+
+    def get_pdf(self, atoms, iq_std=None, noise_distribution=np.random.normal):
+        """Atomic pair distribution function G(r) (reference
+        ``__init__.py:343-391``)."""
+        self._ensure_wrapped(atoms)
+        r = self.get_r()
+        if iq_std is None:
+            be = self._load(atoms, self.pdf_qbin, 'PDF')
+            be.set_transform(self.exp['rstep'], self.pdf_qbin, r, self.exp['qmin'])
+            return be.pdf(atoms.get_positions())
+        fq = np.array(self.fq(atoms, self.pdf_qbin, 'PDF'), dtype=np.float64)
+        a = np.abs(self.get_scatter_vector(pdf=True))
+        b = np.abs(np.average(atoms.get_array('PDF scatter') ** 2, axis=0))
+        fq_noise = _interp_std(iq_std, len(a)) * a / b
+        if fq_noise[0] == 0.0:
+            fq_noise[0] += 1e-9
+        fq += self.rs.normal(0, fq_noise)
+        be = self.pdf_backend
+        be.set_transform(self.exp['rstep'], self.pdf_qbin, r, self.exp['qmin'])
+        return be.gr_from_fq(fq)
+
+    def get_sq(self, atoms, iq_std=None, noise_distribution=np.random.normal):
+        """Structure factor S(Q) = F(Q)/Q + 1 (reference ``__init__.py:393-420``)."""
+        fq = self.get_fq(atoms, iq_std, noise_distribution)
+        q = self.get_scatter_vector()
+        with np.errstate(all='ignore'):
+            sq = (fq / q) + np.ones(q.shape)
+        sq[np.isinf(sq)] = 0.
+        return sq
+
+    def get_iq(self, atoms, iq_std=None, noise_distribution=np.random.normal):
+        """Scattering intensity I(Q) (reference ``__init__.py:422-446``)."""
+        sq = self.get_sq(atoms, iq_std, noise_distribution)
+        f2 = np.average(atoms.get_array('F(Q) scatter'), axis=0) ** 2
+        return sq * f2[int(np.floor(self.exp['qmin'] / self.exp['qbin'])):]
+
+    def get_2d_scatter(self, atoms, pixel_array):
+        """I(Q) painted onto a detector Q map (reference ``__init__.py:448-475``)."""
+        iq = self.get_iq(atoms)
+        s = self.get_scatter_vector()
+        qb = self.exp['qbin']
+        fp = np.asarray(pixel_array).ravel()
+        img = np.zeros(fp.shape)
+        for sub_s, i in zip(s, iq):
+            img[(sub_s - qb / 2. < fp) & (sub_s + qb / 2. > fp)] = i
+        return img.reshape(np.asarray(pixel_array).shape)
+
+    def get_grad_fq(self, atoms):
+        """Gradient of F(Q), [N, 3, Q] (reference ``__init__.py:477-496``)."""
+        self._ensure_wrapped(atoms)
+        g = self.grad(atoms, self.exp['qbin'])
+        return g[:, :, int(np.floor(self.exp['qmin'] / self.exp['qbin'])):]
+
+    def get_grad_pdf(self, atoms):
+        """Gradient of the PDF, float64 [N, 3, R] (reference
+        ``__init__.py:498-524``)."""
+        self._ensure_wrapped(atoms)
+        fq_grad = self.grad(atoms, self.pdf_qbin, 'PDF')
+        qmin_bin = int(self.exp['qmin'] / self.pdf_qbin)
+        fq_grad[:, :, :qmin_bin] = 0.
+        return self.grad_pdf(fq_grad, self.exp['rstep'], self.pdf_qbin,
+                             self.get_r(), self.exp['qmin'])
+
+    def get_scatter_vector(self, pdf=False):
+        """Q grid of the experiment (reference ``__init__.py:526-547``)."""
+        if pdf:
+            return np.arange(0., math.floor(self.exp['qmax'] / self.pdf_qbin) *
+                             self.pdf_qbin, self.pdf_qbin)
+        return np.arange(self.exp['qmin'],
+                         math.floor(self.exp['qmax'] / self.exp['qbin']) *
+                         self.exp['qbin'], self.exp['qbin'])
+
+    def get_r(self):
+        """r grid of the experiment (reference ``__init__.py:549-558``)."""
+        return np.arange(self.exp['rmin'], self.exp['rmax'], self.exp['rstep'])
+
+    # -- fused path used by Calc1D ------------------------------------------------
+    def get_pdf_energy_forces(self, atoms, target, potential='rw', conv=1.,
+                              want_forces=True):
+        """Rw / chi^2 of ``get_pdf(atoms)`` against ``target`` and its forces in
+        one evaluation: what ``Calc1D`` computes from ``get_pdf`` +
+        ``get_grad_pdf`` (``pyiid/calc/calc_1d.py:78-95``) without the
+        N x 3 x R gradient array.  Returns (energy, scale, forces)."""
+        self._ensure_wrapped(atoms)
+        be = self._load(atoms, self.pdf_qbin, 'PDF')
+        be.set_transform(self.exp['rstep'], self.pdf_qbin, self.get_r(),
+                         self.exp['qmin'])
+        e, scale, forces, _ = be.energy_forces(
+            atoms.get_positions(), target, potential, conv, want_forces)
+        return e, scale, forces
+
+
+def wrap_atoms(atoms, exp_dict=None):
+    """Attach scatter-factor arrays for the default (or given) experiment."""
+    scat = ElasticScatter(exp_dict)
+    scat._wrap_atoms(atoms)
+    return scat

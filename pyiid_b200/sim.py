@@ -1,0 +1,254 @@
+"""Leapfrog and the No-U-Turn sampler over the ASE calculator protocol.
+
+Interface mirror of ``pyiid/sim/__init__.py`` (``leapfrog :10-38``,
+``Ensemble :41-82``) and ``pyiid/sim/nuts_hmc.py`` (``buildtree :15-88``,
+``NUTSCanonicalEnsemble :91-244``) so scripts written against ``pyiid.sim``
+run on the B200 calculator.  The reference's own sampler source also runs
+unchanged on this package's ``Calc1D`` (it only speaks the ASE protocol);
+``tests/test_reference_sim.py`` exercises that when the reference mount is
+present.  The algorithm is the slice-sampling NUTS of Hoffman & Gelman
+(2014, Alg. 6) with dual-averaging step-size adaptation, in the reference's
+conventions: Hamiltonian = ``atoms.get_total_energy()`` in eV, the temperature
+only enters through the Maxwell-Boltzmann momentum refresh, tree doubling
+stops at ``escape_level``.
+"""
+from __future__ import print_function
+
+from collections import namedtuple
+from copy import deepcopy as dc
+from time import time
+
+import numpy as np
+from numpy.random import RandomState
+
+from . import ase_shim
+
+if ase_shim.have_real_ase():  # pragma: no cover
+    from ase.optimize.optimize import Optimizer
+    from ase.md.velocitydistribution import MaxwellBoltzmannDistribution
+    from ase.units import kB, fs
+else:
+    Optimizer = ase_shim.Optimizer
+    MaxwellBoltzmannDistribution = ase_shim.MaxwellBoltzmannDistribution
+    kB, fs = ase_shim.units.kB, ase_shim.units.fs
+
+__all__ = ['leapfrog', 'Ensemble', 'NUTSCanonicalEnsemble', 'buildtree']
+
+Emax = 200  # energy error beyond which a trajectory counts as divergent
+
+
+def leapfrog(atoms, step, center=True):
+    """One kick-drift-kick step on a copy of ``atoms``
+    (``pyiid/sim/__init__.py:10-38``).  ``get_forces`` is evaluated once at the
+    new positions; the first half kick reuses the cached forces."""
+    latoms = dc(atoms)
+    latoms.set_momenta(latoms.get_momenta() + 0.5 * step * latoms.get_forces())
+    latoms.positions += step * latoms.get_velocities()
+    latoms.set_momenta(latoms.get_momenta() + 0.5 * step * latoms.get_forces())
+    if center:
+        latoms.center()
+    return latoms
+
+
+class Ensemble(Optimizer):
+    """Base class of the samplers (``pyiid/sim/__init__.py:41-82``)."""
+
+    def __init__(self, atoms, restart=None, logfile=None, trajectory=None,
+                 seed=None, verbose=False):
+        Optimizer.__init__(self, atoms, restart, logfile, trajectory)
+        atoms.get_forces()
+        atoms.get_potential_energy()
+        if seed is None:
+            seed = np.random.randint(0, 2 ** 31)
+        self.verbose = verbose
+        self.random_state = RandomState(seed)
+        self.starting_atoms = dc(atoms)
+        self.traj = [dc(atoms)]
+        self.pe = []
+        self.metadata = {'seed': seed}
+
+    def check_eq(self, eq_steps, tol):
+        ret = np.cumsum(self.pe, dtype=float)
+        ret[eq_steps:] = ret[eq_steps:] - ret[:-eq_steps]
+        ret = ret[eq_steps - 1:] / eq_steps
+        return np.sum(np.gradient(ret[eq_steps:])) < tol
+
+    def run(self, steps=100000000, eq_steps=None, eq_tol=None, **kwargs):
+        self.metadata['planned iterations'] = steps
+        try:
+            for i in range(steps):
+                if eq_steps is not None and self.check_eq(eq_steps, eq_tol):
+                    break
+                if self.verbose:
+                    print('iteration number', i)
+                self.step()
+        except KeyboardInterrupt:
+            print('Interupted, returning data')
+        return self.traj, self.metadata
+
+    def step(self):
+        pass
+
+    def estimate_simulation_duration(self, atoms, iterations):
+        pass
+
+
+_Tree = namedtuple('_Tree', 'minus plus proposal n_valid keep_going '
+                            'accept_sum n_leaves')
+
+
+def _no_u_turn(minus, plus):
+    span = (plus.positions - minus.positions).ravel()
+    return (span.dot(minus.get_velocities().ravel()) >= 0) and \
+        (span.dot(plus.get_velocities().ravel()) >= 0)
+
+
+def _safe_exp(x):
+    with np.errstate(over='ignore', invalid='ignore'):
+        v = np.exp(x)
+    return v if np.isfinite(v) else (np.inf if x > 0 else 0.0)
+
+
+def buildtree(input_atoms, u, v, j, e, e0, rs, beta=1):
+    """Recursive doubling of the NUTS trajectory (``nuts_hmc.py:15-88``).
+    Returns (neg_atoms, pos_atoms, proposal, n_valid, keep_going, accept_sum,
+    n_leaves)."""
+    if j == 0:
+        leaf = leapfrog(input_atoms, v * e)
+        neg_delta = e0 - leaf.get_total_energy()
+        n_valid = int(u <= _safe_exp(neg_delta))
+        keep_going = int(u < _safe_exp(Emax + neg_delta))
+        accept = min(1., _safe_exp(input_atoms.get_total_energy() -
+                                   leaf.get_total_energy()))
+        return _Tree(leaf, leaf, leaf, n_valid, keep_going, accept, 1)
+    first = buildtree(input_atoms, u, v, j - 1, e, e0, rs, beta)
+    if first.keep_going != 1:
+        return first
+    if v == -1:
+        second = buildtree(first.minus, u, v, j - 1, e, e0, rs, beta)
+        minus, plus = second.minus, first.plus
+    else:
+        second = buildtree(first.plus, u, v, j - 1, e, e0, rs, beta)
+        minus, plus = first.minus, second.plus
+    proposal = first.proposal
+    total = first.n_valid + second.n_valid
+    if rs.uniform() < float(second.n_valid) / max(total, 1):
+        proposal = second.proposal
+    keep_going = int(second.keep_going and _no_u_turn(minus, plus))
+    return _Tree(minus, plus, proposal, total, keep_going,
+                 first.accept_sum + second.accept_sum,
+                 first.n_leaves + second.n_leaves)
+
+
+class NUTSCanonicalEnsemble(Ensemble):
+    """No-U-Turn sampler in the canonical ensemble (``nuts_hmc.py:91-244``)."""
+
+    def __init__(self, atoms, restart=None, logfile=None, trajectory=None,
+                 temperature=100, escape_level=13, accept_target=.65,
+                 momentum=None, seed=None, verbose=False):
+        Ensemble.__init__(self, atoms, restart, logfile, trajectory, seed,
+                          verbose)
+        self.accept_target = accept_target
+        self.temp = temperature
+        self.thermal_nrg = self.temp * kB
+        self.momentum = momentum
+        self.step_size = self._find_step_size(atoms, self.thermal_nrg)
+        self.mu = np.log(10 * self.step_size)
+        self.sim_hbar = 0
+        self.gamma = 0.05
+        self.t0 = 10
+        self.metadata.update({'samples_total': 0, 'accepted_samples': 0})
+        self.escape_level = escape_level
+        self.m = 0
+        self.leapfrogs = 0
+
+    def _refresh_momenta(self, atoms):
+        if self.momentum is None:
+            MaxwellBoltzmannDistribution(atoms, self.thermal_nrg,
+                                         force_temp=True)
+        else:
+            atoms.set_momenta(self.random_state.normal(0, 1, (len(atoms), 3)))
+
+    def _find_step_size(self, input_atoms, thermal_nrg=None, momentum=None):
+        """Hoffman & Gelman Alg. 4 (``nuts_hmc.py:113-158``): double or halve
+        until the one-step acceptance crosses 1/2."""
+        atoms = dc(input_atoms)
+        step_size = .5
+        self._refresh_momenta(atoms)
+        e_start = atoms.get_total_energy()
+
+        def ratio(eps):
+            return _safe_exp(e_start - leapfrog(atoms, eps).get_total_energy())
+
+        a = 1 if ratio(step_size) > 0.5 else -1
+        while ratio(step_size) ** a > 2. ** -a:
+            step_size *= 2. ** a
+            if self.verbose:
+                print('trying step size', step_size)
+            if step_size < 1e-7 or step_size > 1e7:
+                step_size = 1.
+                break
+        if self.verbose:
+            print('optimal step size', step_size)
+        return step_size
+
+    def step(self):
+        """One NUTS iteration (``nuts_hmc.py:160-232``); returns the list of
+        accepted configurations or None."""
+        current = self.traj[-1]
+        accepted = []
+        if self.verbose:
+            print('\ttime step size', self.step_size / fs, 'fs')
+        self._refresh_momenta(current)
+        u = self.random_state.uniform(0, 1)
+        e0 = current.get_total_energy()
+        e = self.step_size
+        n, keep_going, depth = 1, 1, 0
+        minus = dc(current)
+        plus = dc(current)
+        acc_sum, leaves = 0., 1
+        while keep_going == 1:
+            v = self.random_state.choice([-1, 1])
+            tree = buildtree(minus if v == -1 else plus, u, v, depth, e, e0,
+                             self.random_state, 1 / self.thermal_nrg)
+            if v == -1:
+                minus = tree.minus
+            else:
+                plus = tree.plus
+            acc_sum, leaves = tree.accept_sum, tree.n_leaves
+            self.leapfrogs += tree.n_leaves
+            if tree.keep_going == 1 and self.random_state.uniform() < min(
+                    1, tree.n_valid * 1. / n):
+                self.traj += [tree.proposal]
+                self.metadata['accepted_samples'] += 1
+                accepted.append(tree.proposal)
+                tree.proposal.get_forces()
+                tree.proposal.get_potential_energy()
+                self.call_observers()
+            n += tree.n_valid
+            keep_going = int(tree.keep_going and _no_u_turn(minus, plus))
+            depth += 1
+            if self.verbose:
+                print('\t \tdepth', depth, 'samples', 2 ** depth)
+            self.metadata['samples_total'] += 2 ** depth
+            if depth >= self.escape_level:
+                if self.verbose:
+                    print('\t \t \tjmax emergency escape at {}'.format(depth))
+                keep_going = 0
+        # dual averaging of the step size (Hoffman & Gelman Alg. 6)
+        w = 1. / (self.m + self.t0)
+        self.sim_hbar = (1 - w) * self.sim_hbar + \
+            w * (self.accept_target - acc_sum / leaves)
+        self.step_size = np.exp(self.mu - (self.m ** .5 / self.gamma) *
+                                self.sim_hbar)
+        self.m += 1
+        return accepted if accepted else None
+
+    def estimate_simulation_duration(self, atoms, iterations):
+        t0 = time()
+        atoms.get_forces()
+        tf = time() - t0
+        t2 = time()
+        atoms.get_potential_energy()
+        te = time() - t2
+        return iterations * (tf * 2 + te) * 2 ** self.escape_level
