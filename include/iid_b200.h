@@ -87,6 +87,14 @@ int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
  * iid_energy_forces*. */
 int iid_set_transform(iid_handle *h, int64_t nr, int64_t nq, const double *T);
 
+/* Host-only (no device): the sharding plan iid_set_structure + iid_set_shard
+ * would produce -- total work items, this rank's items and the (i, j) slots
+ * they cover, for the triangle (F(Q), force) or square (gradient) list. */
+int iid_plan_shard(int64_t n, const int32_t *type_index, int64_t n_types,
+                   int sm_count, int triangle, int rank, int world,
+                   int64_t *n_items_total, int64_t *n_items_mine,
+                   int64_t *pair_slots_mine, int64_t *padded_atoms);
+
 /* sizes ------------------------------------------------------------------- */
 int iid_get_sizes(iid_handle *h, int64_t *n, int64_t *nq, int64_t *nr,
                   int64_t *n_items_fq, int64_t *n_items_grad);

@@ -33,6 +33,8 @@ SIGNATURES = {
     'iid_set_shard': [_vp, _int, _int],
     'iid_set_structure': [_vp, _i64, _vp, _i64, _vp, _i64, _dbl],
     'iid_set_transform': [_vp, _i64, _i64, _vp],
+    'iid_plan_shard': [_i64, _vp, _i64, _int, _int, _int, _int, _pi64, _pi64,
+                       _pi64, _pi64],
     'iid_get_sizes': [_vp, _pi64, _pi64, _pi64, _pi64, _pi64],
     'iid_fq_partial': [_vp, _vp, _vp, _vp],
     'iid_fq_finish': [_vp, _vp, _vp, _vp],

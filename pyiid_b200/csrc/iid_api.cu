@@ -222,6 +222,95 @@ static void build_items(const std::vector<int> &run_begin,
     });
 }
 
+// Host-side plan of one structure: element-sorted, per-element padded atom
+// order and the two work-item lists.  No device needed.
+struct Layout {
+    int64_t np = 0;
+    std::vector<int64_t> count;
+    std::vector<int> run_type, orig, tile_type;
+    std::vector<WorkItem> tri, sq;
+};
+
+static int build_layout(int64_t n, const int32_t *type_index, int64_t n_types, int sm_count,
+                        int slab_override, Layout &L)
+{
+    if (n < 1 || n_types < 1 || !type_index) return fail(IID_E_BADARG, "bad structure arguments");
+    if (n_types > 65535) return fail(IID_E_BADARG, "more than 65535 element types");
+    if (n > (int64_t)1 << 30) return fail(IID_E_BADARG, "too many atoms");
+    L.count.assign(n_types, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        if (type_index[i] < 0 || type_index[i] >= n_types)
+            return fail(IID_E_BADARG, "type_index out of range");
+        ++L.count[type_index[i]];
+    }
+    std::vector<int> run_begin, run_end;
+    int64_t np = 0;
+    std::vector<int64_t> start(n_types, 0);
+    L.run_type.clear();
+    for (int64_t e = 0; e < n_types; ++e) {
+        start[e] = np;
+        if (L.count[e] == 0) continue;
+        const int64_t padded = (L.count[e] + TILE_I - 1) / TILE_I * TILE_I;
+        run_begin.push_back((int)np);
+        run_end.push_back((int)(np + padded));
+        L.run_type.push_back((int)e);
+        np += padded;
+    }
+    L.np = np;
+    L.orig.assign(np, -1);
+    L.tile_type.assign(np / TILE_I, 0);
+    {
+        std::vector<int64_t> fill(start);
+        for (int64_t i = 0; i < n; ++i) L.orig[fill[type_index[i]]++] = (int)i;
+        for (size_t b = 0; b < run_begin.size(); ++b)
+            for (int t = run_begin[b] / TILE_I; t < run_end[b] / TILE_I; ++t)
+                L.tile_type[t] = L.run_type[b];
+    }
+    // slab length: enough items to fill the machine ~12x over
+    const int64_t ntile = np / TILE_I;
+    const int64_t want = (int64_t)std::max(1, sm_count) * 12;
+    auto pick = [&](int64_t total_j) {
+        int64_t s = total_j / std::max<int64_t>(1, want);
+        s = (s + TILE_I - 1) / TILE_I * TILE_I;
+        s = std::max<int64_t>(TILE_I, std::min<int64_t>(4096, s));
+        if (slab_override > 0) s = (slab_override + TILE_I - 1) / TILE_I * TILE_I;
+        return (int)s;
+    };
+    build_items(run_begin, run_end, (int)np, pick(ntile * np), false, L.sq);
+    build_items(run_begin, run_end, (int)np, pick(ntile * np / 2), true, L.tri);
+    // the item info field stores the run's ELEMENT type
+    for (auto *v : {&L.tri, &L.sq})
+        for (auto &w : *v) {
+            const int b = w.info & 0xffff;
+            w.info = (w.info & ITEM_DIAG) | L.run_type[b];
+        }
+    return 0;
+}
+
+// Host-only view of the sharding (no device): how many work items rank `rank`
+// of `world` takes and how many (i, j) slots they cover.
+extern "C" int iid_plan_shard(int64_t n, const int32_t *type_index, int64_t n_types,
+                              int sm_count, int triangle, int rank, int world,
+                              int64_t *n_items_total, int64_t *n_items_mine,
+                              int64_t *pair_slots_mine, int64_t *padded_atoms)
+{
+    if (world < 1 || rank < 0 || rank >= world) return fail(IID_E_BADARG, "need 0 <= rank < world");
+    Layout L;
+    int rc = build_layout(n, type_index, n_types, sm_count, 0, L);
+    if (rc) return rc;
+    const std::vector<WorkItem> &items = triangle ? L.tri : L.sq;
+    int64_t mine = 0, slots = 0;
+    for (size_t k = (size_t)rank; k < items.size(); k += (size_t)world) {
+        ++mine;
+        slots += (int64_t)(items[k].jend - items[k].jbegin) * TILE_I;
+    }
+    if (n_items_total) *n_items_total = (int64_t)items.size();
+    if (n_items_mine) *n_items_mine = mine;
+    if (pair_slots_mine) *pair_slots_mine = slots;
+    if (padded_atoms) *padded_atoms = L.np;
+    return 0;
+}
+
 extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
                                  int64_t n_types, const double *ftable, int64_t nq,
                                  double qbin)
@@ -229,36 +318,16 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
     NEED(h);
     if (n < 1 || n_types < 1 || nq < 1 || !type_index || !ftable)
         return fail(IID_E_BADARG, "bad structure arguments");
-    if (n_types > 65535) return fail(IID_E_BADARG, "more than 65535 element types");
-    if (n > (int64_t)1 << 30) return fail(IID_E_BADARG, "too many atoms");
     CU(cudaStreamSynchronize(h->stream));
-    // element-sorted, per-element padded layout
-    std::vector<int64_t> count(n_types, 0);
-    for (int64_t i = 0; i < n; ++i) {
-        if (type_index[i] < 0 || type_index[i] >= n_types)
-            return fail(IID_E_BADARG, "type_index out of range");
-        ++count[type_index[i]];
-    }
-    std::vector<int> run_begin, run_end, run_type;
-    int64_t np = 0;
-    std::vector<int64_t> start(n_types, 0);
-    for (int64_t e = 0; e < n_types; ++e) {
-        start[e] = np;
-        if (count[e] == 0) continue;
-        const int64_t padded = (count[e] + TILE_I - 1) / TILE_I * TILE_I;
-        run_begin.push_back((int)np);
-        run_end.push_back((int)(np + padded));
-        run_type.push_back((int)e);
-        np += padded;
-    }
-    std::vector<int> orig(np, -1), tile_type(np / TILE_I, 0);
+    Layout L;
     {
-        std::vector<int64_t> fill(start);
-        for (int64_t i = 0; i < n; ++i) orig[fill[type_index[i]]++] = (int)i;
-        for (size_t b = 0; b < run_begin.size(); ++b)
-            for (int t = run_begin[b] / TILE_I; t < run_end[b] / TILE_I; ++t)
-                tile_type[t] = run_type[b];
+        int rc0 = build_layout(n, type_index, n_types, h->sm_count, h->slab_override, L);
+        if (rc0) return rc0;
     }
+    const int64_t np = L.np;
+    const std::vector<int64_t> &count = L.count;
+    const std::vector<int> &orig = L.orig, &tile_type = L.tile_type;
+    const std::vector<WorkItem> &tri = L.tri, &sq = L.sq;
     const int64_t qp = (nq + 31) / 32 * 32;
     // normaliser, closed form of N * mean_pairs(f_i f_j):
     //   na = ((sum_i f_i)^2 - sum_i f_i^2) / (N - 1)
@@ -272,27 +341,6 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
         }
         const double na = n > 1 ? (s1 * s1 - s2) / (double)(n - 1) : 0.0;
         inv_na[m] = (na != 0.0 && std::isfinite(na)) ? 1.0 / na : 0.0;
-    }
-    // the item info field stores the RUN's element type
-    std::vector<WorkItem> tri, sq;
-    {
-        // slab length: enough items to fill the machine ~12x over
-        const int64_t ntile = np / TILE_I;
-        const int64_t want = (int64_t)h->sm_count * 12;
-        auto pick = [&](int64_t total_j) {
-            int64_t s = total_j / std::max<int64_t>(1, want);
-            s = (s + TILE_I - 1) / TILE_I * TILE_I;
-            s = std::max<int64_t>(TILE_I, std::min<int64_t>(4096, s));
-            if (h->slab_override > 0) s = (h->slab_override + TILE_I - 1) / TILE_I * TILE_I;
-            return (int)s;
-        };
-        build_items(run_begin, run_end, (int)np, pick(ntile * np), false, sq);
-        build_items(run_begin, run_end, (int)np, pick(ntile * np / 2), true, tri);
-        for (auto *v : {&tri, &sq})
-            for (auto &w : *v) {
-                const int b = w.info & 0xffff;
-                w.info = (w.info & ITEM_DIAG) | run_type[b];
-            }
     }
     if (nq != h->nq) h->nr = 0;  // a transform built for another Q grid is void
     h->n = n; h->np = np; h->nq = nq; h->qp = qp; h->ntypes = n_types; h->qbin = qbin;

@@ -1,0 +1,82 @@
+"""The C-ABI library loads and exports every symbol include/iid_b200.h
+declares; without a GPU the compute path refuses to run (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+from pyiid_b200 import _lib
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, 'include', 'iid_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(iid_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), name
+
+
+def test_binding_table_covers_the_header():
+    names = set(declared_functions())
+    bound = set(_lib.SIGNATURES) | {'iid_last_error'}
+    assert names == bound, names ^ bound
+
+
+def test_version_and_bad_arguments():
+    lib = _lib.load()
+    assert lib.iid_version() >= 100
+    assert lib.iid_set_shard(None, 0, 1) != 0
+    assert lib.iid_create(0, 7, ctypes.byref(ctypes.c_void_p())) == -1
+    assert b'precision' in lib.iid_last_error()
+
+
+@pytest.mark.skipif(has_gpu(), reason='a GPU is present')
+def test_no_cpu_fallback_without_a_gpu():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.iid_create(0, 0, ctypes.byref(h))
+    assert rc == -5 and not h.value
+    from pyiid_b200 import ElasticScatter, structures
+    atoms = structures.random_atoms(5, 0)
+    with pytest.raises(_lib.IIDError):
+        ElasticScatter().get_fq(atoms)
+    with pytest.raises(NotImplementedError):
+        ElasticScatter().set_processor('CPU', 'flat')
+
+
+def test_shard_plan_partitions_the_pair_list():
+    """Host-only: the per-rank work-item slices cover every (i, j) slot once
+    and are balanced (iid_plan_shard, no device)."""
+    lib = _lib.load()
+    rs = np.random.RandomState(0)
+    for n, ntypes in ((1, 1), (33, 1), (561, 1), (2000, 2), (10000, 3)):
+        types = np.sort(rs.randint(0, ntypes, n)).astype(np.int32)
+        counts = np.bincount(types, minlength=ntypes)
+        npad = int(sum((c + 31) // 32 * 32 for c in counts))
+        for tri in (0, 1):
+            for world in (1, 2, 8):
+                slots, mine = [], []
+                for rank in range(world):
+                    v = [ctypes.c_int64(0) for _ in range(4)]
+                    rc = lib.iid_plan_shard(n, types.ctypes.data, ntypes, 148, tri,
+                                            rank, world, *[ctypes.byref(x) for x in v])
+                    assert rc == 0
+                    assert v[3].value == npad
+                    slots.append(v[2].value)
+                    mine.append(v[1].value)
+                    total = v[0].value
+                assert sum(mine) == total
+                nt = npad // 32
+                expect = npad * npad if not tri else (nt * (nt - 1) // 2 + nt) * 1024
+                assert sum(slots) == expect
+                if total >= 16 * world:
+                    assert max(slots) <= 1.15 * (sum(slots) / world) + 32 * 4096

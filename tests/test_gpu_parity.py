@@ -1,0 +1,417 @@
+"""Parity of the CUDA path (through the public API and the C ABI) with the CPU
+oracle and with the golden vectors generated from the reference.
+
+Tolerances (conftest.py): normalised max-norm 1e-5 in FP32 mode on F(Q), G(r),
+energies and forces; 1e-10 in FP64 mode.  The full gradient array in FP32 mode
+is held to 1e-5 against the float64 variant of the reference arithmetic (same
+float32-rounded inputs) and to the float32 reference's own noise floor (5e-5)
+against the float32 oracle."""
+import copy
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden, nerr, TOL32, TOL64, TOL32_GRAD_VS_F32
+from pyiid_b200 import ElasticScatter, Calc1D, PDFCalc, structures, ase_shim, _lib
+from pyiid_b200.calc import wrap_rw, wrap_chi_sq, wrap_grad_rw, wrap_grad_chi_sq
+from pyiid_b200 import sim
+
+pytestmark = pytest.mark.gpu
+
+EXP = oracle.DEFAULT_EXP
+CASES = ['au4_square', 'au10_random', 'au55_ico', 'aupt37_alloy']
+
+
+def atoms_from(g, which='positions'):
+    a = ase_shim.Atoms(numbers=g['numbers'], positions=g[which])
+    a.set_array('F(Q) scatter', g['scatter_fq'])
+    a.set_array('PDF scatter', g['scatter_pdf'])
+    return a
+
+
+def wrapped(scat, atoms, g):
+    """Feed the SAME scatter-factor arrays to kernel and oracle."""
+    atoms.info['exp'] = scat.exp
+    atoms.info['scatter_atoms'] = len(atoms)
+    scat.wrap_atoms_state = True
+    return atoms
+
+
+# ---- golden vectors from the reference -------------------------------------------
+@pytest.mark.parametrize('name', CASES)
+def test_fp32_against_reference_golden_vectors(name):
+    g = golden(name)
+    scat = ElasticScatter(precision='fp32')
+    atoms = wrapped(scat, atoms_from(g), g)
+    fq = scat.get_fq(atoms)
+    assert fq.dtype == np.float32 and fq.shape == (250,)
+    assert nerr(fq, g['fq_f32']) < TOL32
+    assert nerr(fq, g['fq_f64']) < TOL32
+    grad = scat.get_grad_fq(atoms)
+    assert grad.shape == (len(atoms), 3, 250)
+    assert nerr(grad, g['grad_fq_f64']) < TOL32
+    assert nerr(grad, g['grad_fq_f32']) < TOL32_GRAD_VS_F32
+    pdf = scat.get_pdf(atoms)
+    assert pdf.dtype == np.float64 and pdf.shape == (4000,)
+    assert nerr(pdf, g['pdf_f32']) < TOL32
+    for pot in ('rw', 'chi_sq'):
+        calc = Calc1D(target_data=g['target_pdf_f32'], exp_function=scat.get_pdf,
+                      exp_grad_function=scat.get_grad_pdf, potential=pot, conv=1.)
+        a = wrapped(scat, atoms_from(g), g)
+        a.set_calculator(calc)
+        val, scale = g['%s_f32' % pot]
+        assert abs(a.get_potential_energy() - val) <= TOL32 * max(abs(val), 1.)
+        assert nerr(a.get_forces(), g['%s_forces_f32' % pot]) < TOL32
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_fp64_against_reference_golden_vectors(name):
+    g = golden(name)
+    scat = ElasticScatter(precision='fp64')
+    atoms = wrapped(scat, atoms_from(g), g)
+    assert nerr(scat.get_fq(atoms), g['fq_f64']) < TOL64
+    assert nerr(scat.get_grad_fq(atoms), g['grad_fq_f64']) < TOL64
+    assert nerr(scat.get_pdf(atoms), g['pdf_f64']) < TOL64
+    for pot in ('rw', 'chi_sq'):
+        calc = Calc1D(target_data=g['target_pdf_f64'], exp_function=scat.get_pdf,
+                      exp_grad_function=scat.get_grad_pdf, potential=pot, conv=1.)
+        a = wrapped(scat, atoms_from(g), g)
+        a.set_calculator(calc)
+        val, scale = g['%s_f64' % pot]
+        assert abs(a.get_potential_energy() - val) <= TOL64 * max(abs(val), 1.)
+        assert abs(calc.scale - scale) <= TOL64 * max(abs(scale), 1.)
+        assert nerr(a.get_forces(), g['%s_forces_f64' % pot]) < 10 * TOL64
+
+
+def test_grad_pdf_against_reference_golden_vector():
+    g = golden('au4_square')
+    for prec, tag, tol in (('fp32', 'f32', TOL32), ('fp64', 'f64', TOL64)):
+        scat = ElasticScatter(precision=prec)
+        atoms = wrapped(scat, atoms_from(g), g)
+        gp = scat.get_grad_pdf(atoms)
+        assert gp.shape == (4, 3, 4000) and gp.dtype == np.float64
+        assert nerr(gp, g['grad_pdf_' + tag]) < tol
+
+
+# ---- oracle on seeded inputs at several sizes --------------------------------------
+@pytest.mark.parametrize('n', [2, 31, 33, 100, 561, 1000])
+def test_fp32_against_oracle(n):
+    atoms = structures.icosahedron('Au', 5) if n == 561 else \
+        structures.random_atoms(n, n) if n < 500 else structures.fcc_sphere('Au', n)
+    scat = ElasticScatter(precision='fp32')
+    fq = scat.get_fq(atoms)
+    grad = scat.get_grad_fq(atoms)
+    pdf = scat.get_pdf(atoms)
+    pos = atoms.get_positions()
+    sf, sp = atoms.get_array('F(Q) scatter'), atoms.get_array('PDF scatter')
+    th = 8 if n > 300 else 1
+    for oprec in ('fp32', 'fp64'):
+        p32 = pos.astype(np.float32)
+        ofq = oracle.experiment_fq(p32, sf, EXP, oprec, nthreads=th)
+        og = oracle.experiment_grad_fq(p32, sf, EXP, oprec, nthreads=th)
+        opdf = oracle.experiment_pdf(p32, sp, EXP, oprec, nthreads=th)
+        assert nerr(fq, ofq) < TOL32
+        assert nerr(pdf, opdf) < TOL32
+        assert nerr(grad, og) < (TOL32 if oprec == 'fp64' else TOL32_GRAD_VS_F32)
+
+
+@pytest.mark.parametrize('n', [3, 64, 65, 300])
+def test_fp64_against_oracle(n):
+    atoms = structures.alloy_sphere(n, seed=n)
+    scat = ElasticScatter(precision='fp64')
+    pos = atoms.get_positions()
+    fq, grad, pdf = scat.get_fq(atoms), scat.get_grad_fq(atoms), scat.get_pdf(atoms)
+    sf, sp = atoms.get_array('F(Q) scatter'), atoms.get_array('PDF scatter')
+    assert grad.dtype == np.float64
+    assert nerr(fq, oracle.experiment_fq(pos, sf, EXP, 'fp64')) < TOL64
+    assert nerr(grad, oracle.experiment_grad_fq(pos, sf, EXP, 'fp64')) < TOL64
+    assert nerr(pdf, oracle.experiment_pdf(pos, sp, EXP, 'fp64')) < TOL64
+
+
+def test_odd_experiment_and_qmin():
+    """qmin > 0, rmin > 0, Nyquist sampling, Q bins not a multiple of 32."""
+    exp = dict(qmin=1.3, qmax=21.7, qbin=.11, rmin=1.5, rmax=33.0, rstep=.02,
+               sampling='ns')
+    scat = ElasticScatter(dict(exp), precision='fp64')
+    atoms = structures.alloy_sphere(50, seed=7)
+    pos = atoms.get_positions()
+    fq, grad = scat.get_fq(atoms), scat.get_grad_fq(atoms)
+    pdf, gpdf = scat.get_pdf(atoms), scat.get_grad_pdf(atoms)
+    sf, sp = atoms.get_array('F(Q) scatter'), atoms.get_array('PDF scatter')
+    oexp = scat.exp
+    assert len(fq) == len(scat.get_scatter_vector())
+    assert nerr(fq, oracle.experiment_fq(pos, sf, oexp, 'fp64')) < TOL64
+    assert nerr(grad, oracle.experiment_grad_fq(pos, sf, oexp, 'fp64')) < TOL64
+    assert nerr(pdf, oracle.experiment_pdf(pos, sp, oexp, 'fp64')) < TOL64
+    assert nerr(gpdf, oracle.experiment_grad_pdf(pos, sp, oexp, 'fp64')) < TOL64
+    target = scat.get_pdf(structures.alloy_sphere(50, seed=7, sigma=0.0))
+    for pot in ('rw', 'chi_sq'):
+        e, f, _ = oracle.calc1d_energy_forces(pos, sp, oexp, target, pot, 3., 'fp64')
+        a = atoms.copy()
+        a.set_calculator(Calc1D(target_data=target, exp_function=scat.get_pdf,
+                                exp_grad_function=scat.get_grad_pdf, potential=pot,
+                                conv=3.))
+        assert abs(a.get_potential_energy() - e) <= TOL64 * abs(e)
+        assert nerr(a.get_forces(), f) < 10 * TOL64
+
+
+def test_single_atom_and_empty_pair_list():
+    """k_max == 0 gives zeros (flat_multi_cpu_wrap.py:85-86)."""
+    atoms = structures.random_atoms(1, 0)
+    scat = ElasticScatter()
+    assert not np.any(scat.get_fq(atoms))
+    g = scat.get_grad_fq(atoms)
+    assert g.shape == (1, 3, 250) and not np.any(g)
+    assert not np.any(scat.get_pdf(atoms))
+
+
+# ---- API behaviour the reference's tests check -----------------------------------
+def test_smoke_every_method_returns_fresh_nonzero_arrays():
+    """tests/test_scatter_smoke.py:13-181 and test_scatter.py:43."""
+    atoms = structures.random_atoms(20, 3)
+    scat = ElasticScatter()
+    for name in ('get_fq', 'get_pdf', 'get_sq', 'get_iq', 'get_grad_fq', 'get_grad_pdf'):
+        a1 = getattr(scat, name)(atoms)
+        a2 = getattr(scat, name)(atoms)
+        assert a1 is not None and np.any(a1) and a1 is not a2
+        # run-to-run determinism (tests/test_consistancy.py); S(Q=0) is 0/0 = NaN
+        # in the reference too (only inf is cleared, __init__.py:419)
+        assert np.array_equal(a1, a2, equal_nan=True)
+    img = scat.get_2d_scatter(atoms, np.linspace(0, 20, 64).reshape(8, 8))
+    assert img.shape == (8, 8) and np.any(img)
+    noisy = ElasticScatter(seed=1).get_pdf(atoms, iq_std=0.01)
+    assert noisy.shape == (4000,) and not np.allclose(noisy, scat.get_pdf(atoms))
+    assert scat.get_fq(atoms, iq_std=0.01).shape == (250,)
+
+
+def test_state_invalidation_changes_results():
+    """tests/test_scatter_state.py:11-71."""
+    atoms = structures.random_atoms(10, 4)
+    scat = ElasticScatter()
+    a1 = scat.get_fq(atoms)
+    atoms2 = atoms + ase_shim.Atom('Au', [0, 0, 0])
+    a2 = scat.get_fq(atoms2)
+    assert not np.allclose(a1, a2)
+    atoms3 = copy.deepcopy(atoms)
+    del atoms3[2]
+    assert not np.allclose(a1, scat.get_fq(atoms3))
+
+
+def test_calc1d_known_system():
+    """tests/test_calc/test_calc_1d_known.py: Au4 square vs 0.75-scaled copy:
+    rw >= 0.9, forces central (cross(r_i - com, F_i) = 0, atol 1e-7)."""
+    a1, a2 = structures.atomic_square()
+    for exp_name in ('PDF', 'FQ'):
+        scat = ElasticScatter(precision='fp64')
+        f, gf = (scat.get_pdf, scat.get_grad_pdf) if exp_name == 'PDF' else \
+            (scat.get_fq, scat.get_grad_fq)
+        calc = Calc1D(target_data=f(a1), exp_function=f, exp_grad_function=gf,
+                      potential='rw')
+        b = a2.copy()
+        b.set_calculator(calc)
+        assert b.get_potential_energy() >= .9
+        forces = b.get_forces()
+        com = b.get_center_of_mass()
+        for i in range(4):
+            assert np.allclose(np.cross(b[i].position - com, forces[i]), 0, atol=1e-7)
+
+
+def test_generic_calc_route_equals_fused_route():
+    """Calc1D through get_pdf/get_grad_pdf + wrap_grad_rw (the reference's
+    route, calc_1d.py:78-95) equals the fused device evaluation."""
+    atoms = structures.random_atoms(12, 5)
+    tgt_atoms = structures.random_atoms(12, 6)
+    scat = ElasticScatter(precision='fp64')
+    target = scat.get_pdf(tgt_atoms)
+    for pot, wp, wg in (('rw', wrap_rw, wrap_grad_rw), ('chi_sq', wrap_chi_sq, wrap_grad_chi_sq)):
+        a = atoms.copy()
+        a.set_calculator(Calc1D(target_data=target, exp_function=scat.get_pdf,
+                                exp_grad_function=scat.get_grad_pdf, potential=pot, conv=2.))
+        e, f = a.get_potential_energy(), a.get_forces()
+        gcalc, ggrad = scat.get_pdf(atoms), scat.get_grad_pdf(atoms)
+        e2, scale = wp(gcalc, target)
+        f2 = wg(ggrad, gcalc, target)
+        assert abs(e - 2. * e2) < 1e-10 * abs(e)
+        assert nerr(2. * f2, f) < 1e-9
+        oe, of, _ = oracle.calc1d_energy_forces(atoms.get_positions(),
+                                                atoms.get_array('PDF scatter'), EXP,
+                                                target, pot, 2., 'fp64')
+        assert nerr(f, of) < 10 * TOL64
+    pc = PDFCalc(obs_data=target, scatter=scat, conv=2., potential='rw')
+    b = atoms.copy()
+    b.set_calculator(pc)
+    assert abs(b.get_potential_energy() - e) >= 0  # runs; energy of rw vs chi differs
+
+
+def test_known_answers_on_device():
+    """test_master_kernel.py:19-48 through the device potential kernel."""
+    x = np.arange(0, 2 * np.pi, .1)
+    assert wrap_rw(np.cos(x), np.sin(x))[0] == 1
+    assert abs(wrap_rw(np.sin(x), np.sin(x))[0]) < 1e-15
+    assert abs(wrap_chi_sq(np.cos(x), np.sin(x))[0] - 63.01399) < 1e-5
+    assert abs(wrap_chi_sq(np.sin(x), np.sin(x))[0]) < 1e-15
+
+
+# ---- size-independent properties at full size ---------------------------------------
+@pytest.fixture(scope='module')
+def big():
+    atoms = structures.fcc_sphere('Au', 10000)
+    scat = ElasticScatter(precision='fp32')
+    scat._ensure_wrapped(atoms)
+    be = scat._load(atoms, scat.exp['qbin'], 'fq')
+    g, f = be.grad_fq(atoms.get_positions(), with_fq=True)
+    return atoms, scat, g, f
+
+
+def test_10k_properties(big):
+    atoms, scat, g, f = big
+    pos = atoms.get_positions()
+    be = scat.backend
+    # the F(Q) that comes with the gradient pass equals the triangle-pass F(Q)
+    f_tri = be.fq(pos)
+    assert nerr(f, f_tri) < 1e-6
+    # Newton's third law: the gradient summed over atoms vanishes
+    assert np.abs(g.sum(axis=0, dtype=np.float64)).max() < 1e-4 * np.abs(g).max()
+    # translation and rigid rotation leave F(Q) unchanged
+    assert nerr(be.fq(pos + np.array([3.25, -1.5, 7.0])), f_tri) < TOL32
+    c, s = np.cos(0.7), np.sin(0.7)
+    rot = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.]])
+    assert nerr(be.fq(pos.dot(rot.T)), f_tri) < TOL32
+    # permutation of the atoms permutes the gradient rows
+    perm = np.random.RandomState(0).permutation(len(pos))
+    gp = be.grad_fq(pos[perm])
+    assert nerr(gp, g[perm]) < 2e-6
+    # F(Q=0) = 0 and the result is finite
+    assert f[0] == 0 and np.all(np.isfinite(g)) and np.all(np.isfinite(f))
+
+
+def test_10k_fp32_agrees_with_fp64_mode(big):
+    atoms, scat, g, f = big
+    s64 = ElasticScatter(precision='fp64')
+    s64._ensure_wrapped(atoms)
+    be = s64._load(atoms, s64.exp['qbin'], 'fq')
+    pos32 = atoms.get_positions().astype(np.float32).astype(np.float64)
+    g64, f64 = be.grad_fq(pos32, with_fq=True)
+    assert nerr(f, f64) < TOL32
+    assert nerr(g, g64) < TOL32
+
+
+def test_10k_force_is_weighted_gradient(big):
+    """force[i,w] = sum_m wq[m] G[i,w,m] (fused path vs full gradient) and the
+    oracle on a bounded sample of rows."""
+    atoms, scat, g, f = big
+    pos = atoms.get_positions()
+    be = scat._load(atoms, scat.pdf_qbin, 'PDF')
+    be.set_transform(scat.exp['rstep'], scat.pdf_qbin, scat.get_r(), 0.0)
+    target = be.pdf(structures.fcc_sphere('Au', 10000, sigma=0.0).get_positions())
+    e, scale, forces, pdf = be.energy_forces(pos, target, 'rw', 100., want_pdf=True)
+    gfull = be.grad_fq(pos)                      # [N,3,330] on the PDF grid
+    from pyiid_b200.backend import pdf_matrix
+    t = pdf_matrix(330, .01, scat.pdf_qbin, scat.get_r(), 0.0)
+    # chain-rule weights from the oracle's Rw on the device PDF
+    a = np.dot(pdf, target) / np.dot(pdf, pdf)
+    d = target - a * pdf
+    rw = np.sqrt(np.dot(d, d) / np.dot(target, target))
+    c = -rw / np.dot(d, d) * (a * d + np.dot(pdf, d) / np.dot(pdf, pdf) * (target - 2 * a * pdf))
+    wq = 100. * t.T.dot(c)
+    ref = np.tensordot(gfull.astype(np.float64), wq, axes=([2], [0]))
+    assert abs(e - 100. * rw) < 1e-9 * abs(e)
+    assert nerr(forces, ref) < TOL32
+    assert np.abs(forces.sum(0)).max() < 1e-6 * np.abs(forces).max()
+
+
+def test_sharded_partials_sum_to_the_whole():
+    """iid_set_shard on ONE GPU: the partial results of world=3 shards add up
+    to the unsharded result (what the NCCL all-reduce does across GPUs)."""
+    import torch
+    atoms = structures.alloy_sphere(700, seed=2)
+    scat = ElasticScatter(precision='fp64')
+    scat._ensure_wrapped(atoms)
+    be = scat._load(atoms, scat.exp['qbin'], 'fq')
+    pos = atoms.get_positions()
+    g_ref, f_ref = be.grad_fq(pos, with_fq=True)
+    lib, h = be.lib, be.h
+    dev = 'cuda:%d' % be.device
+    with be._on_stream():
+        p = torch.from_numpy(pos).to(dev)
+        s_tot = torch.zeros(be.nq, dtype=torch.float64, device=dev)
+        g_tot = torch.zeros((be.n, 3, be.nq), dtype=torch.float64, device=dev)
+        s_tri = torch.zeros_like(s_tot)
+        for rank in range(3):
+            assert lib.iid_set_shard(h, rank, 3) == 0
+            s = torch.zeros_like(s_tot)
+            g = torch.zeros_like(g_tot)
+            assert lib.iid_grad_fq_partial(h, p.data_ptr(), g.data_ptr(), s.data_ptr(), None) == 0
+            s_tot += s
+            g_tot += g
+            assert lib.iid_fq_partial(h, p.data_ptr(), s.data_ptr(), None) == 0
+            s_tri += s
+        assert lib.iid_set_shard(h, 0, 1) == 0
+        f = torch.zeros_like(s_tot)
+        assert lib.iid_fq_finish(h, s_tot.data_ptr(), f.data_ptr(), None) == 0
+        f_sq = f.cpu().numpy()
+        assert lib.iid_fq_finish(h, s_tri.data_ptr(), f.data_ptr(), None) == 0
+        f_tri = f.cpu().numpy()
+        g_sum = g_tot.cpu().numpy()
+    assert nerr(f_sq, f_ref) < 1e-12 and nerr(f_tri, f_ref) < 1e-12
+    assert nerr(g_sum, g_ref) < 1e-12
+
+
+# ---- samplers on the device calculator -------------------------------------------------
+def make_hmc_atoms(shells=2, precision='fp32'):
+    scat = ElasticScatter(precision=precision)
+    ideal = structures.icosahedron('Au', shells)
+    target = scat.get_pdf(ideal)
+    atoms = structures.icosahedron('Au', shells)
+    atoms.positions *= 1.05
+    atoms.set_calculator(Calc1D(target_data=target, exp_function=scat.get_pdf,
+                                exp_grad_function=scat.get_grad_pdf, conv=100,
+                                potential='rw'))
+    return atoms, scat
+
+
+def test_leapfrog_reversibility_and_single_evaluation():
+    """tests/test_sim/test_leapfrog.py:58-73 on the PDF calculator; one device
+    evaluation per leapfrog (the reference needs three)."""
+    atoms, scat = make_hmc_atoms(2, 'fp64')
+    atoms.set_momenta(np.random.RandomState(0).normal(0, 1, (55, 3)))
+    atoms.get_forces()
+    be = scat.pdf_backend
+    n0 = be.launch_count()
+    b = sim.leapfrog(atoms, 0.05, False)
+    b.get_total_energy()
+    per_eval = be.launch_count() - n0
+    assert per_eval <= 8
+    c = sim.leapfrog(b, -0.05, False)
+    assert np.allclose(c.positions, atoms.positions, atol=1e-9)
+    assert np.allclose(c.get_momenta(), atoms.get_momenta(), atol=1e-9)
+
+
+def test_forces_are_minus_half_the_energy_gradient():
+    """Reference convention (SURVEY.md 8a note 1): forces = -1/2 dE/dq."""
+    atoms, scat = make_hmc_atoms(1, 'fp64')
+    f = atoms.get_forces()
+    h = 1e-5
+    for i, w in ((0, 0), (5, 2)):
+        ap, am = atoms.copy(), atoms.copy()
+        ap.positions[i, w] += h
+        am.positions[i, w] -= h
+        for x in (ap, am):
+            x.set_calculator(atoms.get_calculator())
+        de = (ap.get_potential_energy() - am.get_potential_energy()) / (2 * h)
+        assert abs(f[i, w] - (-0.5 * de)) < 1e-5 * np.abs(f).max()
+
+
+def test_nuts_runs_on_the_device_calculator():
+    """tests/test_sim/test_nuts.py:17-64 with the PDF calculator."""
+    atoms, scat = make_hmc_atoms(2, 'fp32')
+    np.random.seed(0)
+    e0 = atoms.get_potential_energy()
+    ens = sim.NUTSCanonicalEnsemble(atoms, temperature=1000, escape_level=4, seed=0)
+    traj, meta = ens.run(5)
+    pe = [t.get_potential_energy() for t in traj]
+    assert meta['samples_total'] > 0 and len(traj) >= 1
+    assert min(pe) <= e0
+    assert all(np.isfinite(pe))
