@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "iid_debye.cuh"
+#include "iid_debye2.cuh"
 #include "iid_small.cuh"
 
 using namespace iid;
@@ -80,6 +81,7 @@ struct iid_handle {
     // tunables
     int nw_max = 8;
     int slab_override = 0;
+    bool use_v1 = false;
     // instrumentation
     int64_t launches = 0;
     bool timing = false;
@@ -139,6 +141,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     CU(cudaMalloc((void **)&h->out4, 4 * sizeof(double)));
     if (const char *s = getenv("IID_NW")) h->nw_max = std::max(1, std::min(12, atoi(s)));
     h->nw_max = std::min(h->nw_max, 12);
+    if (const char *s = getenv("IID_V1")) h->use_v1 = atoi(s) != 0;
     if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
     *out = h;
     return 0;
@@ -467,6 +470,44 @@ static int launch_debye_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
     return 0;
 }
 
+// FP32: producer/consumer kernel (iid_debye2.cuh); IID_V1=1 selects the
+// simpler per-warp set-up kernel of iid_debye.cuh for comparison.
+template <int C, int MODE>
+static int launch_debye2_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
+                           cudaStream_t st)
+{
+    const int nchunk = (int)((h->nq + C - 1) / C);
+    const int gy = (nchunk + h->nw_max - 1) / h->nw_max;
+    const int nw = (nchunk + gy - 1) / gy;
+    dim3 grid((unsigned)nblocks, (unsigned)gy, 1), block(32 * nw, 1, 1);
+    const size_t smem = 2 * debye2_buf_bytes(nw);
+    if (h->timing) CU(cudaEventRecord(h->ev0, st));
+    if (nw <= 8) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, 256>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_done = true;
+        }
+        debye2_kernel<C, MODE, 256><<<grid, block, smem, st>>>(p);
+    } else {
+        static bool attr_done = false;
+        if (!attr_done) {
+            CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, 384>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_done = true;
+        }
+        debye2_kernel<C, MODE, 384><<<grid, block, smem, st>>>(p);
+    }
+    ++h->launches;
+    CU(cudaGetLastError());
+    if (h->timing) {
+        CU(cudaEventRecord(h->ev1, st));
+        h->ev_pending = true;
+    }
+    return 0;
+}
+
 constexpr int C32 = 32;  // Q bins per warp, float32 kernels
 constexpr int C64 = 16;  // Q bins per warp, float64 kernels
 
@@ -489,6 +530,11 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     const int64_t mine = nitems > h->rank ? (nitems - h->rank + h->world - 1) / h->world : 0;
     h->last_pairq = 0.5 * (double)h->n * (double)(h->n - 1) * (double)h->nq / h->world;
     if (mine == 0) return 0;
+    if (h->precision == IID_FP32 && !h->use_v1) {
+        if (mode == MODE_FQ) return launch_debye2_t<C32, MODE_FQ>(h, p, mine, st);
+        if (mode == MODE_GRAD) return launch_debye2_t<C32, MODE_GRAD>(h, p, mine, st);
+        return launch_debye2_t<C32, MODE_FORCE>(h, p, mine, st);
+    }
     if (h->precision == IID_FP32) {
         if (mode == MODE_FQ) return launch_debye_t<float, C32, MODE_FQ>(h, p, mine, st);
         if (mode == MODE_GRAD) return launch_debye_t<float, C32, MODE_GRAD>(h, p, mine, st);

@@ -319,7 +319,8 @@ def test_10k_force_is_weighted_gradient(big):
     ref = np.tensordot(gfull.astype(np.float64), wq, axes=([2], [0]))
     assert abs(e - 100. * rw) < 1e-9 * abs(e)
     assert nerr(forces, ref) < TOL32
-    assert np.abs(forces.sum(0)).max() < 1e-6 * np.abs(forces).max()
+    # Newton's third law up to float32 rounding of the per-pair scalar
+    assert np.abs(forces.sum(0)).max() < 1e-4 * np.abs(forces).max()
 
 
 def test_sharded_partials_sum_to_the_whole():
