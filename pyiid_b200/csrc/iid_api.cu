@@ -82,6 +82,7 @@ struct iid_handle {
     int nw_max = 8;
     int slab_override = 0;
     bool use_v1 = false;
+    bool cheb = true;
     // instrumentation
     int64_t launches = 0;
     bool timing = false;
@@ -142,6 +143,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_NW")) h->nw_max = std::max(1, std::min(12, atoi(s)));
     h->nw_max = std::min(h->nw_max, 12);
     if (const char *s = getenv("IID_V1")) h->use_v1 = atoi(s) != 0;
+    if (const char *s = getenv("IID_CHEB")) h->cheb = atoi(s) != 0;
     if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
     *out = h;
     return 0;
@@ -472,7 +474,7 @@ static int launch_debye_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
 
 // FP32: producer/consumer kernel (iid_debye2.cuh); IID_V1=1 selects the
 // simpler per-warp set-up kernel of iid_debye.cuh for comparison.
-template <int C, int MODE>
+template <int C, int MODE, bool CHEB>
 static int launch_debye2_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
                            cudaStream_t st)
 {
@@ -485,19 +487,19 @@ static int launch_debye2_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
     if (nw <= 8) {
         static bool attr_done = false;
         if (!attr_done) {
-            CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, 256>,
+            CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, 256, CHEB>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_done = true;
         }
-        debye2_kernel<C, MODE, 256><<<grid, block, smem, st>>>(p);
+        debye2_kernel<C, MODE, 256, CHEB><<<grid, block, smem, st>>>(p);
     } else {
         static bool attr_done = false;
         if (!attr_done) {
-            CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, 384>,
+            CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, 384, CHEB>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_done = true;
         }
-        debye2_kernel<C, MODE, 384><<<grid, block, smem, st>>>(p);
+        debye2_kernel<C, MODE, 384, CHEB><<<grid, block, smem, st>>>(p);
     }
     ++h->launches;
     CU(cudaGetLastError());
@@ -530,10 +532,15 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     const int64_t mine = nitems > h->rank ? (nitems - h->rank + h->world - 1) / h->world : 0;
     h->last_pairq = 0.5 * (double)h->n * (double)(h->n - 1) * (double)h->nq / h->world;
     if (mine == 0) return 0;
+    if (h->precision == IID_FP32 && !h->use_v1 && h->cheb) {
+        if (mode == MODE_FQ) return launch_debye2_t<C32, MODE_FQ, true>(h, p, mine, st);
+        if (mode == MODE_GRAD) return launch_debye2_t<C32, MODE_GRAD, true>(h, p, mine, st);
+        return launch_debye2_t<C32, MODE_FORCE, true>(h, p, mine, st);
+    }
     if (h->precision == IID_FP32 && !h->use_v1) {
-        if (mode == MODE_FQ) return launch_debye2_t<C32, MODE_FQ>(h, p, mine, st);
-        if (mode == MODE_GRAD) return launch_debye2_t<C32, MODE_GRAD>(h, p, mine, st);
-        return launch_debye2_t<C32, MODE_FORCE>(h, p, mine, st);
+        if (mode == MODE_FQ) return launch_debye2_t<C32, MODE_FQ, false>(h, p, mine, st);
+        if (mode == MODE_GRAD) return launch_debye2_t<C32, MODE_GRAD, false>(h, p, mine, st);
+        return launch_debye2_t<C32, MODE_FORCE, false>(h, p, mine, st);
     }
     if (h->precision == IID_FP32) {
         if (mode == MODE_FQ) return launch_debye_t<float, C32, MODE_FQ>(h, p, mine, st);

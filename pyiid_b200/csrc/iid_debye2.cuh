@@ -12,18 +12,30 @@
 // float32 minimax polynomial on the quadrant-reduced angle, the chunk seeds by
 // rotating with e^{i C theta}), double-buffered so that the records of tile
 // t+1 are produced while tile t is consumed.  The consumer's per-(pair, chunk)
-// overhead is 3 shared-memory loads; its bin loop is pure FP32 pipe work:
-// 10 instructions per bin for F + grad F, 5 for F only, 6 for the force.
+// overhead is a handful of shared-memory loads; its bin loop is pure FP32 pipe
+// work: 10 instructions per bin for F + grad F, 5 for F only, 6 for the force.
+//
+// Packed arithmetic.  With one atom pair per lane every FFMA operand is a
+// per-lane register, and on sm_100 a scalar FFMA whose two multiplicands sit
+// in the same register bank costs an extra dispatch cycle (measured: the scalar
+// loop reaches 73 % of the FP32 pipe, scripts/ubench2.cu).  The loop is
+// therefore written on float2 values with the sm_100 packed instructions
+// (FFMA2/FMUL2/FADD2): a warp advances TWO half-chunks of C/2 bins per
+// instruction (bins m0+k and m0+C/2+k, two independent rotation recurrences
+// with their own seeds), the accumulators live in aligned register pairs and
+// the per-pair constants enter as broadcast scalars; this reaches 87 % of the
+// pipe in the same micro-benchmark.
 #pragma once
 #include "iid_debye.cuh"
 
 namespace iid {
 
 constexpr int TJ2 = 16;  // j atoms per produced tile
+constexpr int NREC = 10;  // floats per pair record shared by all warps
 
 __host__ __device__ inline size_t debye2_buf_bytes(int nwarp)
 {
-    return (size_t)TJ2 * 32 * sizeof(float) * (7 + 2 * (size_t)nwarp);
+    return (size_t)TJ2 * 32 * sizeof(float) * (NREC + 4 * (size_t)nwarp);
 }
 
 // sin, cos of 2 pi u for any u >= 0 held in float64: quadrant in float64,
@@ -41,7 +53,16 @@ __device__ __forceinline__ void sincos_turns(double u, float &s, float &c)
     if (quad >= 2) s = -s;
 }
 
-template <int C, int MODE, int MAXT>
+// CHEB selects how sin/cos are advanced from bin to bin: false = complex
+// rotation everywhere (2 FMUL + 2 FFMA per bin, error ~1.4e-7 rms); true = the
+// three-term recurrence x[k+1] = 2 cos(theta) x[k] - x[k-1] (1 FFMA per
+// sequence per bin) inside quarter-chunks of C/4 bins.  The float32 rounding
+// of 2 cos(theta) is a small frequency error that grows linearly with the
+// number of steps, so every quarter-chunk restarts from an exact seed (the
+// second one is the half-chunk seed rotated by C/4 bins) and takes its first
+// step with the rotation; over 8 bins the error is 1.3-2.5e-7 rms, the same
+// as the rotation ("recurrences").
+template <int C, int MODE, int MAXT, bool CHEB>
 __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -74,21 +95,31 @@ __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
     // opposite register banks (vector loads would pin their parities)
     auto tab = [&](int b) { return reinterpret_cast<float *>(smem_raw + (size_t)b * buf_bytes); };
 
-    float accF[MODE != MODE_FORCE ? C : 1];
-    float accX[MODE == MODE_GRAD ? C : 1], accY[MODE == MODE_GRAD ? C : 1],
-        accZ[MODE == MODE_GRAD ? C : 1];
-    float w0[MODE == MODE_FORCE ? C : 1], w1[MODE == MODE_FORCE ? C : 1];
+    static_assert(C % 2 == 0, "C must be even");
+    constexpr int H = C / 2;  // bins per half-chunk; .x = bin m0+k, .y = bin m0+H+k
+    float2 accF[MODE != MODE_FORCE ? H : 1];
+    float2 accX[MODE == MODE_GRAD ? H : 1], accY[MODE == MODE_GRAD ? H : 1],
+        accZ[MODE == MODE_GRAD ? H : 1];
+    float2 w0[MODE == MODE_FORCE ? H : 1], w1[MODE == MODE_FORCE ? H : 1];
     float fix = 0.f, fiy = 0.f, fiz = 0.f;
 #pragma unroll
-    for (int m = 0; m < C; ++m) {
-        if constexpr (MODE != MODE_FORCE) accF[m] = 0.f;
-        if constexpr (MODE == MODE_GRAD) { accX[m] = 0.f; accY[m] = 0.f; accZ[m] = 0.f; }
+    for (int k = 0; k < H; ++k) {
+        if constexpr (MODE != MODE_FORCE) accF[k] = make_float2(0.f, 0.f);
+        if constexpr (MODE == MODE_GRAD) {
+            accX[k] = make_float2(0.f, 0.f);
+            accY[k] = make_float2(0.f, 0.f);
+            accZ[k] = make_float2(0.f, 0.f);
+        }
         if constexpr (MODE == MODE_FORCE) {
-            const int bin = m0 + m;
-            float w = 0.f;
-            if (bin < p.nq) w = (float)(p.wq[bin]) * fa[bin] * fb[bin] * inv_na[bin];
-            w0[m] = w;
-            w1[m] = w * (float)bin;
+            float w[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int bin = m0 + hh * H + k;
+                w[hh] = 0.f;
+                if (bin < p.nq) w[hh] = (float)(p.wq[bin]) * fa[bin] * fb[bin] * inv_na[bin];
+            }
+            w0[k] = make_float2(w[0], w[1]);
+            w1[k] = make_float2(w[0] * (float)(m0 + k), w[1] * (float)(m0 + H + k));
         }
     }
     if constexpr (MODE == MODE_FORCE)
@@ -97,7 +128,7 @@ __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
     // ---- producer: the pair records of one j tile -----------------------------
     auto produce = [&](int jt, int b) {
         float *T = tab(b);
-        float *S = T + 7 * NPAIR;
+        float *S = T + NREC * NPAIR;
         for (int pr = threadIdx.x; pr < NPAIR; pr += blockDim.x) {
             const int jj = pr >> 5;  // (pr & 31) == lane: this thread's own atom i
             const int gj = jt + jj;
@@ -110,9 +141,10 @@ __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
             if (!(keep && r2f > 0.f)) y = 0.0;   // self pair, ghost atom, r == 0
             const double r = r2 * y;
             const double u = r * p.qbin_turns;   // turns per Q bin
-            float sth, cth, sC, cC, s, c;
+            float sth, cth, sC, cC, sQ, cQ, s, c;
             sincos_turns(u, sth, cth);
-            sincos_turns(u * (double)C, sC, cC);
+            sincos_turns(u * (double)H, sC, cC);        // rotation by one half-chunk
+            sincos_turns(u * (double)(H / 2), sQ, cQ);  // rotation by one quarter-chunk
             if (chunk0 == 0) { s = 0.f; c = 1.f; }
             else sincos_turns(u * (double)(chunk0 * C), s, c);
             const float invr = (float)y;
@@ -126,13 +158,16 @@ __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
             T[4 * NPAIR + pr] = (float)dxd;
             T[5 * NPAIR + pr] = (float)dyd;
             T[6 * NPAIR + pr] = (float)dzd;
+            T[7 * NPAIR + pr] = cQ;
+            T[8 * NPAIR + pr] = sQ;
+            float2 *S2 = reinterpret_cast<float2 *>(S);
             for (int w = 0; w < nwarp; ++w) {
-                S[(2 * w) * NPAIR + pr] = s;
-                S[(2 * w + 1) * NPAIR + pr] = c;
-                const float sn = fmaf(s, cC, c * sC);
-                const float cn = fmaf(c, cC, -(s * sC));
-                s = sn;
-                c = cn;
+                const float s1 = fmaf(s, cC, c * sC);
+                const float c1 = fmaf(c, cC, -(s * sC));
+                S2[(2 * w) * NPAIR + pr] = make_float2(s, s1);      // sin at m0, m0+H
+                S2[(2 * w + 1) * NPAIR + pr] = make_float2(c, c1);  // cos at m0, m0+H
+                s = fmaf(s1, cC, c1 * sC);
+                c = fmaf(c1, cC, -(s1 * sC));
             }
         }
     };
@@ -140,45 +175,90 @@ __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
     // ---- consumer: this warp's chunk of bins for pairs (lane, jj) --------------
     auto consume = [&](int b, int jlo, int jhi, int fbuf) {
         const float *T = tab(b) + lane;
-        const float *S = T + (7 + 2 * warp) * NPAIR;
+        const float2 *S2 = reinterpret_cast<const float2 *>(tab(b) + NREC * NPAIR) +
+                           (2 * warp) * NPAIR + lane;
         float n_cth = T[jlo * 32], n_sth = T[NPAIR + jlo * 32], n_kap = T[2 * NPAIR + jlo * 32],
               n_r2 = T[3 * NPAIR + jlo * 32], n_dx = T[4 * NPAIR + jlo * 32],
               n_dy = T[5 * NPAIR + jlo * 32], n_dz = T[6 * NPAIR + jlo * 32],
-              n_s = S[jlo * 32], n_c = S[NPAIR + jlo * 32];
+              n_cq = T[7 * NPAIR + jlo * 32], n_sq = T[8 * NPAIR + jlo * 32];
+        float2 n_s = S2[jlo * 32], n_c = S2[NPAIR + jlo * 32];
         for (int jj = jlo; jj < jhi; ++jj) {
             const float cth = n_cth, sth = n_sth, kap = n_kap, r2 = n_r2;
-            const float dx = n_dx, dy = n_dy, dz = n_dz;
-            float s = n_s, c = n_c;
+            const float dx = n_dx, dy = n_dy, dz = n_dz, cq = n_cq, sq = n_sq;
+            float2 s = n_s, c = n_c;
             {   // prefetch the next pair's record
                 const int jn = min(jj + 1, jhi - 1) * 32;
                 n_cth = T[jn]; n_sth = T[NPAIR + jn]; n_kap = T[2 * NPAIR + jn];
                 n_r2 = T[3 * NPAIR + jn]; n_dx = T[4 * NPAIR + jn];
                 n_dy = T[5 * NPAIR + jn]; n_dz = T[6 * NPAIR + jn];
-                n_s = S[jn]; n_c = S[NPAIR + jn];
+                if constexpr (CHEB) { n_cq = T[7 * NPAIR + jn]; n_sq = T[8 * NPAIR + jn]; }
+                n_s = S2[jn]; n_c = S2[NPAIR + jn];
             }
-            float mk = kap * (float)m0;
-            float p0 = 0.f, p1 = 0.f;
+            const float2 cth2 = make_float2(cth, cth), sth2 = make_float2(sth, sth),
+                         nsth2 = make_float2(-sth, -sth), r22 = make_float2(r2, r2),
+                         kap2 = make_float2(kap, kap);
+            const float tc = cth + cth;
+            const float2 tc2 = make_float2(tc, tc);
+            float2 mk = make_float2(kap * (float)m0, kap * (float)(m0 + H));
+            // four independent partial sums each: a single FFMA2 chain over the
+            // bins would be latency-bound
+            float2 p0[4], p1[4];
 #pragma unroll
-            for (int m = 0; m < C; ++m) {
-                if constexpr (MODE != MODE_FORCE) accF[m] = fmaf(s, r2, accF[m]);
+            for (int q = 0; q < 4; ++q) { p0[q] = make_float2(0.f, 0.f); p1[q] = make_float2(0.f, 0.f); }
+            float2 sp = s, cp = c;  // previous bin (three-term recurrence)
+            constexpr int HQ = H / 2;  // bins per quarter-chunk
+            // seed of the second quarter-chunk: the exact seed rotated by HQ bins
+            float2 s8 = s, c8 = c;
+            if constexpr (CHEB) {
+                const float2 cq2 = make_float2(cq, cq), sq2 = make_float2(sq, sq),
+                             nsq2 = make_float2(-sq, -sq);
+                s8 = __ffma2_rn(s, cq2, __fmul2_rn(c, sq2));
+                c8 = __ffma2_rn(c, cq2, __fmul2_rn(s, nsq2));
+            }
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                if constexpr (MODE != MODE_FORCE) accF[k] = __ffma2_rn(s, r22, accF[k]);
                 if constexpr (MODE == MODE_GRAD) {
-                    const float a = fmaf(mk, c, -s);
-                    accX[m] = fmaf(a, dx, accX[m]);
-                    accY[m] = fmaf(a, dy, accY[m]);
-                    accZ[m] = fmaf(a, dz, accZ[m]);
-                    mk += kap;
+                    const float2 a = __ffma2_rn(mk, c, make_float2(-s.x, -s.y));
+                    accX[k] = __ffma2_rn(a, make_float2(dx, dx), accX[k]);
+                    accY[k] = __ffma2_rn(a, make_float2(dy, dy), accY[k]);
+                    accZ[k] = __ffma2_rn(a, make_float2(dz, dz), accZ[k]);
+                    mk = __fadd2_rn(mk, kap2);
                 }
                 if constexpr (MODE == MODE_FORCE) {
-                    p1 = fmaf(w1[m], c, p1);
-                    p0 = fmaf(w0[m], s, p0);
+                    p1[k & 3] = __ffma2_rn(w1[k], c, p1[k & 3]);
+                    p0[k & 3] = __ffma2_rn(w0[k], s, p0[k & 3]);
                 }
-                const float sn = fmaf(s, cth, c * sth);
-                const float cn = fmaf(c, cth, -(s * sth));
-                s = sn;
-                c = cn;
+                if (k + 1 < H) {
+                    if (CHEB && k + 1 == HQ) {
+                        s = s8;  // fresh seed for the second quarter-chunk
+                        c = c8;
+                    } else if (!CHEB || k % HQ == 0) {
+                        const float2 sn = __ffma2_rn(s, cth2, __fmul2_rn(c, sth2));
+                        const float2 cn = __ffma2_rn(c, cth2, __fmul2_rn(s, nsth2));
+                        sp = s;
+                        cp = c;
+                        s = sn;
+                        c = cn;
+                    } else {
+                        const float2 sn = __ffma2_rn(tc2, s, make_float2(-sp.x, -sp.y));
+                        sp = s;
+                        s = sn;
+                        // cos is only needed for a (MODE_GRAD), the force sum and
+                        // the rotation steps; MODE_FQ skips it in the last
+                        // Chebyshev steps of a quarter where nothing reads it
+                        if (MODE != MODE_FQ || (k % HQ) < 1) {
+                            const float2 cn = __ffma2_rn(tc2, c, make_float2(-cp.x, -cp.y));
+                            cp = c;
+                            c = cn;
+                        }
+                    }
+                }
             }
             if constexpr (MODE == MODE_FORCE) {
-                const float phi = fmaf(kap, p1, -p0);
+                const float2 q1 = __fadd2_rn(__fadd2_rn(p1[0], p1[1]), __fadd2_rn(p1[2], p1[3]));
+                const float2 q0 = __fadd2_rn(__fadd2_rn(p0[0], p0[1]), __fadd2_rn(p0[2], p0[3]));
+                const float phi = fmaf(kap, q1.x + q1.y, -(q0.x + q0.y));
                 fix = fmaf(phi, dx, fix);
                 fiy = fmaf(phi, dy, fiy);
                 fiz = fmaf(phi, dz, fiz);
@@ -237,16 +317,19 @@ __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
         for (int m = 0; m < C; ++m) {
             const int bin = m0 + m;
             if (bin < p.nq) {  // warp-uniform
+                const int k = m % H;
+                const bool hi = m >= H;
                 const float ff = fa[bin] * fb[bin];
                 if constexpr (MODE == MODE_GRAD) if (oi >= 0) {
                     const float sc = ff * inv_na[bin];
                     float *row = G + (size_t)oi * 3 * p.nq + bin;
-                    atomicAdd(row, accX[m] * sc);
-                    atomicAdd(row + p.nq, accY[m] * sc);
-                    atomicAdd(row + 2 * (size_t)p.nq, accZ[m] * sc);
+                    atomicAdd(row, (hi ? accX[k].y : accX[k].x) * sc);
+                    atomicAdd(row + p.nq, (hi ? accY[k].y : accY[k].x) * sc);
+                    atomicAdd(row + 2 * (size_t)p.nq, (hi ? accZ[k].y : accZ[k].x) * sc);
                 }
                 if (p.S != nullptr) {
-                    const double v = warp_sum((double)accF[m] * (double)ff);
+                    const float fv = hi ? accF[k].y : accF[k].x;
+                    const double v = warp_sum((double)fv * (double)ff);
                     if (lane == 0) atomicAdd(&p.S[bin], fweight * v);
                 }
             }

@@ -19,7 +19,7 @@ for name, atoms in [('Au10', structures.random_atoms(10, 1)),
                     ('Au561', structures.icosahedron('Au', 5)),
                     ('AuPt300', structures.alloy_sphere(300)),
                     ('Au1000', structures.fcc_sphere('Au', 1000))]:
-    for prec in ('fp32', 'fp64'):
+    for prec in (('fp32',) if 'quick' in sys.argv else ('fp32', 'fp64')):
         scat = ElasticScatter(precision=prec)
         t = time.time()
         fq = scat.get_fq(atoms); g = scat.get_grad_fq(atoms); pdf = scat.get_pdf(atoms)
@@ -54,6 +54,8 @@ for prec in ('fp32', 'fp64'):
         print('square', prec, pot, 'E', e, oe, 'force err', nerr(f, of), 'generic err', nerr(f2, of), flush=True)
 
 # timings
+if 'quick' in sys.argv:
+    sys.exit(0)
 for n, prec in [(10000, 'fp32'), (10000, 'fp64'), (50000, 'fp32')]:
     atoms = structures.fcc_sphere('Au' if n == 10000 else 'Pt', n)
     scat = ElasticScatter(precision=prec)
