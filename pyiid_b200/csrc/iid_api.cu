@@ -474,6 +474,22 @@ static int launch_debye_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
 
 // FP32: producer/consumer kernel (iid_debye2.cuh); IID_V1=1 selects the
 // simpler per-warp set-up kernel of iid_debye.cuh for comparison.
+template <int C, int MODE, int MAXT, int MINB, int TJ, bool CHEB>
+static int launch_debye2_v(iid_handle *h, const DebyeParams &p, dim3 grid, dim3 block, int nw,
+                           cudaStream_t st)
+{
+    const size_t smem = 2 * debye2_buf_bytes(nw, TJ) +
+                        (MODE == MODE_FORCE ? debye2_phi_bytes(nw, TJ) : 0);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, MAXT, MINB, TJ, CHEB>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    debye2_kernel<C, MODE, MAXT, MINB, TJ, CHEB><<<grid, block, smem, st>>>(p);
+    return 0;
+}
+
 template <int C, int MODE, bool CHEB>
 static int launch_debye2_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
                            cudaStream_t st)
@@ -482,25 +498,19 @@ static int launch_debye2_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
     const int gy = (nchunk + h->nw_max - 1) / h->nw_max;
     const int nw = (nchunk + gy - 1) / gy;
     dim3 grid((unsigned)nblocks, (unsigned)gy, 1), block(32 * nw, 1, 1);
-    const size_t smem = 2 * debye2_buf_bytes(nw);
     if (h->timing) CU(cudaEventRecord(h->ev0, st));
-    if (nw <= 8) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, 256, CHEB>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done = true;
-        }
-        debye2_kernel<C, MODE, 256, CHEB><<<grid, block, smem, st>>>(p);
+    int rc;
+    if constexpr (MODE == MODE_GRAD) {
+        // 4C accumulators: one block of <= 8 warps (255 registers) or <= 12 (168)
+        rc = nw <= 8 ? launch_debye2_v<C, MODE, 256, 1, 16, CHEB>(h, p, grid, block, nw, st)
+                     : launch_debye2_v<C, MODE, 384, 1, 8, CHEB>(h, p, grid, block, nw, st);
     } else {
-        static bool attr_done = false;
-        if (!attr_done) {
-            CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, 384, CHEB>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done = true;
-        }
-        debye2_kernel<C, MODE, 384, CHEB><<<grid, block, smem, st>>>(p);
+        // F(Q) / force: few accumulators, short dependent chains -> two blocks
+        // per SM (8-j tiles keep two blocks' pair tables in shared memory)
+        rc = nw <= 8 ? launch_debye2_v<C, MODE, 256, 2, 8, CHEB>(h, p, grid, block, nw, st)
+                     : launch_debye2_v<C, MODE, 384, 1, 8, CHEB>(h, p, grid, block, nw, st);
     }
+    if (rc) return rc;
     ++h->launches;
     CU(cudaGetLastError());
     if (h->timing) {

@@ -30,12 +30,17 @@
 
 namespace iid {
 
-constexpr int TJ2 = 16;  // j atoms per produced tile
 constexpr int NREC = 10;  // floats per pair record shared by all warps
 
-__host__ __device__ inline size_t debye2_buf_bytes(int nwarp)
+// TJ2 = j atoms per produced tile (template parameter of the kernel)
+__host__ __device__ inline size_t debye2_buf_bytes(int nwarp, int tj)
 {
-    return (size_t)TJ2 * 32 * sizeof(float) * (NREC + 4 * (size_t)nwarp);
+    return (size_t)tj * 32 * sizeof(float) * (NREC + 4 * (size_t)nwarp);
+}
+// MODE_FORCE keeps the per-(pair, warp) scalars of one tile for the j-side sum
+__host__ __device__ inline size_t debye2_phi_bytes(int nwarp, int tj)
+{
+    return (size_t)tj * 32 * sizeof(float) * (size_t)nwarp;
 }
 
 // sin, cos of 2 pi u for any u >= 0 held in float64: quadrant in float64,
@@ -62,11 +67,10 @@ __device__ __forceinline__ void sincos_turns(double u, float &s, float &c)
 // second one is the half-chunk seed rotated by C/4 bins) and takes its first
 // step with the rotation; over 8 bins the error is 1.3-2.5e-7 rms, the same
 // as the rotation ("recurrences").
-template <int C, int MODE, int MAXT, bool CHEB>
-__global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
+template <int C, int MODE, int MAXT, int MINB, int TJ2, bool CHEB>
+__global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double sfj[MODE == MODE_FORCE ? 2 * 3 * TJ2 : 1];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -89,7 +93,9 @@ __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
     const float *inv_na = reinterpret_cast<const float *>(p.inv_na);
 
     constexpr int NPAIR = TJ2 * 32;
-    const size_t buf_bytes = debye2_buf_bytes(nwarp);
+    const size_t buf_bytes = debye2_buf_bytes(nwarp, TJ2);
+    float *phis = reinterpret_cast<float *>(smem_raw + 2 * buf_bytes);  // MODE_FORCE
+    const int nactive = min(nwarp, (p.nq - chunk0 * C + C - 1) / C);
     // structure of arrays, [field][jj][lane]: scalar, conflict-free loads that
     // leave the register allocator free to keep the FFMA operand pairs in
     // opposite register banks (vector loads would pin their parities)
@@ -122,8 +128,6 @@ __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
             w1[k] = make_float2(w[0] * (float)(m0 + k), w[1] * (float)(m0 + H + k));
         }
     }
-    if constexpr (MODE == MODE_FORCE)
-        for (int t = threadIdx.x; t < 2 * 3 * TJ2; t += blockDim.x) sfj[t] = 0.0;
 
     // ---- producer: the pair records of one j tile -----------------------------
     auto produce = [&](int jt, int b) {
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
     };
 
     // ---- consumer: this warp's chunk of bins for pairs (lane, jj) --------------
-    auto consume = [&](int b, int jlo, int jhi, int fbuf) {
+    auto consume = [&](int b, int jlo, int jhi) {
         const float *T = tab(b) + lane;
         const float2 *S2 = reinterpret_cast<const float2 *>(tab(b) + NREC * NPAIR) +
                            (2 * warp) * NPAIR + lane;
@@ -262,16 +266,27 @@ __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
                 fix = fmaf(phi, dx, fix);
                 fiy = fmaf(phi, dy, fiy);
                 fiz = fmaf(phi, dz, fiz);
-                if (!diag) {
-                    const float jx = warp_sum(-phi * dx);
-                    const float jy = warp_sum(-phi * dy);
-                    const float jz = warp_sum(-phi * dz);
-                    if (lane == 0) {
-                        atomicAdd(&sfj[fbuf * 3 * TJ2 + 3 * jj], (double)jx);
-                        atomicAdd(&sfj[fbuf * 3 * TJ2 + 3 * jj + 1], (double)jy);
-                        atomicAdd(&sfj[fbuf * 3 * TJ2 + 3 * jj + 2], (double)jz);
-                    }
-                }
+                // the j atom's share is summed over warps and lanes once per
+                // tile (reduce_j below) from this scalar
+                if (!diag) phis[warp * NPAIR + jj * 32 + lane] = phi;
+            }
+        }
+    };
+
+    // ---- MODE_FORCE: Newton's third law for the j atoms of one tile -----------
+    auto reduce_j = [&](int b, int jt) {
+        const float *T = tab(b) + lane;
+        for (int jj = warp; jj < TJ2; jj += nwarp) {
+            float phi = 0.f;
+            for (int w = 0; w < nactive; ++w) phi += phis[w * NPAIR + jj * 32 + lane];
+            const float jx = warp_sum(-phi * T[4 * NPAIR + jj * 32]);
+            const float jy = warp_sum(-phi * T[5 * NPAIR + jj * 32]);
+            const float jz = warp_sum(-phi * T[6 * NPAIR + jj * 32]);
+            const int oj = p.orig[jt + jj];
+            if (lane == 0 && oj >= 0) {
+                atomicAdd(&p.force[(size_t)oj * 3 + 0], (double)jx);
+                atomicAdd(&p.force[(size_t)oj * 3 + 1], (double)jy);
+                atomicAdd(&p.force[(size_t)oj * 3 + 2], (double)jz);
             }
         }
     };
@@ -287,17 +302,14 @@ __global__ void __launch_bounds__(MAXT, 1) debye2_kernel(const DebyeParams p)
         const bool has_next = t + 1 < ntile;
         const int jnext = it.jbegin + (t + 1) * TJ2;
         if (has_next && early) produce(jnext, b ^ 1);
-        if (active) consume(b, 0, TJ2 / 2, b);
+        if (active) consume(b, 0, TJ2 / 2);
         if (has_next && !early) produce(jnext, b ^ 1);
-        if (active) consume(b, TJ2 / 2, TJ2, b);
+        if (active) consume(b, TJ2 / 2, TJ2);
         __syncthreads();
         if constexpr (MODE == MODE_FORCE) {
-            if (!diag && threadIdx.x < 3 * TJ2) {
-                const int k = threadIdx.x;
-                const int oj = p.orig[it.jbegin + t * TJ2 + k / 3];
-                const double v = sfj[b * 3 * TJ2 + k];
-                sfj[b * 3 * TJ2 + k] = 0.0;
-                if (oj >= 0) atomicAdd(&p.force[(size_t)oj * 3 + k % 3], v);
+            if (!diag) {
+                reduce_j(b, it.jbegin + t * TJ2);
+                __syncthreads();  // records of buffer b are rewritten next iteration
             }
         }
     }
