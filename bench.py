@@ -397,11 +397,11 @@ def main():
     achieved = (pairq / world) / (kernel_ms_avg * 1e-3)
     roofline = {
         'bound': 'fp32_fma+sfu (no tensor cores, HBM negligible: SURVEY.md 8d)',
-        'kernel': 'iid::debye_kernel<float, 32, MODE_GRAD>',
+        'kernel': 'iid::debye2_kernel<32, MODE_GRAD, 256, 1, 16, CHEB>',
         'achieved': achieved, 'peak': peak_pairq, 'unit': UNIT, 'frac': achieved / peak_pairq,
         'peak_how': '%d SMs x %.0f MHz (max SM clock, MEASURED_PEAKS.json / nvidia-smi) x 8 pair*Q/clk/SM '
                     '= min(SFU 16/clk / 2, FP32 128/clk / 12); algorithmic count, our kernel replaces '
-                    'the SFU sin/cos by an FP32 rotation recurrence' % (sm_count.value, sm_max_mhz),
+                    'the SFU sin/cos by FP32 recurrences' % (sm_count.value, sm_max_mhz),
         'kernel_ms': kernel_ms_avg,
         'achieved_tflops': achieved * FLOP_PER_PAIRQ / 1e12,
         'peak_tflops_fp32': sm_count.value * 128 * 2 * sm_max_mhz * 1e6 / 1e12,
@@ -440,7 +440,7 @@ def main():
 
 # dram bytes (read + write) of one MODE_GRAD launch at the bench workload, from
 # the ncu --set full capture summarised in profiles/; None until measured there.
-TRAFFIC_BYTES = None
+TRAFFIC_BYTES = 555.9e6  # profiles/r1_ncu_full_grad50k_metrics.csv: 301.7 MB read + 254.3 MB write
 
 if __name__ == '__main__':
     main()
