@@ -70,6 +70,13 @@ class Atom(object):
         return chemical_symbols[self.number]
 
 
+# Per-atom scatter-factor tables are written once by ElasticScatter._wrap_atoms
+# (always replaced wholesale, never edited in place) and are by far the largest
+# arrays on the object; copies of an Atoms share them instead of duplicating
+# them on every leapfrog (pyiid/sim/__init__.py:29 deep-copies the atoms).
+SHARED_ARRAYS = ('F(Q) scatter', 'PDF scatter')
+
+
 class Atoms(object):
     def __init__(self, symbols=None, positions=None, numbers=None, cell=None,
                  pbc=False, momenta=None, calculator=None, info=None):
@@ -150,7 +157,9 @@ class Atoms(object):
     def get_masses(self):
         if 'masses' in self.arrays:
             return self.arrays['masses'].copy()
-        return np.array([_mass(z) for z in self.arrays['numbers']])
+        numbers = self.arrays['numbers']
+        zs, inv = np.unique(numbers, return_inverse=True)
+        return np.array([_mass(z) for z in zs])[inv.reshape(-1)]
 
     def set_masses(self, masses):
         self.set_array('masses', masses, float)
@@ -195,7 +204,13 @@ class Atoms(object):
                              cell=self.cell.copy(), pbc=self.pbc.copy(),
                              info=copy.deepcopy(self.info))
         for k, v in self.arrays.items():
-            new.arrays[k] = v.copy()
+            new.arrays[k] = v if k in SHARED_ARRAYS else v.copy()
+        return new
+
+    def __deepcopy__(self, memo):
+        new = self.copy()
+        memo[id(self)] = new
+        new._calc = copy.deepcopy(self._calc, memo)
         return new
 
     def __add__(self, other):

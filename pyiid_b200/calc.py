@@ -15,6 +15,7 @@ properties are cached for that configuration; the reference runs
 pair of experiment functions takes the generic route below; its reductions
 also run on the device.
 """
+import copy
 import ctypes
 
 import numpy as np
@@ -127,6 +128,32 @@ class Calc1D(Calculator):
         scat = _bound_to(exp_function, 'get_pdf')
         self._fused = scat if (scat is not None and scat is _bound_to(
             exp_grad_function, 'get_grad_pdf')) else None
+
+    def __deepcopy__(self, memo):
+        """Copies share the target data and the ElasticScatter (and through it
+        the native handle); only the results cache and the reference atoms are
+        private.  leapfrog deep-copies atoms + calculator on every step."""
+        new = copy.copy(self)
+        memo[id(self)] = new
+        new.results = {k: (v.copy() if isinstance(v, np.ndarray) else v)
+                       for k, v in self.results.items()}
+        new.atoms = None if self.atoms is None else self.atoms.copy()
+        if hasattr(self, 'parameters'):
+            new.parameters = copy.copy(self.parameters)
+        return new
+
+    def check_state(self, atoms, tol=1e-15):
+        """F(Q), G(r) and therefore Rw/chi^2 and the forces are invariant under
+        rigid translation; leapfrog re-centres the atoms after its last force
+        evaluation (pyiid/sim/__init__.py:36-37), which must not invalidate
+        the cached results."""
+        changes = Calculator.check_state(self, atoms, tol)
+        if changes == ['positions'] and self.atoms is not None and \
+                len(self.atoms) == len(atoms) and len(atoms) > 0:
+            old, new = self.atoms.positions, atoms.positions
+            if np.allclose(new - new[0], old - old[0], rtol=0., atol=1e-10):
+                return []
+        return changes
 
     def calculate(self, atoms=None, properties=['energy'],
                   system_changes=['positions', 'numbers', 'cell', 'pbc',
