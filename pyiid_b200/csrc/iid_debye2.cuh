@@ -155,14 +155,9 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
             const float b3 = invr * invr * invr;
             s *= b3;
             c *= b3;
-            T[pr] = cth;
-            T[NPAIR + pr] = sth;
-            T[2 * NPAIR + pr] = (float)(p.qbin * r);
-            T[3 * NPAIR + pr] = r2f;
-            T[4 * NPAIR + pr] = (float)dxd;
-            T[5 * NPAIR + pr] = (float)dyd;
-            T[6 * NPAIR + pr] = (float)dzd;
-            T[7 * NPAIR + pr] = cQ;
+            float4 *RA = reinterpret_cast<float4 *>(T);
+            RA[pr] = make_float4(cth, sth, (float)(p.qbin * r), r2f);
+            RA[NPAIR + pr] = make_float4((float)dxd, (float)dyd, (float)dzd, cQ);
             T[8 * NPAIR + pr] = sQ;
             float2 *S2 = reinterpret_cast<float2 *>(S);
             for (int w = 0; w < nwarp; ++w) {
@@ -177,27 +172,30 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
     };
 
     // ---- consumer: this warp's chunk of bins for pairs (lane, jj) --------------
-    auto consume = [&](int b, int jlo, int jhi) {
-        const float *T = tab(b) + lane;
-        const float2 *S2 = reinterpret_cast<const float2 *>(tab(b) + NREC * NPAIR) +
-                           (2 * warp) * NPAIR + lane;
-        float n_cth = T[jlo * 32], n_sth = T[NPAIR + jlo * 32], n_kap = T[2 * NPAIR + jlo * 32],
-              n_r2 = T[3 * NPAIR + jlo * 32], n_dx = T[4 * NPAIR + jlo * 32],
-              n_dy = T[5 * NPAIR + jlo * 32], n_dz = T[6 * NPAIR + jlo * 32],
-              n_cq = T[7 * NPAIR + jlo * 32], n_sq = T[8 * NPAIR + jlo * 32];
-        float2 n_s = S2[jlo * 32], n_c = S2[NPAIR + jlo * 32];
-        for (int jj = jlo; jj < jhi; ++jj) {
-            const float cth = n_cth, sth = n_sth, kap = n_kap, r2 = n_r2;
-            const float dx = n_dx, dy = n_dy, dz = n_dz, cq = n_cq, sq = n_sq;
-            float2 s = n_s, c = n_c;
-            {   // prefetch the next pair's record
-                const int jn = min(jj + 1, jhi - 1) * 32;
-                n_cth = T[jn]; n_sth = T[NPAIR + jn]; n_kap = T[2 * NPAIR + jn];
-                n_r2 = T[3 * NPAIR + jn]; n_dx = T[4 * NPAIR + jn];
-                n_dy = T[5 * NPAIR + jn]; n_dz = T[6 * NPAIR + jn];
-                if constexpr (CHEB) { n_cq = T[7 * NPAIR + jn]; n_sq = T[8 * NPAIR + jn]; }
-                n_s = S2[jn]; n_c = S2[NPAIR + jn];
-            }
+    // one pair record as the consumer holds it in registers
+    struct Rec {
+        float4 a;   // cos(theta), sin(theta), kappa, r^2
+        float4 b;   // dx, dy, dz, cos(HQ theta)
+        float sq;   // sin(HQ theta)
+        float2 s, c;  // seeds of this warp's two half-chunks
+    };
+    auto load_rec = [&](int b, int jj) {
+        Rec r;
+        const float *T = tab(b);
+        const float4 *RA = reinterpret_cast<const float4 *>(T) + jj * 32 + lane;
+        const float2 *S2 = reinterpret_cast<const float2 *>(T + NREC * NPAIR) +
+                           (2 * warp) * NPAIR + jj * 32 + lane;
+        r.a = RA[0];
+        r.b = RA[NPAIR];
+        r.sq = CHEB ? T[8 * NPAIR + jj * 32 + lane] : 0.f;
+        r.s = S2[0];
+        r.c = S2[NPAIR];
+        return r;
+    };
+    auto bins = [&](const Rec &rec, int jj) {
+        const float cth = rec.a.x, sth = rec.a.y, kap = rec.a.z, r2 = rec.a.w;
+        const float dx = rec.b.x, dy = rec.b.y, dz = rec.b.z, cq = rec.b.w, sq = rec.sq;
+        float2 s = rec.s, c = rec.c;
             const float2 cth2 = make_float2(cth, cth), sth2 = make_float2(sth, sth),
                          nsth2 = make_float2(-sth, -sth), r22 = make_float2(r2, r2),
                          kap2 = make_float2(kap, kap);
@@ -270,18 +268,30 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
                 // tile (reduce_j below) from this scalar
                 if (!diag) phis[warp * NPAIR + jj * 32 + lane] = phi;
             }
+    };
+    // two pairs per trip with ping-pong register sets: the record of the next
+    // pair is in flight while the bin loop of the current one runs
+    auto consume = [&](int b) {
+        Rec r0 = load_rec(b, 0);
+#pragma unroll 1
+        for (int jj = 0; jj < TJ2; jj += 2) {
+            Rec r1 = load_rec(b, jj + 1);
+            bins(r0, jj);
+            r0 = load_rec(b, min(jj + 2, TJ2 - 1));
+            bins(r1, jj + 1);
         }
     };
 
     // ---- MODE_FORCE: Newton's third law for the j atoms of one tile -----------
     auto reduce_j = [&](int b, int jt) {
-        const float *T = tab(b) + lane;
+        const float4 *RB = reinterpret_cast<const float4 *>(tab(b)) + NPAIR + lane;
         for (int jj = warp; jj < TJ2; jj += nwarp) {
             float phi = 0.f;
             for (int w = 0; w < nactive; ++w) phi += phis[w * NPAIR + jj * 32 + lane];
-            const float jx = warp_sum(-phi * T[4 * NPAIR + jj * 32]);
-            const float jy = warp_sum(-phi * T[5 * NPAIR + jj * 32]);
-            const float jz = warp_sum(-phi * T[6 * NPAIR + jj * 32]);
+            const float4 d = RB[jj * 32];  // dx, dy, dz of pair (lane, jj)
+            const float jx = warp_sum(-phi * d.x);
+            const float jy = warp_sum(-phi * d.y);
+            const float jz = warp_sum(-phi * d.z);
             const int oj = p.orig[jt + jj];
             if (lane == 0 && oj >= 0) {
                 atomicAdd(&p.force[(size_t)oj * 3 + 0], (double)jx);
@@ -292,8 +302,8 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
     };
 
     const int ntile = (it.jend - it.jbegin) / TJ2;  // slabs are multiples of 32
-    // warps w and w+4 share a scheduler: stagger their producer phases so one
-    // of them always feeds the FP32 pipe
+    // warps w and w+4 share a scheduler: one produces the next tile before its
+    // consume phase, the other after it, so one of them always feeds the FP32 pipe
     const bool early = ((warp >> 2) & 1) == 0;
     produce(it.jbegin, 0);
     __syncthreads();
@@ -302,9 +312,8 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
         const bool has_next = t + 1 < ntile;
         const int jnext = it.jbegin + (t + 1) * TJ2;
         if (has_next && early) produce(jnext, b ^ 1);
-        if (active) consume(b, 0, TJ2 / 2);
+        if (active) consume(b);
         if (has_next && !early) produce(jnext, b ^ 1);
-        if (active) consume(b, TJ2 / 2, TJ2);
         __syncthreads();
         if constexpr (MODE == MODE_FORCE) {
             if (!diag) {
