@@ -1,0 +1,70 @@
+"""Two-process NCCL run of the sharded path (needs >= 2 GPUs; skipped on a
+single-GPU box).  Each rank computes its slice of the pair-tile work list and
+the all-reduced results must equal the oracle / the single-GPU results."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ['IID_ROOT'])
+import torch, torch.distributed as dist
+rank = int(os.environ['RANK']); local = int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+import oracle
+from pyiid_b200 import ElasticScatter, Calc1D, structures
+def nerr(a, b):
+    return float(np.abs(np.asarray(a, float) - b).max() / np.abs(b).max())
+atoms = structures.alloy_sphere(300, seed=4)
+ideal = structures.alloy_sphere(300, seed=4, sigma=0.0)
+exp = oracle.DEFAULT_EXP
+for prec, tol in (('fp32', 1e-5), ('fp64', 1e-10)):
+    scat = ElasticScatter(precision=prec)
+    fq = scat.get_fq(atoms); grad = scat.get_grad_fq(atoms); pdf = scat.get_pdf(atoms)
+    assert scat.backend.world == 2
+    pos = atoms.get_positions()
+    opos = pos.astype(np.float32) if prec == 'fp32' else pos
+    sf, sp = atoms.get_array('F(Q) scatter'), atoms.get_array('PDF scatter')
+    assert nerr(fq, oracle.experiment_fq(opos, sf, exp, 'fp64')) < tol
+    assert nerr(grad, oracle.experiment_grad_fq(opos, sf, exp, 'fp64')) < tol
+    assert nerr(pdf, oracle.experiment_pdf(opos, sp, exp, 'fp64')) < tol
+    target = scat.get_pdf(ideal)
+    a = atoms.copy()
+    a.set_calculator(Calc1D(target_data=target, exp_function=scat.get_pdf,
+                            exp_grad_function=scat.get_grad_pdf, conv=10., potential='rw'))
+    e, f = a.get_potential_energy(), a.get_forces()
+    oe, of, _ = oracle.calc1d_energy_forces(opos, sp, exp, target, 'rw', 10., 'fp64')
+    assert abs(e - oe) < tol * abs(oe), (e, oe)
+    assert nerr(f, of) < 10 * tol
+    # every rank holds the same reduced result
+    t = torch.tensor(np.concatenate([fq.astype(np.float64), f.ravel()]), device='cuda')
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi)
+dist.barrier()
+if rank == 0:
+    print('MULTIGPU_OK')
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_nccl_results_match_the_oracle(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER)
+    env = dict(os.environ, IID_ROOT=ROOT)
+    out = subprocess.run(
+        [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+         '--master-addr', '127.0.0.1', '--master-port', '29533', str(script)],
+        env=env, capture_output=True, text=True, timeout=600)
+    assert 'MULTIGPU_OK' in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
