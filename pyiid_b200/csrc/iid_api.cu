@@ -82,6 +82,13 @@ struct iid_handle {
     int nw_max = 8;
     int slab_override = 0;
     bool use_v1 = false;
+    // CUDA graph of the fused energy+forces sequence (small-N latency)
+    cudaGraphExec_t ef_graph = nullptr;
+    int ef_key_pot = -1;
+    double ef_key_conv = 0.0;
+    bool ef_key_pdf = false;
+    int ef_warm = 0;
+    bool use_graph = true;
     bool cheb = true;
     // instrumentation
     int64_t launches = 0;
@@ -143,6 +150,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_NW")) h->nw_max = std::max(1, std::min(12, atoi(s)));
     h->nw_max = std::min(h->nw_max, 12);
     if (const char *s = getenv("IID_V1")) h->use_v1 = atoi(s) != 0;
+    if (const char *s = getenv("IID_GRAPH")) h->use_graph = atoi(s) != 0;
     if (const char *s = getenv("IID_CHEB")) h->cheb = atoi(s) != 0;
     if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
     *out = h;
@@ -162,6 +170,7 @@ extern "C" int iid_destroy(iid_handle *h)
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ef_graph) cudaGraphExecDestroy(h->ef_graph);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -181,11 +190,21 @@ extern "C" int iid_synchronize(iid_handle *h)
     return 0;
 }
 
+static void drop_graph(iid_handle *h)
+{
+    if (h->ef_graph) {
+        cudaGraphExecDestroy(h->ef_graph);
+        h->ef_graph = nullptr;
+    }
+    h->ef_warm = 0;
+}
+
 extern "C" int iid_set_shard(iid_handle *h, int rank, int world)
 {
     if (!h) return fail(IID_E_BADARG, "null handle");
     if (world < 1 || rank < 0 || rank >= world)
         return fail(IID_E_BADARG, "need 0 <= rank < world");
+    if (rank != h->rank || world != h->world) drop_graph(h);
     h->rank = rank;
     h->world = world;
     return 0;
@@ -324,6 +343,7 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
     if (n < 1 || n_types < 1 || nq < 1 || !type_index || !ftable)
         return fail(IID_E_BADARG, "bad structure arguments");
     CU(cudaStreamSynchronize(h->stream));
+    drop_graph(h);
     Layout L;
     {
         int rc0 = build_layout(n, type_index, n_types, h->sm_count, h->slab_override, L);
@@ -406,6 +426,7 @@ extern "C" int iid_set_transform(iid_handle *h, int64_t nr, int64_t nq, const do
     if (nq != h->nq) return fail(IID_E_BADARG, "transform nq differs from structure nq");
     if (nr < 1 || !T) return fail(IID_E_BADARG, "bad transform arguments");
     CU(cudaStreamSynchronize(h->stream));
+    drop_graph(h);
     int rc;
     if ((rc = dev_alloc(&h->T, (size_t)nr * h->qp)) || (rc = dev_alloc(&h->Gr, nr)) ||
         (rc = dev_alloc(&h->cr, nr)) || (rc = dev_alloc(&h->target, nr)))
@@ -649,7 +670,7 @@ extern "C" int iid_potential(iid_handle *h, const double *G_dev, const double *t
     CU(cudaGetLastError());
     if (wq_dev) {
         CU(cudaMemsetAsync(wq_dev, 0, h->nq * sizeof(double), st));
-        wq_kernel<<<(unsigned)((h->nr + WQ_ROWS - 1) / WQ_ROWS), 128, 0, st>>>(
+        wq_kernel<<<(unsigned)((h->nr + WQ_ROWS - 1) / WQ_ROWS), 352, 0, st>>>(
             h->T, h->cr, (int)h->nr, (int)h->nq, (int)h->qp, conv, wq_dev);
         ++h->launches;
         CU(cudaGetLastError());
@@ -776,24 +797,68 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
         CU(cudaMemcpyAsync(h->target, pt, h->nr * sizeof(double), cudaMemcpyHostToDevice,
                            h->stream));
     }
-    if ((rc = upload_positions(h, pos_host))) return rc;
-    if ((rc = iid_fq_partial(h, h->pos, h->S, nullptr))) return rc;
-    if ((rc = iid_fq_finish(h, h->S, h->F, nullptr))) return rc;
-    if ((rc = iid_fq_to_gr(h, h->F, h->Gr, nullptr))) return rc;
-    if ((rc = iid_potential(h, h->Gr, h->target, potential, conv, h->out4,
-                            forces_host ? h->wq : nullptr, nullptr)))
-        return rc;
-    if (forces_host) {
-        // positions are already staged by iid_fq_partial; enqueue the force pass
-        CU(cudaMemsetAsync(h->force, 0, (size_t)h->n * 3 * sizeof(double), h->stream));
-        if ((rc = launch_debye(h, MODE_FORCE, nullptr, nullptr, h->wq, h->force, h->stream)))
-            return rc;
-        CU(cudaMemcpyAsync(pfor, h->force, (size_t)3 * h->n * sizeof(double),
-                           cudaMemcpyDeviceToHost, h->stream));
+    // The whole sequence (H2D, 7 kernels, 3 memsets, D2H) is replayed from a
+    // CUDA graph once it has run twice with the same shape: at a few hundred
+    // atoms the evaluation is bound by launch latency, not by arithmetic.
+    const bool graphable = h->use_graph && !h->timing && forces_host != nullptr;
+    if (graphable && h->ef_graph &&
+        (h->ef_key_pot != potential || h->ef_key_conv != conv || h->ef_key_pdf != (pdf_host != nullptr)))
+        drop_graph(h);
+    memcpy(h->pin, pos_host, (size_t)3 * h->n * sizeof(double));
+    auto enqueue = [&]() -> int {
+        int rc2;
+        CU(cudaMemcpyAsync(h->pos, h->pin, (size_t)3 * h->n * sizeof(double),
+                           cudaMemcpyHostToDevice, h->stream));
+        if ((rc2 = iid_fq_partial(h, h->pos, h->S, nullptr))) return rc2;
+        if ((rc2 = iid_fq_finish(h, h->S, h->F, nullptr))) return rc2;
+        if ((rc2 = iid_fq_to_gr(h, h->F, h->Gr, nullptr))) return rc2;
+        if ((rc2 = iid_potential(h, h->Gr, h->target, potential, conv, h->out4,
+                                 forces_host ? h->wq : nullptr, nullptr)))
+            return rc2;
+        if (forces_host) {
+            // positions are already staged by iid_fq_partial; enqueue the force pass
+            CU(cudaMemsetAsync(h->force, 0, (size_t)h->n * 3 * sizeof(double), h->stream));
+            if ((rc2 = launch_debye(h, MODE_FORCE, nullptr, nullptr, h->wq, h->force, h->stream)))
+                return rc2;
+            CU(cudaMemcpyAsync(pfor, h->force, (size_t)3 * h->n * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->stream));
+        }
+        CU(cudaMemcpyAsync(po, h->out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (pdf_host)
+            CU(cudaMemcpyAsync(pg, h->Gr, h->nr * sizeof(double), cudaMemcpyDeviceToHost,
+                               h->stream));
+        return 0;
+    };
+    if (graphable && h->ef_graph) {
+        CU(cudaGraphLaunch(h->ef_graph, h->stream));
+        h->launches += 7;
+    } else if (graphable && h->ef_warm >= 2) {
+        cudaGraph_t graph = nullptr;
+        const int64_t launches0 = h->launches;
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue();
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        h->launches = launches0;
+        if (rc == 0 && ce == cudaSuccess && graph &&
+            cudaGraphInstantiate(&h->ef_graph, graph, 0) == cudaSuccess) {
+            h->ef_key_pot = potential;
+            h->ef_key_conv = conv;
+            h->ef_key_pdf = pdf_host != nullptr;
+            cudaGraphDestroy(graph);
+            CU(cudaGraphLaunch(h->ef_graph, h->stream));
+            h->launches += 7;
+        } else {
+            // capture refused: fall back to plain launches for good
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            h->ef_graph = nullptr;
+            h->use_graph = false;
+            if ((rc = enqueue())) return rc;
+        }
+    } else {
+        if ((rc = enqueue())) return rc;
+        ++h->ef_warm;
     }
-    CU(cudaMemcpyAsync(po, h->out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (pdf_host)
-        CU(cudaMemcpyAsync(pg, h->Gr, h->nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     memcpy(out_host, po, 4 * sizeof(double));
     if (forces_host) memcpy(forces_host, pfor, (size_t)3 * h->n * sizeof(double));

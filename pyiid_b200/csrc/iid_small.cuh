@@ -149,19 +149,28 @@ __global__ void potential_kernel(const double *__restrict__ gc,
     }
 }
 
-// wq[m] = conv * sum_r c[r] T[r][m]; block = slab of RS rows, thread = m.
-constexpr int WQ_ROWS = 32;
+// wq[m] = conv * sum_r c[r] T[r][m].  Block = slab of WQ_ROWS rows, thread =
+// one m (coalesced along m), four independent partial sums per thread; the
+// slab partials meet in one double atomicAdd per (slab, m).  Few, fat slabs:
+// same-address double atomics serialise at ~0.2 us each in L2.
+constexpr int WQ_ROWS = 128;
 __global__ void wq_kernel(const double *__restrict__ T,
                           const double *__restrict__ cr, int nr, int nq, int qp,
                           double conv, double *__restrict__ wq)
 {
-    const int m = threadIdx.x;
     const int r0 = blockIdx.x * WQ_ROWS;
     const int r1 = min(nr, r0 + WQ_ROWS);
-    for (int mm = m; mm < nq; mm += blockDim.x) {
-        double acc = 0.0;
-        for (int r = r0; r < r1; ++r) acc = fma(cr[r], T[(size_t)r * qp + mm], acc);
-        atomicAdd(&wq[mm], conv * acc);
+    for (int mm = threadIdx.x; mm < nq; mm += blockDim.x) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int r = r0;
+        for (; r + 3 < r1; r += 4) {
+            a0 = fma(cr[r], T[(size_t)r * qp + mm], a0);
+            a1 = fma(cr[r + 1], T[(size_t)(r + 1) * qp + mm], a1);
+            a2 = fma(cr[r + 2], T[(size_t)(r + 2) * qp + mm], a2);
+            a3 = fma(cr[r + 3], T[(size_t)(r + 3) * qp + mm], a3);
+        }
+        for (; r < r1; ++r) a0 = fma(cr[r], T[(size_t)r * qp + mm], a0);
+        atomicAdd(&wq[mm], conv * ((a0 + a1) + (a2 + a3)));
     }
 }
 
