@@ -14,6 +14,7 @@
 
 #include "iid_debye.cuh"
 #include "iid_debye2.cuh"
+#include "iid_debye64.cuh"
 #include "iid_small.cuh"
 
 using namespace iid;
@@ -541,6 +542,37 @@ static int launch_debye2_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
     return 0;
 }
 
+// FP64: producer/consumer kernel (iid_debye64.cuh); IID_V1=1 selects the
+// per-warp set-up kernel of iid_debye.cuh.
+template <int C, int MODE>
+static int launch_debye64_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
+                            cudaStream_t st)
+{
+    constexpr int TJ = 8;
+    const int nchunk = (int)((h->nq + C - 1) / C);
+    const int nwmax = std::min(h->nw_max, 8);
+    const int gy = (nchunk + nwmax - 1) / nwmax;
+    const int nw = (nchunk + gy - 1) / gy;
+    dim3 grid((unsigned)nblocks, (unsigned)gy, 1), block(32 * nw, 1, 1);
+    const size_t smem = 2 * debye64_buf_bytes(nw, TJ) +
+                        (MODE == MODE_FORCE ? debye64_phi_bytes(nw, TJ) : 0);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU(cudaFuncSetAttribute(debye64_kernel<C, MODE, 256, TJ>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    if (h->timing) CU(cudaEventRecord(h->ev0, st));
+    debye64_kernel<C, MODE, 256, TJ><<<grid, block, smem, st>>>(p);
+    ++h->launches;
+    CU(cudaGetLastError());
+    if (h->timing) {
+        CU(cudaEventRecord(h->ev1, st));
+        h->ev_pending = true;
+    }
+    return 0;
+}
+
 constexpr int C32 = 32;  // Q bins per warp, float32 kernels
 constexpr int C64 = 16;  // Q bins per warp, float64 kernels
 
@@ -577,6 +609,11 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
         if (mode == MODE_FQ) return launch_debye_t<float, C32, MODE_FQ>(h, p, mine, st);
         if (mode == MODE_GRAD) return launch_debye_t<float, C32, MODE_GRAD>(h, p, mine, st);
         return launch_debye_t<float, C32, MODE_FORCE>(h, p, mine, st);
+    }
+    if (!h->use_v1) {
+        if (mode == MODE_FQ) return launch_debye64_t<C64, MODE_FQ>(h, p, mine, st);
+        if (mode == MODE_GRAD) return launch_debye64_t<C64, MODE_GRAD>(h, p, mine, st);
+        return launch_debye64_t<C64, MODE_FORCE>(h, p, mine, st);
     }
     if (mode == MODE_FQ) return launch_debye_t<double, C64, MODE_FQ>(h, p, mine, st);
     if (mode == MODE_GRAD) return launch_debye_t<double, C64, MODE_GRAD>(h, p, mine, st);

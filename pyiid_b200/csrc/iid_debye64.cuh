@@ -1,0 +1,256 @@
+// iid_debye64.cuh -- FP64 Debye-sum kernel, producer/consumer version (sm_100a).
+//
+// The float64 twin of iid_debye2.cuh: block = one (i-tile, j-slab) work item,
+// warp = Q chunk of C bins, lane = atom i, accumulators in registers; the
+// 32 x TJ pair records of a j tile (cos/sin theta, kappa, r^2, d, and one
+// (sin, cos)(m0 theta)/r^3 seed per warp) are produced once per block into
+// double-buffered shared memory.  Everything is float64 (there is no packed
+// DFMA and no FP64 SFU on sm_100; the bound is the 64 lane/clk/SM DFMA pipe).
+// Inside a chunk sin/cos advance by one rotation step from the seed and then
+// by the three-term recurrence x[k+1] = 2cos(theta) x[k] - x[k-1]; in float64
+// its rounding (1e-16 k / sin(theta)) is far below the 1e-10 tolerance, so no
+// re-seeding inside the chunk is needed.  F + grad F: 8 DFMA-class
+// instructions per bin per ordered pair.
+#pragma once
+#include "iid_debye.cuh"
+
+namespace iid {
+
+constexpr int NREC64 = 8;  // doubles per pair record shared by all warps
+
+__host__ __device__ inline size_t debye64_buf_bytes(int nwarp, int tj)
+{
+    return (size_t)tj * 32 * sizeof(double) * (NREC64 + 2 * (size_t)nwarp);
+}
+__host__ __device__ inline size_t debye64_phi_bytes(int nwarp, int tj)
+{
+    return (size_t)tj * 32 * sizeof(double) * (size_t)nwarp;
+}
+
+template <int C, int MODE, int MAXT, int TJ>
+__global__ void __launch_bounds__(MAXT, 1) debye64_kernel(const DebyeParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw64[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarp = blockDim.x >> 5;
+    const int chunk0 = blockIdx.y * nwarp;
+    const int m0 = (chunk0 + warp) * C;
+    const bool active = m0 < p.nq;
+
+    const WorkItem it = p.items[p.item_begin + (int64_t)blockIdx.x * p.item_stride];
+    const bool diag = (it.info & ITEM_DIAG) != 0;
+    const int btype = it.info & 0xffff;
+    const int atype = p.tile_type[it.itile];
+    const int gi = it.itile * TILE_I + lane;
+    const double xi = p.x[gi], yi = p.y[gi], zi = p.z[gi];
+    const bool vi = p.valid[gi] != 0.f;
+
+    const double *ftab = reinterpret_cast<const double *>(p.ftab);
+    const double *fa = ftab + (size_t)atype * p.qp;
+    const double *fb = ftab + (size_t)btype * p.qp;
+    const double *inv_na = reinterpret_cast<const double *>(p.inv_na);
+
+    constexpr int NPAIR = TJ * 32;
+    const size_t buf_bytes = debye64_buf_bytes(nwarp, TJ);
+    auto tab = [&](int b) { return reinterpret_cast<double2 *>(smem_raw64 + (size_t)b * buf_bytes); };
+    double *phis = reinterpret_cast<double *>(smem_raw64 + 2 * buf_bytes);  // MODE_FORCE
+    const int nactive = min(nwarp, (p.nq - chunk0 * C + C - 1) / C);
+
+    double accF[MODE != MODE_FORCE ? C : 1];
+    double accX[MODE == MODE_GRAD ? C : 1], accY[MODE == MODE_GRAD ? C : 1],
+        accZ[MODE == MODE_GRAD ? C : 1];
+    double w0[MODE == MODE_FORCE ? C : 1], w1[MODE == MODE_FORCE ? C : 1];
+    double fix = 0.0, fiy = 0.0, fiz = 0.0;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        if constexpr (MODE != MODE_FORCE) accF[k] = 0.0;
+        if constexpr (MODE == MODE_GRAD) { accX[k] = 0.0; accY[k] = 0.0; accZ[k] = 0.0; }
+        if constexpr (MODE == MODE_FORCE) {
+            const int bin = m0 + k;
+            double w = 0.0;
+            if (bin < p.nq) w = p.wq[bin] * fa[bin] * fb[bin] * inv_na[bin];
+            w0[k] = w;
+            w1[k] = w * (double)bin;
+        }
+    }
+
+    // ---- producer -----------------------------------------------------------------
+    // record layout (double2 arrays of NPAIR): [0] cos,sin theta  [1] kappa, r^2
+    // [2] dx, dy  [3] dz, -   then one (sin, cos) seed per warp
+    auto produce = [&](int jt, int b) {
+        double2 *T = tab(b);
+        for (int pr = threadIdx.x; pr < NPAIR; pr += blockDim.x) {
+            const int jj = pr >> 5;  // (pr & 31) == lane
+            const int gj = jt + jj;
+            const double dx = p.x[gj] - xi, dy = p.y[gj] - yi, dz = p.z[gj] - zi;
+            const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+            const bool ok = vi && p.valid[gj] != 0.f && r2 > 0.0;
+            const double r = sqrt(r2);
+            const double invr = ok ? 1.0 / r : 0.0;
+            const double u = r * p.qbin_turns;  // turns per Q bin
+            double sth, cth, sC, cC, s, c;
+            sincospi(2.0 * (u - rint(u)), &sth, &cth);
+            double ph = u * (double)C;
+            sincospi(2.0 * (ph - rint(ph)), &sC, &cC);
+            ph = u * (double)(chunk0 * C);
+            sincospi(2.0 * (ph - rint(ph)), &s, &c);
+            const double b3 = invr * invr * invr;
+            s *= b3;
+            c *= b3;
+            T[pr] = make_double2(cth, sth);
+            T[NPAIR + pr] = make_double2(p.qbin * r, r2);
+            T[2 * NPAIR + pr] = make_double2(dx, dy);
+            T[3 * NPAIR + pr] = make_double2(dz, 0.0);
+            for (int w = 0; w < nwarp; ++w) {
+                T[(4 + w) * NPAIR + pr] = make_double2(s, c);
+                const double sn = fma(s, cC, c * sC);
+                const double cn = fma(c, cC, -(s * sC));
+                s = sn;
+                c = cn;
+            }
+        }
+    };
+
+    struct Rec {
+        double2 cs, kr, dxy, dz, seed;
+    };
+    auto load_rec = [&](int b, int jj) {
+        Rec r;
+        const double2 *T = tab(b) + jj * 32 + lane;
+        r.cs = T[0];
+        r.kr = T[NPAIR];
+        r.dxy = T[2 * NPAIR];
+        r.dz = T[3 * NPAIR];
+        r.seed = T[(4 + warp) * NPAIR];
+        return r;
+    };
+    auto bins = [&](const Rec &rec, int jj) {
+        const double cth = rec.cs.x, sth = rec.cs.y, kap = rec.kr.x, r2 = rec.kr.y;
+        const double dx = rec.dxy.x, dy = rec.dxy.y, dz = rec.dz.x;
+        const double tc = cth + cth;
+        double s = rec.seed.x, c = rec.seed.y, sp = s, cp = c;
+        double mk = kap * (double)m0;
+        double p0[2] = {0.0, 0.0}, p1[2] = {0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            if constexpr (MODE != MODE_FORCE) accF[k] = fma(s, r2, accF[k]);
+            if constexpr (MODE == MODE_GRAD) {
+                const double a = fma(mk, c, -s);
+                accX[k] = fma(a, dx, accX[k]);
+                accY[k] = fma(a, dy, accY[k]);
+                accZ[k] = fma(a, dz, accZ[k]);
+                mk += kap;
+            }
+            if constexpr (MODE == MODE_FORCE) {
+                p1[k & 1] = fma(w1[k], c, p1[k & 1]);
+                p0[k & 1] = fma(w0[k], s, p0[k & 1]);
+            }
+            if (k + 1 < C) {
+                if (k == 0) {
+                    const double sn = fma(s, cth, c * sth);
+                    const double cn = fma(c, cth, -(s * sth));
+                    sp = s; cp = c; s = sn; c = cn;
+                } else {
+                    const double sn = fma(tc, s, -sp);
+                    sp = s;
+                    s = sn;
+                    if constexpr (MODE != MODE_FQ) {
+                        const double cn = fma(tc, c, -cp);
+                        cp = c;
+                        c = cn;
+                    }
+                }
+            }
+        }
+        if constexpr (MODE == MODE_FORCE) {
+            const double phi = fma(kap, p1[0] + p1[1], -(p0[0] + p0[1]));
+            fix = fma(phi, dx, fix);
+            fiy = fma(phi, dy, fiy);
+            fiz = fma(phi, dz, fiz);
+            if (!diag) phis[warp * NPAIR + jj * 32 + lane] = phi;
+        }
+    };
+    auto consume = [&](int b) {
+        Rec r0 = load_rec(b, 0);
+#pragma unroll 1
+        for (int jj = 0; jj < TJ; jj += 2) {
+            Rec r1 = load_rec(b, jj + 1);
+            bins(r0, jj);
+            r0 = load_rec(b, min(jj + 2, TJ - 1));
+            bins(r1, jj + 1);
+        }
+    };
+    auto reduce_j = [&](int b, int jt) {
+        const double2 *T = tab(b) + lane;
+        for (int jj = warp; jj < TJ; jj += nwarp) {
+            double phi = 0.0;
+            for (int w = 0; w < nactive; ++w) phi += phis[w * NPAIR + jj * 32 + lane];
+            const double2 dxy = T[2 * NPAIR + jj * 32];
+            const double2 dzz = T[3 * NPAIR + jj * 32];
+            const double jx = warp_sum(-phi * dxy.x);
+            const double jy = warp_sum(-phi * dxy.y);
+            const double jz = warp_sum(-phi * dzz.x);
+            const int oj = p.orig[jt + jj];
+            if (lane == 0 && oj >= 0) {
+                atomicAdd(&p.force[(size_t)oj * 3 + 0], jx);
+                atomicAdd(&p.force[(size_t)oj * 3 + 1], jy);
+                atomicAdd(&p.force[(size_t)oj * 3 + 2], jz);
+            }
+        }
+    };
+
+    const int ntile = (it.jend - it.jbegin) / TJ;  // slabs are multiples of 32
+    const bool early = ((warp >> 2) & 1) == 0;
+    produce(it.jbegin, 0);
+    __syncthreads();
+    for (int t = 0; t < ntile; ++t) {
+        const int b = t & 1;
+        const bool has_next = t + 1 < ntile;
+        const int jnext = it.jbegin + (t + 1) * TJ;
+        if (has_next && early) produce(jnext, b ^ 1);
+        if (active) consume(b);
+        if (has_next && !early) produce(jnext, b ^ 1);
+        __syncthreads();
+        if constexpr (MODE == MODE_FORCE) {
+            if (!diag) {
+                reduce_j(b, it.jbegin + t * TJ);
+                __syncthreads();
+            }
+        }
+    }
+
+    if (!active) return;
+    const int oi = p.orig[gi];
+    if constexpr (MODE == MODE_FORCE) {
+        if (oi >= 0) {
+            atomicAdd(&p.force[(size_t)oi * 3 + 0], fix);
+            atomicAdd(&p.force[(size_t)oi * 3 + 1], fiy);
+            atomicAdd(&p.force[(size_t)oi * 3 + 2], fiz);
+        }
+    } else {
+        const double fweight = (MODE == MODE_GRAD || diag) ? 0.5 : 1.0;
+        double *G = reinterpret_cast<double *>(p.G);
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int bin = m0 + k;
+            if (bin < p.nq) {  // warp-uniform
+                const double ff = fa[bin] * fb[bin];
+                if constexpr (MODE == MODE_GRAD) if (oi >= 0) {
+                    const double sc = ff * inv_na[bin];
+                    double *row = G + (size_t)oi * 3 * p.nq + bin;
+                    atomicAdd(row, accX[k] * sc);
+                    atomicAdd(row + p.nq, accY[k] * sc);
+                    atomicAdd(row + 2 * (size_t)p.nq, accZ[k] * sc);
+                }
+                if (p.S != nullptr) {
+                    const double v = warp_sum(accF[k] * ff);
+                    if (lane == 0) atomicAdd(&p.S[bin], fweight * v);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace iid
