@@ -184,6 +184,11 @@ int iid_contract_host(iid_handle *h, const void *A_host, int a_is_f32,
  * elasticscatter/__init__.py:371-390). */
 int iid_fq_to_gr_host(iid_handle *h, const double *F_host, double *pdf_host);
 
+/* Device array -> pageable host memory through pipelined pinned staging,
+ * ordered after the work already enqueued on the handle's stream; complete on
+ * return.  (The multi-GPU host layer uses it after the NCCL all-reduce.) */
+int iid_download_host(iid_handle *h, const void *dev, void *host, int64_t bytes);
+
 /* instrumentation ---------------------------------------------------------- */
 /* number of kernels this handle has launched since creation */
 int iid_launch_count(iid_handle *h, int64_t *count);

@@ -268,7 +268,8 @@ class Backend(object):
             dist.all_reduce(s)
             dist.all_reduce(gt)
             check(self.lib.iid_fq_finish(self.h, s.data_ptr(), ft.data_ptr(), st))
-            g = gt.cpu().numpy()
+            check(self.lib.iid_download_host(self.h, gt.data_ptr(), g.ctypes.data,
+                                             g.nbytes))
             f = ft.cpu().numpy()
         return (g, f) if with_fq else g
 
