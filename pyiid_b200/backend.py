@@ -12,6 +12,7 @@ all-reduced over NCCL.
 PyTorch is used only when world_size > 1 (device buffers for the collective);
 the single-GPU path talks to the library with numpy host buffers.
 """
+import atexit
 import ctypes
 import math
 import os
@@ -96,6 +97,18 @@ def element_table(scatter_array, numbers=None):
 class Backend(object):
     """One native handle on one GPU for one precision."""
     _instances = {}
+
+    @classmethod
+    def close_all(cls):
+        """Destroy every native handle (registered with atexit)."""
+        for inst in list(cls._instances.values()):
+            inst.close()
+        cls._instances.clear()
+
+    def close(self):
+        if self.h is not None and self.h.value:
+            self.lib.iid_destroy(self.h)
+            self.h = ctypes.c_void_p()
 
     @classmethod
     def get(cls, precision='fp32', device=None, slot='fq'):
@@ -415,3 +428,6 @@ class Backend(object):
         check(self.lib.iid_get_sizes(self.h, *[ctypes.byref(x) for x in v]))
         return dict(zip(('n', 'nq', 'nr', 'items_fq', 'items_grad'),
                         [x.value for x in v]))
+
+
+atexit.register(Backend.close_all)

@@ -510,11 +510,12 @@ static int launch_debye2_v(iid_handle *h, const DebyeParams &p, dim3 grid, dim3 
 {
     const size_t smem = 2 * debye2_buf_bytes(nw, TJ) +
                         (MODE == MODE_FORCE ? debye2_phi_bytes(nw, TJ) : 0);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // function attributes are per device: remember which devices are done
+    static bool attr_done[64] = {false};
+    if (!attr_done[h->device & 63]) {
         CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, MAXT, MINB, TJ, CHEB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done = true;
+        attr_done[h->device & 63] = true;
     }
     debye2_kernel<C, MODE, MAXT, MINB, TJ, CHEB><<<grid, block, smem, st>>>(p);
     return 0;
@@ -569,11 +570,11 @@ static int launch_debye64_t(iid_handle *h, const DebyeParams &p, int64_t nblocks
     dim3 grid((unsigned)nblocks, (unsigned)gy, 1), block(32 * nw, 1, 1);
     const size_t smem = 2 * debye64_buf_bytes(nw, TJ) +
                         (MODE == MODE_FORCE ? debye64_phi_bytes(nw, TJ) : 0);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {false};
+    if (!attr_done[h->device & 63]) {
         CU(cudaFuncSetAttribute(debye64_kernel<C, MODE, 256, TJ>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done = true;
+        attr_done[h->device & 63] = true;
     }
     if (h->timing) CU(cudaEventRecord(h->ev0, st));
     debye64_kernel<C, MODE, 256, TJ><<<grid, block, smem, st>>>(p);
