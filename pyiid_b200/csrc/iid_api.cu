@@ -88,7 +88,6 @@ struct iid_handle {
     int nw_max = 12;
     int slab_override = 0;
     bool use_v1 = false;
-    bool c24 = false;  // 24-bin chunks for the FP32 gradient (11-12 warps per block)
     // CUDA graph of the fused energy+forces sequence (small-N latency)
     cudaGraphExec_t ef_graph = nullptr;
     int ef_key_pot = -1;
@@ -157,7 +156,6 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_NW")) h->nw_max = std::max(1, std::min(12, atoi(s)));
     h->nw_max = std::min(h->nw_max, 12);
     if (const char *s = getenv("IID_V1")) h->use_v1 = atoi(s) != 0;
-    if (const char *s = getenv("IID_C24")) h->c24 = atoi(s) != 0;
     if (const char *s = getenv("IID_GRAPH")) h->use_graph = atoi(s) != 0;
     if (const char *s = getenv("IID_CHEB")) h->cheb = atoi(s) != 0;
     if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
@@ -532,7 +530,7 @@ static int launch_debye2_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
     // to 12 warps so that one block covers the whole PDF grid (11 chunks) and
     // the pair records are produced once, not once per chunk group.
     const int nchunk = (int)((h->nq + C - 1) / C);
-    const int nwmax = (MODE == MODE_GRAD && C >= 32) ? std::min(h->nw_max, 8) : h->nw_max;
+    const int nwmax = MODE == MODE_GRAD ? std::min(h->nw_max, 8) : h->nw_max;
     const int gy = (nchunk + nwmax - 1) / nwmax;
     const int nw = (nchunk + gy - 1) / gy;
     dim3 grid((unsigned)nblocks, (unsigned)gy, 1), block(32 * nw, 1, 1);
@@ -611,8 +609,6 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     const int64_t mine = nitems > h->rank ? (nitems - h->rank + h->world - 1) / h->world : 0;
     h->last_pairq = 0.5 * (double)h->n * (double)(h->n - 1) * (double)h->nq / h->world;
     if (mine == 0) return 0;
-    if (h->precision == IID_FP32 && !h->use_v1 && h->cheb && h->c24 && mode == MODE_GRAD)
-        return launch_debye2_t<24, MODE_GRAD, true>(h, p, mine, st);
     if (h->precision == IID_FP32 && !h->use_v1 && h->cheb) {
         if (mode == MODE_FQ) return launch_debye2_t<C32, MODE_FQ, true>(h, p, mine, st);
         if (mode == MODE_GRAD) return launch_debye2_t<C32, MODE_GRAD, true>(h, p, mine, st);
