@@ -38,6 +38,9 @@ def _mass(z):
     return _MASS.get(int(z), 2.5 * int(z))
 
 
+_MASS_CACHE = {}
+
+
 # ase.units (CODATA 2014 as in ASE 3.x)
 class units(object):
     kB = 8.6173303e-05
@@ -158,8 +161,15 @@ class Atoms(object):
         if 'masses' in self.arrays:
             return self.arrays['masses'].copy()
         numbers = self.arrays['numbers']
-        zs, inv = np.unique(numbers, return_inverse=True)
-        return np.array([_mass(z) for z in zs])[inv.reshape(-1)]
+        key = numbers.tobytes()
+        m = _MASS_CACHE.get(key)
+        if m is None:
+            zs, inv = np.unique(numbers, return_inverse=True)
+            m = np.array([_mass(z) for z in zs])[inv.reshape(-1)]
+            if len(_MASS_CACHE) > 64:
+                _MASS_CACHE.clear()
+            _MASS_CACHE[key] = m
+        return m.copy()
 
     def set_masses(self, masses):
         self.set_array('masses', masses, float)
@@ -199,12 +209,15 @@ class Atoms(object):
             p[:, a] += shift[a]
 
     def copy(self):
-        new = self.__class__(numbers=self.arrays['numbers'].copy(),
-                             positions=self.arrays['positions'].copy(),
-                             cell=self.cell.copy(), pbc=self.pbc.copy(),
-                             info=copy.deepcopy(self.info))
-        for k, v in self.arrays.items():
-            new.arrays[k] = v if k in SHARED_ARRAYS else v.copy()
+        new = object.__new__(self.__class__)
+        new.arrays = {k: (v if k in SHARED_ARRAYS else v.copy())
+                      for k, v in self.arrays.items()}
+        new.cell = self.cell.copy()
+        new.pbc = self.pbc.copy()
+        # info holds small bookkeeping (the experiment dict, counters)
+        new.info = {k: (dict(v) if isinstance(v, dict) else copy.deepcopy(v))
+                    for k, v in self.info.items()}
+        new._calc = None
         return new
 
     def __deepcopy__(self, memo):
