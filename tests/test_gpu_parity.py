@@ -416,3 +416,79 @@ def test_nuts_runs_on_the_device_calculator():
     assert meta['samples_total'] > 0 and len(traj) >= 1
     assert min(pe) <= e0
     assert all(np.isfinite(pe))
+
+
+# ---- randomised experiments and odd inputs (reference tests/__init__.py:117-128) -----
+def random_experiment(rs):
+    exp = {}
+    ranges = dict(qmin=(0, 1.5), qmax=(19., 25.), qbin=(.08, .12), rmin=(0., 2.5),
+                  rmax=(30., 50.), rstep=(.005, .015))
+    for k, (lo, hi) in ranges.items():
+        exp[k] = float(rs.uniform(lo, hi))
+    exp['sampling'] = str(rs.choice(['full', 'ns']))
+    return exp
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_random_experiments_against_oracle(seed):
+    rs = np.random.RandomState(100 + seed)
+    exp = random_experiment(rs)
+    n = int(rs.choice([10, 57, 100]))
+    atoms = structures.alloy_sphere(n, seed=seed) if seed % 2 else structures.random_atoms(n, seed)
+    for prec, tol, gtol in (('fp32', TOL32, TOL32), ('fp64', TOL64, TOL64)):
+        scat = ElasticScatter(dict(exp), precision=prec)
+        fq, grad, pdf = scat.get_fq(atoms), scat.get_grad_fq(atoms), scat.get_pdf(atoms)
+        pos = atoms.get_positions()
+        opos = pos.astype(np.float32) if prec == 'fp32' else pos
+        sf, sp = atoms.get_array('F(Q) scatter'), atoms.get_array('PDF scatter')
+        assert nerr(fq, oracle.experiment_fq(opos, sf, scat.exp, 'fp64')) < tol
+        assert nerr(grad, oracle.experiment_grad_fq(opos, sf, scat.exp, 'fp64')) < gtol
+        assert nerr(pdf, oracle.experiment_pdf(opos, sp, scat.exp, 'fp64')) < tol
+        assert len(pdf) == len(scat.get_r())
+
+
+def test_sq_iq_follow_the_reference_formulas():
+    """get_sq = F/Q + 1 (inf -> 0), get_iq = S * <f>^2 (__init__.py:393-446)."""
+    atoms = structures.alloy_sphere(40, seed=9)
+    scat = ElasticScatter()
+    fq = scat.get_fq(atoms).astype(np.float64)
+    q = scat.get_scatter_vector()
+    sq = scat.get_sq(atoms)
+    assert np.isnan(sq[0]) and np.allclose(sq[1:], fq[1:] / q[1:] + 1, rtol=1e-6)
+    f2 = np.average(atoms.get_array('F(Q) scatter'), axis=0) ** 2
+    assert np.allclose(scat.get_iq(atoms)[1:], sq[1:] * f2[1:], rtol=1e-6)
+
+
+def test_per_atom_scatter_rows_that_differ_within_an_element():
+    """A caller may hand in arbitrary per-atom scatter-factor rows; they are
+    grouped by unique row, not by atomic number."""
+    rs = np.random.RandomState(5)
+    atoms = structures.random_atoms(23, 8)
+    scat = ElasticScatter(precision='fp64')
+    scat._ensure_wrapped(atoms)
+    sf = atoms.get_array('F(Q) scatter')
+    scale = rs.choice([0.5, 1.0, 1.7], size=23).astype(np.float32)
+    sf = sf * scale[:, None]
+    atoms.set_array('F(Q) scatter', sf)
+    fq, grad = scat.get_fq(atoms), scat.get_grad_fq(atoms)
+    pos = atoms.get_positions()
+    assert nerr(fq, oracle.experiment_fq(pos, sf, scat.exp, 'fp64')) < TOL64
+    assert nerr(grad, oracle.experiment_grad_fq(pos, sf, scat.exp, 'fp64')) < TOL64
+
+
+def test_noise_is_reproducible_with_a_seed():
+    atoms = structures.random_atoms(15, 2)
+    a = ElasticScatter(seed=7).get_fq(atoms, iq_std=0.05)
+    b = ElasticScatter(seed=7).get_fq(atoms, iq_std=0.05)
+    c = ElasticScatter(seed=8).get_fq(atoms, iq_std=0.05)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+
+
+def test_fp32_f_of_q_against_oracle_at_2000_atoms():
+    atoms = structures.fcc_sphere('Au', 2000)
+    scat = ElasticScatter()
+    fq = scat.get_fq(atoms)
+    pos = atoms.get_positions().astype(np.float32)
+    sf = atoms.get_array('F(Q) scatter')
+    assert nerr(fq, oracle.experiment_fq(pos, sf, EXP, 'fp32', nthreads=8)) < TOL32
+    assert nerr(fq, oracle.experiment_fq(pos, sf, EXP, 'fp64', nthreads=8)) < TOL32
