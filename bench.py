@@ -262,18 +262,22 @@ def hmc_extra():
     for i in range(reps):
         be.energy_forces(pos + 1e-6 * i, target, 'rw', 100.)
     evals_per_s = reps / (time.perf_counter() - t)
-    np.random.seed(0)
-    ens = sim.NUTSCanonicalEnsemble(atoms, temperature=1000, escape_level=8, seed=0)
-    lf0, t = ens.leapfrogs, time.perf_counter()
-    iters = 3
-    ens.run(iters)
-    dt = time.perf_counter() - t
-    return {'workload': 'Au561 icosahedron x1.05 vs ideal PDF, Calc1D(conv=100, rw), '
-                        'NUTS(T=1000, escape_level=8, seed=0)',
-            'energy_force_evals_per_s': evals_per_s,
-            'hmc_leapfrog_steps_per_s': (ens.leapfrogs - lf0) / dt,
-            'nuts_iterations_per_s': iters / dt,
-            'pairq_per_eval': 561 * 560 // 2 * 330}
+    out = {'workload': 'Au561 icosahedron x1.05 vs ideal PDF, Calc1D(conv=100, rw), '
+                       'NUTS(T=1000, escape_level=8, seed=0)',
+           'energy_force_evals_per_s': evals_per_s,
+           'pairq_per_eval': 561 * 560 // 2 * 330}
+    for fast, tag in ((True, ''), (False, '_atoms_level_path')):
+        np.random.seed(0)
+        a = atoms.copy()
+        a.set_calculator(calc)
+        ens = sim.NUTSCanonicalEnsemble(a, temperature=1000, escape_level=8, seed=0, fast=fast)
+        lf0, t = ens.leapfrogs, time.perf_counter()
+        iters = 6 if fast else 3
+        ens.run(iters)
+        dt = time.perf_counter() - t
+        out['hmc_leapfrog_steps_per_s' + tag] = (ens.leapfrogs - lf0) / dt
+        out['nuts_iterations_per_s' + tag] = iters / dt
+    return out
 
 
 def main():

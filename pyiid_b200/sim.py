@@ -140,14 +140,135 @@ def buildtree(input_atoms, u, v, j, e, e0, rs, beta=1):
                  first.n_leaves + second.n_leaves)
 
 
+class _State(object):
+    """Phase-space point of the array-level sampler path: positions, momenta,
+    potential energy, forces, kinetic energy (no Atoms object per leapfrog)."""
+    __slots__ = ('q', 'p', 'pe', 'f', 'ke')
+
+    def __init__(self, q, p, pe, f, ke):
+        self.q, self.p, self.pe, self.f, self.ke = q, p, pe, f, ke
+
+    @property
+    def total(self):
+        return self.pe + self.ke
+
+
+class _FastSystem(object):
+    """The same dynamics as :func:`leapfrog` + ``get_total_energy`` for atoms
+    whose calculator is the fused device ``Calc1D``: one native
+    energy+forces call per leapfrog on plain arrays.  The reference's sampler
+    deep-copies the Atoms object, its arrays and its calculator on every
+    leapfrog (``pyiid/sim/__init__.py:29``); at a few hundred atoms that host
+    work, not the scattering arithmetic, bounds the sampling rate (SURVEY.md
+    section 8f-2)."""
+
+    def __init__(self, atoms):
+        calc = atoms.get_calculator()
+        self.calc = calc
+        self.scat = calc._fused
+        self.template = atoms
+        self.masses = atoms.get_masses().reshape(-1, 1)
+        self.cell_centre = 0.5 * np.asarray(atoms.cell).sum(0)
+        self.scat._ensure_wrapped(atoms)
+        self.evals = 0
+
+    @staticmethod
+    def usable(atoms):
+        from .calc import Calc1D
+        calc = atoms.get_calculator() if hasattr(atoms, 'get_calculator') else None
+        return isinstance(calc, Calc1D) and calc._fused is not None
+
+    def evaluate(self, q):
+        scat, calc = self.scat, self.calc
+        be = scat._load(self.template, scat.pdf_qbin, 'PDF')
+        be.set_transform(scat.exp['rstep'], scat.pdf_qbin, scat.get_r(), scat.exp['qmin'])
+        e, scale, f, _ = be.energy_forces(q, calc.target_data, calc.potential_name,
+                                          calc.rw_to_eV, True)
+        self.evals += 1
+        return float(e), f
+
+    def kinetic(self, p):
+        return 0.5 * float(np.vdot(p, p / self.masses))
+
+    def state_of(self, atoms):
+        q = atoms.get_positions()
+        p = atoms.get_momenta()
+        return _State(q, p, float(atoms.get_potential_energy()), atoms.get_forces(),
+                      self.kinetic(p))
+
+    def leapfrog(self, st, step, center=True):
+        p = st.p + 0.5 * step * st.f
+        q = st.q + step * (p / self.masses)
+        pe, f = self.evaluate(q)
+        p = p + 0.5 * step * f
+        if center:
+            q = q + (self.cell_centre - 0.5 * (q.min(0) + q.max(0)))
+        return _State(q, p, pe, f, self.kinetic(p))
+
+    def to_atoms(self, st):
+        """An Atoms object with this state and a calculator whose result cache
+        already holds its energy and forces."""
+        atoms = self.template.copy()
+        atoms.set_positions(st.q)
+        atoms.set_momenta(st.p)
+        calc = dc(self.calc)
+        calc.atoms = atoms.copy()
+        calc.results = {'energy': st.pe, 'forces': st.f.copy()}
+        atoms.set_calculator(calc)
+        return atoms
+
+
+def _no_u_turn_states(minus, plus, masses):
+    span = (plus.q - minus.q).ravel()
+    return (span.dot((minus.p / masses).ravel()) >= 0) and \
+        (span.dot((plus.p / masses).ravel()) >= 0)
+
+
+def _buildtree_states(system, st, u, v, j, e, e0, rs):
+    """:func:`buildtree` on :class:`_State` objects (same random-number
+    consumption, same arithmetic)."""
+    if j == 0:
+        leaf = system.leapfrog(st, v * e)
+        neg_delta = e0 - leaf.total
+        n_valid = int(u <= _safe_exp(neg_delta))
+        keep_going = int(u < _safe_exp(Emax + neg_delta))
+        accept = min(1., _safe_exp(st.total - leaf.total))
+        return _Tree(leaf, leaf, leaf, n_valid, keep_going, accept, 1)
+    first = _buildtree_states(system, st, u, v, j - 1, e, e0, rs)
+    if first.keep_going != 1:
+        return first
+    if v == -1:
+        second = _buildtree_states(system, first.minus, u, v, j - 1, e, e0, rs)
+        minus, plus = second.minus, first.plus
+    else:
+        second = _buildtree_states(system, first.plus, u, v, j - 1, e, e0, rs)
+        minus, plus = first.minus, second.plus
+    proposal = first.proposal
+    total = first.n_valid + second.n_valid
+    if rs.uniform() < float(second.n_valid) / max(total, 1):
+        proposal = second.proposal
+    keep_going = int(second.keep_going and _no_u_turn_states(minus, plus, system.masses))
+    return _Tree(minus, plus, proposal, total, keep_going,
+                 first.accept_sum + second.accept_sum,
+                 first.n_leaves + second.n_leaves)
+
+
 class NUTSCanonicalEnsemble(Ensemble):
-    """No-U-Turn sampler in the canonical ensemble (``nuts_hmc.py:91-244``)."""
+    """No-U-Turn sampler in the canonical ensemble (``nuts_hmc.py:91-244``).
+
+    ``fast`` (default: automatic) selects the array-level path
+    (:class:`_FastSystem`) when the atoms carry the fused device ``Calc1D``;
+    it draws the same random numbers and performs the same arithmetic as the
+    Atoms-level path, so both produce the same trajectory."""
 
     def __init__(self, atoms, restart=None, logfile=None, trajectory=None,
                  temperature=100, escape_level=13, accept_target=.65,
-                 momentum=None, seed=None, verbose=False):
+                 momentum=None, seed=None, verbose=False, fast=None):
         Ensemble.__init__(self, atoms, restart, logfile, trajectory, seed,
                           verbose)
+        if fast is None:
+            fast = _FastSystem.usable(atoms)
+        self.fast = bool(fast) and _FastSystem.usable(atoms)
         self.accept_target = accept_target
         self.temp = temperature
         self.thermal_nrg = self.temp * kB
@@ -195,6 +316,61 @@ class NUTSCanonicalEnsemble(Ensemble):
     def step(self):
         """One NUTS iteration (``nuts_hmc.py:160-232``); returns the list of
         accepted configurations or None."""
+        if self.fast:
+            return self._step_fast()
+        return self._step_atoms()
+
+    def _step_fast(self):
+        current = self.traj[-1]
+        system = _FastSystem(current)
+        accepted = []
+        if self.verbose:
+            print('\ttime step size', self.step_size / fs, 'fs')
+        self._refresh_momenta(current)
+        u = self.random_state.uniform(0, 1)
+        start = system.state_of(current)
+        e0 = start.total
+        e = self.step_size
+        n, keep_going, depth = 1, 1, 0
+        minus, plus = start, start
+        acc_sum, leaves = 0., 1
+        while keep_going == 1:
+            v = self.random_state.choice([-1, 1])
+            tree = _buildtree_states(system, minus if v == -1 else plus, u, v, depth, e,
+                                     e0, self.random_state)
+            if v == -1:
+                minus = tree.minus
+            else:
+                plus = tree.plus
+            acc_sum, leaves = tree.accept_sum, tree.n_leaves
+            self.leapfrogs += tree.n_leaves
+            if tree.keep_going == 1 and self.random_state.uniform() < min(
+                    1, tree.n_valid * 1. / n):
+                sample = system.to_atoms(tree.proposal)
+                self.traj += [sample]
+                self.metadata['accepted_samples'] += 1
+                accepted.append(sample)
+                self.call_observers()
+            n += tree.n_valid
+            keep_going = int(tree.keep_going and
+                             _no_u_turn_states(minus, plus, system.masses))
+            depth += 1
+            if self.verbose:
+                print('\t \tdepth', depth, 'samples', 2 ** depth)
+            self.metadata['samples_total'] += 2 ** depth
+            if depth >= self.escape_level:
+                if self.verbose:
+                    print('\t \t \tjmax emergency escape at {}'.format(depth))
+                keep_going = 0
+        w = 1. / (self.m + self.t0)
+        self.sim_hbar = (1 - w) * self.sim_hbar + \
+            w * (self.accept_target - acc_sum / leaves)
+        self.step_size = np.exp(self.mu - (self.m ** .5 / self.gamma) *
+                                self.sim_hbar)
+        self.m += 1
+        return accepted if accepted else None
+
+    def _step_atoms(self):
         current = self.traj[-1]
         accepted = []
         if self.verbose:

@@ -492,3 +492,28 @@ def test_fp32_f_of_q_against_oracle_at_2000_atoms():
     sf = atoms.get_array('F(Q) scatter')
     assert nerr(fq, oracle.experiment_fq(pos, sf, EXP, 'fp32', nthreads=8)) < TOL32
     assert nerr(fq, oracle.experiment_fq(pos, sf, EXP, 'fp64', nthreads=8)) < TOL32
+
+
+def test_array_level_nuts_equals_atoms_level_nuts():
+    """The fast sampler path (plain arrays, one native call per leapfrog)
+    reproduces the Atoms-level path: same random numbers, same trajectory."""
+    trajs = []
+    for fast in (False, True):
+        atoms, scat = make_hmc_atoms(2, 'fp64')
+        np.random.seed(3)
+        ens = sim.NUTSCanonicalEnsemble(atoms, temperature=1000, escape_level=4, seed=5,
+                                        fast=fast)
+        assert ens.fast is fast
+        traj, meta = ens.run(4)
+        trajs.append((traj, dict(meta), ens.step_size, ens.leapfrogs))
+    (ta, ma, sa, la), (tb, mb, sb, lb) = trajs
+    assert ma == mb and la == lb and len(ta) == len(tb)
+    assert abs(sa - sb) < 1e-6 * abs(sa), (sa, sb)
+    for x, y in zip(ta, tb):
+        # identical up to the chaotic growth of last-bit differences (the
+        # device sums use atomics, so even one path is only reproducible to
+        # ~1e-16 per evaluation)
+        assert np.allclose(x.positions, y.positions, rtol=0, atol=1e-5), \
+            np.abs(x.positions - y.positions).max()
+        assert np.allclose(x.get_momenta(), y.get_momenta(), rtol=0, atol=1e-5)
+        assert abs(x.get_potential_energy() - y.get_potential_energy()) < 1e-5
