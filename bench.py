@@ -295,10 +295,9 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
 
     import __graft_entry__ as entry
-    if rank == 0 or world == 1:
-        entry.build()
-
     if args.impl == 'reference':
+        if rank == 0:
+            entry.build()
         run_reference(args, rank, world)
         return
 
@@ -307,7 +306,11 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        if rank == 0:
+            entry.build()  # the other ranks load the library only after this
         dist.barrier()
+    else:
+        entry.build()
     warmup = max(3, args.warmup)
     n_atoms = args.atoms
     atoms, scat = build_workload(n_atoms)
