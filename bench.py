@@ -154,7 +154,9 @@ def cpu_baseline_sample(atoms, scat, seconds_target=16.0):
     host cores."""
     import oracle
     cores = os.cpu_count() or 1
-    threads = max(1, min(cores, 32, oracle.max_threads()))
+    # explicit thread count: torchrun exports OMP_NUM_THREADS=1, which must not
+    # throttle the CPU baseline (the C port passes it to `num_threads`)
+    threads = max(1, min(cores, 32))
     pos = atoms.get_positions()
     sf = atoms.get_array('F(Q) scatter')
     n, nq = sf.shape
