@@ -282,6 +282,40 @@ def hmc_extra():
     return out
 
 
+def config3_extra():
+    """configs[2]: Au 10 000-atom particle, every pair sum, FP32 and FP64 mode
+    (kernel-only CUDA-event times) plus the fused Rw energy+forces wall time."""
+    from pyiid_b200 import ElasticScatter, structures
+    atoms = structures.fcc_sphere('Au', 10000, sigma=0.05, seed=0)
+    ideal = structures.fcc_sphere('Au', 10000, sigma=0.0)
+    pos = atoms.get_positions()
+    out = {'workload': 'Au 10000-atom fcc particle; F(Q)/grad on 250 bins, energy+forces on the '
+                       '330-bin PDF grid; kernel ms by CUDA events',
+           'pairq_250': 10000 * 9999 // 2 * 250}
+    for prec in ('fp32', 'fp64'):
+        scat = ElasticScatter(precision=prec)
+        scat._ensure_wrapped(atoms)
+        be = scat._load(atoms, scat.exp['qbin'], 'fq')
+        be.set_timing(True)
+        for name, fn in (('fq', be.fq), ('fq_grad', be.grad_fq)):
+            ts = []
+            for _ in range(3):
+                fn(pos)
+                ts.append(be.last_kernel_ms()[0])
+            out['%s_kernel_ms_%s' % (name, prec)] = min(ts)
+        be.set_timing(False)
+        bp = scat._load(atoms, scat.pdf_qbin, 'PDF')
+        bp.set_transform(scat.exp['rstep'], scat.pdf_qbin, scat.get_r(), 0.0)
+        target = bp.pdf(ideal.get_positions())
+        ts = []
+        for _ in range(4):
+            t = time.perf_counter()
+            bp.energy_forces(pos, target, 'rw', 100.)
+            ts.append(time.perf_counter() - t)
+        out['energy_forces_wall_ms_%s' % prec] = 1e3 * min(ts)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -437,10 +471,12 @@ def main():
     if world == 1:
         line['cpu_baseline'] = cpu_baseline_sample(atoms, scat)
         if not args.no_extras:
-            try:
-                line['extras'] = {'hmc_au561': hmc_extra()}
-            except Exception as exc:  # keep the headline line even if the extra fails
-                line['extras'] = {'hmc_au561_error': repr(exc)}
+            line['extras'] = {}
+            for key, fn in (('hmc_au561', hmc_extra), ('au10k_modes', config3_extra)):
+                try:
+                    line['extras'][key] = fn()
+                except Exception as exc:  # keep the headline line even if an extra fails
+                    line['extras'][key + '_error'] = repr(exc)
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
