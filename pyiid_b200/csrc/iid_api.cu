@@ -87,7 +87,6 @@ struct iid_handle {
     // tunables
     int nw_max = 12;
     int slab_override = 0;
-    bool use_v1 = false;
     // CUDA graph of the fused energy+forces sequence (small-N latency)
     cudaGraphExec_t ef_graph = nullptr;
     int ef_key_pot = -1;
@@ -155,7 +154,6 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     CU(cudaMalloc((void **)&h->out4, 4 * sizeof(double)));
     if (const char *s = getenv("IID_NW")) h->nw_max = std::max(1, std::min(12, atoi(s)));
     h->nw_max = std::min(h->nw_max, 12);
-    if (const char *s = getenv("IID_V1")) h->use_v1 = atoi(s) != 0;
     if (const char *s = getenv("IID_GRAPH")) h->use_graph = atoi(s) != 0;
     if (const char *s = getenv("IID_CHEB")) h->cheb = atoi(s) != 0;
     if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
@@ -477,33 +475,6 @@ static int stage_positions(iid_handle *h, const double *pos_dev, cudaStream_t st
     return 0;
 }
 
-template <typename T, int C, int MODE>
-static int launch_debye_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
-                          cudaStream_t st)
-{
-    // warps per block = Q chunks per block.  Up to 8 warps a thread may use
-    // 255 registers (one block per SM); 9..12 warps compile to <= 168.
-    const int nchunk = (int)((h->nq + C - 1) / C);
-    const int nwmax = std::min(h->nw_max, 8);
-    const int gy = (nchunk + nwmax - 1) / nwmax;
-    const int nw = (nchunk + gy - 1) / gy;
-    dim3 grid((unsigned)nblocks, (unsigned)gy, 1), block(32 * nw, 1, 1);
-    if (h->timing) CU(cudaEventRecord(h->ev0, st));
-    if (nw <= 8)
-        debye_kernel<T, C, MODE, 256><<<grid, block, 0, st>>>(p);
-    else
-        debye_kernel<T, C, MODE, 384><<<grid, block, 0, st>>>(p);
-    ++h->launches;
-    CU(cudaGetLastError());
-    if (h->timing) {
-        CU(cudaEventRecord(h->ev1, st));
-        h->ev_pending = true;
-    }
-    return 0;
-}
-
-// FP32: producer/consumer kernel (iid_debye2.cuh); IID_V1=1 selects the
-// simpler per-warp set-up kernel of iid_debye.cuh for comparison.
 template <int C, int MODE, int MAXT, int MINB, int TJ, bool CHEB>
 static int launch_debye2_v(iid_handle *h, const DebyeParams &p, dim3 grid, dim3 block, int nw,
                            cudaStream_t st)
@@ -556,8 +527,7 @@ static int launch_debye2_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
     return 0;
 }
 
-// FP64: producer/consumer kernel (iid_debye64.cuh); IID_V1=1 selects the
-// per-warp set-up kernel of iid_debye.cuh.
+// FP64: producer/consumer kernel (iid_debye64.cuh).
 template <int C, int MODE>
 static int launch_debye64_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
                             cudaStream_t st)
@@ -609,29 +579,19 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     const int64_t mine = nitems > h->rank ? (nitems - h->rank + h->world - 1) / h->world : 0;
     h->last_pairq = 0.5 * (double)h->n * (double)(h->n - 1) * (double)h->nq / h->world;
     if (mine == 0) return 0;
-    if (h->precision == IID_FP32 && !h->use_v1 && h->cheb) {
+    if (h->precision == IID_FP32 && h->cheb) {
         if (mode == MODE_FQ) return launch_debye2_t<C32, MODE_FQ, true>(h, p, mine, st);
         if (mode == MODE_GRAD) return launch_debye2_t<C32, MODE_GRAD, true>(h, p, mine, st);
         return launch_debye2_t<C32, MODE_FORCE, true>(h, p, mine, st);
     }
-    if (h->precision == IID_FP32 && !h->use_v1) {
+    if (h->precision == IID_FP32) {  // IID_CHEB=0: rotation recurrence everywhere
         if (mode == MODE_FQ) return launch_debye2_t<C32, MODE_FQ, false>(h, p, mine, st);
         if (mode == MODE_GRAD) return launch_debye2_t<C32, MODE_GRAD, false>(h, p, mine, st);
         return launch_debye2_t<C32, MODE_FORCE, false>(h, p, mine, st);
     }
-    if (h->precision == IID_FP32) {
-        if (mode == MODE_FQ) return launch_debye_t<float, C32, MODE_FQ>(h, p, mine, st);
-        if (mode == MODE_GRAD) return launch_debye_t<float, C32, MODE_GRAD>(h, p, mine, st);
-        return launch_debye_t<float, C32, MODE_FORCE>(h, p, mine, st);
-    }
-    if (!h->use_v1) {
-        if (mode == MODE_FQ) return launch_debye64_t<C64, MODE_FQ>(h, p, mine, st);
-        if (mode == MODE_GRAD) return launch_debye64_t<C64, MODE_GRAD>(h, p, mine, st);
-        return launch_debye64_t<C64, MODE_FORCE>(h, p, mine, st);
-    }
-    if (mode == MODE_FQ) return launch_debye_t<double, C64, MODE_FQ>(h, p, mine, st);
-    if (mode == MODE_GRAD) return launch_debye_t<double, C64, MODE_GRAD>(h, p, mine, st);
-    return launch_debye_t<double, C64, MODE_FORCE>(h, p, mine, st);
+    if (mode == MODE_FQ) return launch_debye64_t<C64, MODE_FQ>(h, p, mine, st);
+    if (mode == MODE_GRAD) return launch_debye64_t<C64, MODE_GRAD>(h, p, mine, st);
+    return launch_debye64_t<C64, MODE_FORCE>(h, p, mine, st);
 }
 
 static cudaStream_t pick(iid_handle *h, void *stream)
