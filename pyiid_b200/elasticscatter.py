@@ -200,6 +200,12 @@ class ElasticScatter(object):
     def _wrap_fq(self, atoms, qbin=.1, sum_type='fq'):
         """``wrap_fq(atoms, qbin, sum_type) -> float32 [Qbins]``
         (``cpu_wrappers/flat_multi_cpu_wrap.py:22-60``)."""
+        if len(atoms) < 2:
+            # no pairs: k_max == 0 -> zeros (flat_multi_cpu_wrap.py:49-60 with
+            # nan_to_num of 0/0); no device work is needed for that
+            name = 'F(Q) scatter' if sum_type == 'fq' else 'PDF scatter'
+            nq = atoms.get_array(name).shape[1]
+            return np.zeros(nq, np.float32 if self.precision == 'fp32' else np.float64)
         be = self._load(atoms, qbin, sum_type)
         out = be.fq(atoms.get_positions())
         return out.astype(np.float32) if self.precision == 'fp32' else out
@@ -207,9 +213,12 @@ class ElasticScatter(object):
     def _wrap_fq_grad(self, atoms, qbin=.1, sum_type='fq'):
         """``wrap_fq_grad(atoms, qbin, sum_type) -> [N, 3, Qbins]``
         (``flat_multi_cpu_wrap.py:63-102``)."""
-        be = self._load(atoms, qbin, sum_type)
         if len(atoms) < 2:
-            return np.zeros((len(atoms), 3, be.nq), be.gdtype)
+            name = 'F(Q) scatter' if sum_type == 'fq' else 'PDF scatter'
+            nq = atoms.get_array(name).shape[1]
+            return np.zeros((len(atoms), 3, nq),
+                            np.float32 if self.precision == 'fp32' else np.float64)
+        be = self._load(atoms, qbin, sum_type)
         return be.grad_fq(atoms.get_positions())
 
     def _grad_pdf(self, grad_fq, rstep, qstep, rgrid, qmin):
@@ -242,6 +251,8 @@ class ElasticScatter(object):
         ``__init__.py:343-391``)."""
         self._ensure_wrapped(atoms)
         r = self.get_r()
+        if len(atoms) < 2:
+            return np.zeros(len(r))
         if iq_std is None:
             be = self._load(atoms, self.pdf_qbin, 'PDF')
             be.set_transform(self.exp['rstep'], self.pdf_qbin, r, self.exp['qmin'])

@@ -540,3 +540,17 @@ def test_example_workflow_and_coincident_atoms():
     # the duplicated pair adds nothing: remaining pair terms equal those of
     # the 12-atom sum with that one pair removed
     assert np.any(fq)
+
+
+def test_50k_bench_workload_properties():
+    """Maximum-size case of the bench: F(Q) of the Pt 50 000-atom particle is
+    finite, translation invariant and equal on the two Q grids' shared bin 0."""
+    atoms = structures.fcc_sphere('Pt', 50000)
+    scat = ElasticScatter()
+    scat._ensure_wrapped(atoms)
+    be = scat._load(atoms, scat.exp['qbin'], 'fq')
+    pos = atoms.get_positions()
+    f1 = be.fq(pos)
+    f2 = be.fq(pos + np.array([11.0, -7.5, 2.25]))
+    assert np.all(np.isfinite(f1)) and f1[0] == 0
+    assert nerr(f2, f1) < TOL32

@@ -209,3 +209,17 @@ def test_calc1d_argument_checks():
     c2 = Calc1D(target_data=np.zeros(250), exp_function=s.get_fq,
                 exp_grad_function=s.get_grad_fq)
     assert c2._fused is None
+
+
+def test_empty_and_single_atom_inputs_need_no_device():
+    """k_max == 0 gives zeros (flat_multi_cpu_wrap.py:85-86); handled on the
+    host, so it works without a GPU."""
+    s = ElasticScatter()
+    for n in (0, 1):
+        atoms = ase_shim.Atoms(numbers=[79] * n, positions=np.zeros((n, 3)))
+        fq = s.get_fq(atoms)
+        assert fq.shape == (250,) and fq.dtype == np.float32 and not np.any(fq)
+        g = s.get_grad_fq(atoms)
+        assert g.shape == (n, 3, 250) and not np.any(g)
+        pdf = s.get_pdf(atoms)
+        assert pdf.shape == (4000,) and not np.any(pdf)
