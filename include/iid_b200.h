@@ -189,6 +189,13 @@ int iid_fq_to_gr_host(iid_handle *h, const double *F_host, double *pdf_host);
  * return.  (The multi-GPU host layer uses it after the NCCL all-reduce.) */
 int iid_download_host(iid_handle *h, const void *dev, void *host, int64_t bytes);
 
+/* Tunables: "force_table" (0/1: tabulated radial force pass in FP32 mode),
+ * "force_table_min_n" (atoms from which it is used), "graph" (0/1: CUDA-graph
+ * replay of iid_energy_forces_host), "cheb" (0/1: three-term recurrence),
+ * "nw_max" (warps per block).  Defaults can also be set with IID_* environment
+ * variables before iid_create. */
+int iid_set_option(iid_handle *h, const char *key, int64_t value);
+
 /* instrumentation ---------------------------------------------------------- */
 /* number of kernels this handle has launched since creation */
 int iid_launch_count(iid_handle *h, int64_t *count);

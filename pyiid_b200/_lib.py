@@ -51,6 +51,7 @@ SIGNATURES = {
     'iid_contract_host': [_vp, _vp, _int, _i64, _i64, _vp, _vp],
     'iid_fq_to_gr_host': [_vp, _vp, _vp],
     'iid_download_host': [_vp, _vp, _vp, _i64],
+    'iid_set_option': [_vp, ctypes.c_char_p, _i64],
     'iid_launch_count': [_vp, _pi64],
     'iid_last_kernel_ms': [_vp, ctypes.POINTER(ctypes.c_float),
                            ctypes.POINTER(_dbl)],

@@ -408,6 +408,10 @@ class Backend(object):
         check(self.lib.iid_fq_to_gr_host(self.h, f.ctypes.data, g.ctypes.data))
         return g
 
+    def set_option(self, key, value):
+        """Native tunables, see iid_set_option in include/iid_b200.h."""
+        check(self.lib.iid_set_option(self.h, key.encode(), int(value)))
+
     # -- instrumentation ------------------------------------------------------
     def launch_count(self):
         c = ctypes.c_int64(0)

@@ -16,6 +16,7 @@
 #include "iid_debye.cuh"
 #include "iid_debye2.cuh"
 #include "iid_debye64.cuh"
+#include "iid_force_table.cuh"
 #include "iid_small.cuh"
 
 using namespace iid;
@@ -77,6 +78,11 @@ struct iid_handle {
            *target = nullptr;
     void *Gfull = nullptr;
     size_t Gfull_bytes = 0;
+    // tabulated radial function of the force pass (iid_force_table.cuh)
+    float *phi_tab = nullptr;
+    double *phi_info = nullptr;
+    bool use_force_table = true;
+    int64_t force_table_min_n = 1500;  // below this the direct kernel is faster
     // pinned staging for the gradient's way back to pageable host memory
     unsigned char *pinG = nullptr;
     size_t pinG_bytes = 0;
@@ -93,6 +99,7 @@ struct iid_handle {
     double ef_key_conv = 0.0;
     bool ef_key_pdf = false;
     int ef_warm = 0;
+    int64_t ef_launches = 0;  // kernels per replay of the graph
     bool use_graph = true;
     bool cheb = true;
     // instrumentation
@@ -155,6 +162,8 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_NW")) h->nw_max = std::max(1, std::min(12, atoi(s)));
     h->nw_max = std::min(h->nw_max, 12);
     if (const char *s = getenv("IID_GRAPH")) h->use_graph = atoi(s) != 0;
+    if (const char *s = getenv("IID_FORCE_TABLE")) h->use_force_table = atoi(s) != 0;
+    if (const char *s = getenv("IID_FORCE_TABLE_MIN_N")) h->force_table_min_n = atoll(s);
     if (const char *s = getenv("IID_CHEB")) h->cheb = atoi(s) != 0;
     if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
     *out = h;
@@ -169,7 +178,7 @@ extern "C" int iid_destroy(iid_handle *h)
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
                     h->inv_na, h->inv_na_d, h->items_tri, h->items_sq, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
-                    h->target, h->Gfull};
+                    h->target, h->Gfull, h->phi_tab, h->phi_info};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pinG) cudaFreeHost(h->pinG);
@@ -594,6 +603,47 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     return launch_debye64_t<C64, MODE_FORCE>(h, p, mine, st);
 }
 
+// Force pass.  FP32 mode with a handful of element types: sum over the Q bins
+// first (radial table, O(K Q)), then one interpolation per ordered pair
+// (O(N^2)); otherwise the direct O(N^2 Q) kernel.
+static int launch_force(iid_handle *h, const double *wq, double *force, cudaStream_t st)
+{
+    const bool table = h->use_force_table && h->precision == IID_FP32 && h->ntypes <= 4 &&
+                       h->n >= h->force_table_min_n;
+    if (!table) return launch_debye(h, MODE_FORCE, nullptr, nullptr, wq, force, st);
+    const size_t tstride = PHI_KMAX + 2 * PHI_PAD;
+    if (!h->phi_tab) {
+        CU(cudaMalloc((void **)&h->phi_tab, sizeof(float) * tstride * 16));
+        CU(cudaMalloc((void **)&h->phi_info, sizeof(double) * 4));
+    }
+    const int np = (int)h->np, E = (int)h->ntypes;
+    const double qmax = h->qbin * (double)h->nq;
+    const double h_target = 0.05 / (qmax > 0.0 ? qmax : 1.0);
+    h->last_pairq = 0.5 * (double)h->n * (double)(h->n - 1) * (double)h->nq / h->world;
+    if (h->timing) CU(cudaEventRecord(h->ev0, st));
+    phi_grid_kernel<<<1, 1024, 0, st>>>(h->x, h->y, h->z, h->valid, np, h_target, h->phi_info);
+    phi_table_kernel<<<dim3((unsigned)((tstride + 127) / 128), (unsigned)(E * E)), 128,
+                       h->nq * sizeof(double), st>>>(wq, (const float *)h->ftab,
+                                                     (const float *)h->inv_na, (int)h->nq,
+                                                     (int)h->qp, E, h->qbin, h->phi_info,
+                                                     h->phi_tab);
+    const int rows = (np + FT_BLOCK - 1) / FT_BLOCK;
+    const int mine = rows > h->rank ? (rows - h->rank + h->world - 1) / h->world : 0;
+    if (mine > 0) {
+        const int jsplit = std::max(1, std::min(rows, (4 * h->sm_count + mine - 1) / mine));
+        force_table_kernel<<<dim3((unsigned)mine, (unsigned)jsplit), FT_BLOCK, 0, st>>>(
+            h->x, h->y, h->z, h->valid, h->orig, h->tile_type, np, E, h->phi_info, h->phi_tab,
+            jsplit, h->rank, h->world, force);
+    }
+    h->launches += 3;
+    CU(cudaGetLastError());
+    if (h->timing) {
+        CU(cudaEventRecord(h->ev1, st));
+        h->ev_pending = true;
+    }
+    return 0;
+}
+
 static cudaStream_t pick(iid_handle *h, void *stream)
 {
     return stream ? (cudaStream_t)stream : h->stream;
@@ -648,7 +698,7 @@ extern "C" int iid_force_partial(iid_handle *h, const double *pos_dev, const dou
     int rc = stage_positions(h, pos_dev, st);
     if (rc) return rc;
     CU(cudaMemsetAsync(force_dev, 0, (size_t)h->n * 3 * sizeof(double), st));
-    return launch_debye(h, MODE_FORCE, nullptr, nullptr, wq_dev, force_dev, st);
+    return launch_force(h, wq_dev, force_dev, st);
 }
 
 extern "C" int iid_fq_to_gr(iid_handle *h, const double *F_dev, double *G_dev, void *stream)
@@ -892,8 +942,7 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
         if (forces_host) {
             // positions are already staged by iid_fq_partial; enqueue the force pass
             CU(cudaMemsetAsync(h->force, 0, (size_t)h->n * 3 * sizeof(double), h->stream));
-            if ((rc2 = launch_debye(h, MODE_FORCE, nullptr, nullptr, h->wq, h->force, h->stream)))
-                return rc2;
+            if ((rc2 = launch_force(h, h->wq, h->force, h->stream))) return rc2;
             CU(cudaMemcpyAsync(pfor, h->force, (size_t)3 * h->n * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
         }
@@ -905,13 +954,14 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
     };
     if (graphable && h->ef_graph) {
         CU(cudaGraphLaunch(h->ef_graph, h->stream));
-        h->launches += 7;
+        h->launches += h->ef_launches;
     } else if (graphable && h->ef_warm >= 2) {
         cudaGraph_t graph = nullptr;
         const int64_t launches0 = h->launches;
         CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         rc = enqueue();
         cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        h->ef_launches = h->launches - launches0;  // counted while capturing, not yet run
         h->launches = launches0;
         if (rc == 0 && ce == cudaSuccess && graph &&
             cudaGraphInstantiate(&h->ef_graph, graph, 0) == cudaSuccess) {
@@ -920,7 +970,7 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
             h->ef_key_pdf = pdf_host != nullptr;
             cudaGraphDestroy(graph);
             CU(cudaGraphLaunch(h->ef_graph, h->stream));
-            h->launches += 7;
+            h->launches += h->ef_launches;
         } else {
             // capture refused: fall back to plain launches for good
             if (graph) cudaGraphDestroy(graph);
@@ -1040,6 +1090,21 @@ extern "C" int iid_fq_to_gr_host(iid_handle *h, const double *F_host, double *pd
     CU(cudaMemcpyAsync(pg, h->Gr, h->nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     memcpy(pdf_host, pg, h->nr * sizeof(double));
+    return 0;
+}
+
+// Tunables (also read from IID_* environment variables at iid_create).
+extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
+{
+    if (!h || !key) return fail(IID_E_BADARG, "null argument");
+    const std::string k(key);
+    if (k == "force_table") h->use_force_table = value != 0;
+    else if (k == "force_table_min_n") h->force_table_min_n = value;
+    else if (k == "graph") h->use_graph = value != 0;
+    else if (k == "cheb") h->cheb = value != 0;
+    else if (k == "nw_max") h->nw_max = (int)std::max<int64_t>(1, std::min<int64_t>(12, value));
+    else return fail(IID_E_BADARG, "unknown option: " + k);
+    drop_graph(h);
     return 0;
 }
 

@@ -1,0 +1,182 @@
+// iid_force_table.cuh -- the fused force pass as a tabulated radial function.
+//
+// The force of the Rw / chi^2 potential is
+//   force[i] = sum_j (q_j - q_i) * Phi_ab(r_ij),
+//   Phi_ab(r) = sum_m wq[m] f_a(m) f_b(m)/na(m) * (Q_m r cos(Q_m r) - sin(Q_m r)) / r^3,
+// i.e. for fixed chain-rule weights wq the sum over the Q bins depends on the
+// pair only through r and the two element types.  Summing over m FIRST turns
+// the O(N^2 Q) force pass into
+//   1. phi_table_kernel:  Phi_ab on a uniform r grid, O(K Q) (K ~ r_max / 1e-3 A),
+//   2. force_table_kernel: one cubic interpolation per ordered pair, O(N^2).
+// Phi is band limited by Q_max, so with h = 0.05 / Q_max the 4-point Lagrange
+// interpolation error is ~0.023 (Q_max h)^4 |Phi| = 1.5e-7 |Phi|, and the table
+// is stored in float32 (6e-8) -- both far below the FP32-mode tolerance of
+// 1e-5; geometry, interpolation and accumulation are float64.  FP64 mode and
+// small structures (where the table costs more than it saves) keep the direct
+// kernel.  The reference gets the same forces
+// from the N x 3 x R gradient array (calc/calc_1d.py:89-95 with
+// master_kernel.get_grad_rw :293-347).
+#pragma once
+#include "iid_debye.cuh"
+
+namespace iid {
+
+constexpr int PHI_KMAX = 1 << 18;  // table entries per element pair (r = 0 .. (KMAX-1) h)
+constexpr int PHI_PAD = 2;         // entries stored before r = 0 / after the end
+
+// info[0] = h, info[1] = 1/h, info[2] = entries in use
+__global__ void phi_grid_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                const double *__restrict__ z, const float *__restrict__ valid,
+                                int np, double h_target, double *__restrict__ info)
+{
+    __shared__ double smin[3][32], smax[3][32];
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int k = threadIdx.x; k < np; k += blockDim.x) {
+        if (valid[k] == 0.f) continue;
+        const double v[3] = {x[k], y[k], z[k]};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = fmin(lo[a], v[a]); hi[a] = fmax(hi[a], v[a]); }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { smin[a][w] = lo[a]; smax[a][w] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double d2 = 0.0;
+        const int nw = blockDim.x >> 5;
+        for (int a = 0; a < 3; ++a) {
+            double l = 1e300, u = -1e300;
+            for (int k = 0; k < nw; ++k) { l = fmin(l, smin[a][k]); u = fmax(u, smax[a][k]); }
+            const double e = u > l ? u - l : 0.0;
+            d2 += e * e;
+        }
+        const double rmax = sqrt(d2) * 1.0000001 + 1e-9;  // longest possible pair distance
+        double h = h_target;
+        if (rmax / h > (double)(PHI_KMAX - 4)) h = rmax / (double)(PHI_KMAX - 4);
+        info[0] = h;
+        info[1] = 1.0 / h;
+        info[2] = ceil(rmax / h) + 2.0;
+    }
+}
+
+// One thread per table entry and element pair (blockIdx.y = a * ntypes + b).
+__global__ void __launch_bounds__(128) phi_table_kernel(const double *__restrict__ wq,
+                                                        const float *__restrict__ ftab,
+                                                        const float *__restrict__ inv_na,
+                                                        int nq, int qp, int ntypes, double qbin,
+                                                        const double *__restrict__ info,
+                                                        float *__restrict__ tab)
+{
+    extern __shared__ double wab[];  // [nq] weights of this element pair
+    const int a = blockIdx.y / ntypes, b = blockIdx.y % ntypes;
+    const int kused = (int)info[2];
+    if ((int)(blockIdx.x * blockDim.x) > kused + PHI_PAD) return;  // block-uniform
+    for (int m = threadIdx.x; m < nq; m += blockDim.x)
+        wab[m] = wq[m] * (double)ftab[(size_t)a * qp + m] * (double)ftab[(size_t)b * qp + m] *
+                 (double)inv_na[m];
+    __syncthreads();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;  // entry, r = (e - PHI_PAD) h
+    if (e > kused + 2 * PHI_PAD) return;
+    const double r = fabs((double)(e - PHI_PAD)) * info[0];  // Phi is even in r
+    double phi = 0.0;
+    const double qmax_r = qbin * (double)nq * r;
+    if (qmax_r < 0.05) {
+        // (x cos x - sin x)/r^3 = Q^3 (-1/3 + x^2/30 - x^4/840), x = Q r
+        for (int m = 0; m < nq; ++m) {
+            const double q = qbin * (double)m, xx = q * r * q * r;
+            phi += wab[m] * q * q * q * (-1.0 / 3.0 + xx * (1.0 / 30.0 - xx / 840.0));
+        }
+    } else {
+        double sth, cth;
+        const double turns = qbin * r * 0.15915494309189533577;  // theta / 2 pi
+        sincospi(2.0 * (turns - rint(turns)), &sth, &cth);
+        const double kap = qbin * r;
+        double s = 0.0, c = 1.0, mk = 0.0;
+        for (int m = 0; m < nq; ++m) {
+            phi = fma(wab[m], fma(mk, c, -s), phi);
+            const double sn = fma(s, cth, c * sth);
+            const double cn = fma(c, cth, -(s * sth));
+            s = sn;
+            c = cn;
+            mk += kap;
+        }
+        phi /= r * r * r;
+    }
+    tab[(size_t)blockIdx.y * (PHI_KMAX + 2 * PHI_PAD) + e] = (float)phi;
+}
+
+// force[i] = sum_j Phi_{ab}(r_ij) (q_j - q_i): thread = atom i (sorted/padded
+// order), the j range [jbegin, jend) of this block row is staged through shared
+// memory.  Rows are split over blockIdx.y / ranks; partials meet by atomicAdd.
+constexpr int FT_BLOCK = 128;
+__global__ void __launch_bounds__(FT_BLOCK) force_table_kernel(
+    const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+    const float *__restrict__ valid, const int *__restrict__ orig,
+    const int *__restrict__ tile_type, int np, int ntypes, const double *__restrict__ info,
+    const float *__restrict__ tab, int jsplit, int row_begin, int row_stride,
+    double *__restrict__ force)
+{
+    __shared__ double sx[FT_BLOCK], sy[FT_BLOCK], sz[FT_BLOCK];
+    __shared__ int st[FT_BLOCK];
+    const int row = row_begin + blockIdx.x * row_stride;  // block of FT_BLOCK atoms i
+    const int gi = row * FT_BLOCK + threadIdx.x;
+    const bool vi = gi < np && valid[gi] != 0.f;
+    const double xi = gi < np ? x[gi] : 0.0, yi = gi < np ? y[gi] : 0.0, zi = gi < np ? z[gi] : 0.0;
+    const int ta = gi < np ? tile_type[gi / TILE_I] : 0;
+    const double inv_h = info[1];
+    const size_t tstride = PHI_KMAX + 2 * PHI_PAD;
+    const float *taba = tab + (size_t)ta * ntypes * tstride + PHI_PAD;
+    // this block's share of the j atoms, in whole staging tiles
+    const int ntiles = (np + FT_BLOCK - 1) / FT_BLOCK;
+    const int per = (ntiles + jsplit - 1) / jsplit;
+    const int t0 = blockIdx.y * per, t1 = min(ntiles, t0 + per);
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for (int t = t0; t < t1; ++t) {
+        const int gj = t * FT_BLOCK + threadIdx.x;
+        __syncthreads();
+        const bool vj = gj < np && valid[gj] != 0.f;
+        sx[threadIdx.x] = vj ? x[gj] : 0.0;
+        sy[threadIdx.x] = vj ? y[gj] : 0.0;
+        sz[threadIdx.x] = vj ? z[gj] : 0.0;
+        st[threadIdx.x] = vj ? tile_type[gj / TILE_I] : -1;
+        __syncthreads();
+        if (!vi) continue;
+#pragma unroll 4
+        for (int jj = 0; jj < FT_BLOCK; ++jj) {
+            const int tb = st[jj];
+            const double dx = sx[jj] - xi, dy = sy[jj] - yi, dz = sz[jj] - zi;
+            const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+            if (tb < 0 || r2 <= 0.0) continue;  // ghost atom, self pair, r == 0
+            double yv = (double)rsqrtf((float)r2);
+            yv = yv * fma(-0.5 * r2, yv * yv, 1.5);
+            yv = yv * fma(-0.5 * r2, yv * yv, 1.5);  // second Newton step: 1e-15
+            const double tpos = r2 * yv * inv_h;
+            const int k = (int)tpos;
+            const double u = tpos - (double)k;
+            const float *tp = taba + (size_t)tb * tstride + k;
+            const double pm = tp[-1], p0 = tp[0], p1 = tp[1], p2 = tp[2];
+            // 4-point Lagrange on the uniform grid
+            const double um = u - 1.0, u2 = u - 2.0, up = u + 1.0;
+            const double phi = -(u * um * u2) * (1.0 / 6.0) * pm + (up * um * u2) * 0.5 * p0 -
+                               (up * u * u2) * 0.5 * p1 + (up * u * um) * (1.0 / 6.0) * p2;
+            fx = fma(phi, dx, fx);
+            fy = fma(phi, dy, fy);
+            fz = fma(phi, dz, fz);
+        }
+    }
+    if (vi) {
+        const int oi = orig[gi];
+        atomicAdd(&force[(size_t)oi * 3 + 0], fx);
+        atomicAdd(&force[(size_t)oi * 3 + 1], fy);
+        atomicAdd(&force[(size_t)oi * 3 + 2], fz);
+    }
+}
+
+}  // namespace iid

@@ -554,3 +554,45 @@ def test_50k_bench_workload_properties():
     f2 = be.fq(pos + np.array([11.0, -7.5, 2.25]))
     assert np.all(np.isfinite(f1)) and f1[0] == 0
     assert nerr(f2, f1) < TOL32
+
+
+def test_tabulated_force_pass_equals_direct_force_pass():
+    """FP32 mode sums over the Q bins first (radial table + one interpolation
+    per pair) for large structures; it must reproduce the direct O(N^2 Q)
+    force kernel and the oracle."""
+    atoms = structures.alloy_sphere(2000, seed=3)
+    ideal = structures.alloy_sphere(2000, seed=3, sigma=0.0)
+    scat = ElasticScatter(precision='fp32')
+    target = scat.get_pdf(ideal)
+    scat._ensure_wrapped(atoms)
+    be = scat.pdf_backend
+    pos = atoms.get_positions()
+    res = {}
+    for table in (1, 0):
+        be.set_option('force_table', table)
+        be.set_option('force_table_min_n', 2)
+        res[table] = be.energy_forces(pos, target, 'rw', 100.)
+    be.set_option('force_table', 1)
+    be.set_option('force_table_min_n', 1500)
+    (e1, s1, f1, _), (e0, s0, f0, _) = res[1], res[0]
+    # the F(Q) pass is the same kernel both times (atomic order: last bits only)
+    assert abs(e1 - e0) < 1e-12 * abs(e0) and abs(s1 - s0) < 1e-12 * abs(s0)
+    assert nerr(f1, f0) < 2e-6
+    # against the float64 mode (itself pinned to the oracle)
+    s64 = ElasticScatter(precision='fp64')
+    t64 = s64.get_pdf(ideal)
+    s64._ensure_wrapped(atoms)
+    e64, _, f64, _ = s64.pdf_backend.energy_forces(pos.astype(np.float32).astype(np.float64),
+                                                   t64, 'rw', 100.)
+    assert abs(e1 - e64) < TOL32 * abs(e64)
+    assert nerr(f1, f64) < TOL32
+    # small structure: the table also agrees with the oracle
+    g = golden('aupt37_alloy')
+    sc = ElasticScatter(precision='fp32')
+    a = wrapped(sc, atoms_from(g), g)
+    bp = sc._load(a, sc.pdf_qbin, 'PDF')
+    bp.set_transform(sc.exp['rstep'], sc.pdf_qbin, sc.get_r(), 0.0)
+    bp.set_option('force_table_min_n', 2)
+    e, scale, f, _ = bp.energy_forces(g['positions'], g['target_pdf_f32'], 'rw', 1.0)
+    bp.set_option('force_table_min_n', 1500)
+    assert nerr(f, g['rw_forces_f32']) < TOL32
