@@ -81,6 +81,10 @@ struct iid_handle {
     // tabulated radial function of the force pass (iid_force_table.cuh)
     float *phi_tab = nullptr;
     double *phi_info = nullptr;
+    // Q-space shortcut of the chain-rule weights (fused host path):
+    // M = T^T T, vgo = T^T target, coef from the potential kernel
+    double *Mq = nullptr, *vgo = nullptr, *coef = nullptr;
+    bool vgo_valid = false;
     bool use_force_table = true;
     int64_t force_table_min_n = 1500;  // below this the direct kernel is faster
     // pinned staging for the gradient's way back to pageable host memory
@@ -92,6 +96,7 @@ struct iid_handle {
     size_t pin_count = 0;
     // tunables
     int nw_max = 12;
+    bool qspace_wq = true;  // fused host path: chain-rule weights from T^T T (no R x Q pass)
     int slab_override = 0;
     // CUDA graph of the fused energy+forces sequence (small-N latency)
     cudaGraphExec_t ef_graph = nullptr;
@@ -165,6 +170,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_FORCE_TABLE")) h->use_force_table = atoi(s) != 0;
     if (const char *s = getenv("IID_FORCE_TABLE_MIN_N")) h->force_table_min_n = atoll(s);
     if (const char *s = getenv("IID_CHEB")) h->cheb = atoi(s) != 0;
+    if (const char *s = getenv("IID_QSPACE_WQ")) h->qspace_wq = atoi(s) != 0;
     if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
     *out = h;
     return 0;
@@ -178,7 +184,7 @@ extern "C" int iid_destroy(iid_handle *h)
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
                     h->inv_na, h->inv_na_d, h->items_tri, h->items_sq, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
-                    h->target, h->Gfull, h->phi_tab, h->phi_info};
+                    h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pinG) cudaFreeHost(h->pinG);
@@ -450,6 +456,17 @@ extern "C" int iid_set_transform(iid_handle *h, int64_t nr, int64_t nq, const do
     CU(cudaMemcpy2D(h->T, h->qp * sizeof(double), T, nq * sizeof(double),
                     nq * sizeof(double), nr, cudaMemcpyHostToDevice));
     h->nr = nr;
+    if ((rc = dev_alloc(&h->Mq, (size_t)h->qp * h->qp)) || (rc = dev_alloc(&h->vgo, h->qp)) ||
+        (rc = dev_alloc(&h->coef, 2)))
+        return rc;
+    {
+        const unsigned g = (unsigned)((h->qp + 15) / 16);
+        ttt_kernel<<<dim3(g, g), 256, 0, h->stream>>>(h->T, (int)nr, (int)h->nq, (int)h->qp, h->Mq);
+        ++h->launches;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    h->vgo_valid = false;
     const size_t need = (size_t)6 * h->n + 2 * h->qp + 8 + 2 * (size_t)nr;
     if (need > h->pin_count) {
         if (h->pin) cudaFreeHost(h->pin);
@@ -726,7 +743,7 @@ extern "C" int iid_potential(iid_handle *h, const double *G_dev, const double *t
         return fail(IID_E_BADARG, "unknown potential");
     cudaStream_t st = pick(h, stream);
     potential_kernel<<<1, 1024, 0, st>>>(G_dev, target_dev, (int)h->nr, potential, conv,
-                                         out_dev, h->cr);
+                                         out_dev, h->cr, nullptr);
     ++h->launches;
     CU(cudaGetLastError());
     if (wq_dev) {
@@ -920,6 +937,16 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
         memcpy(pt, target_host, h->nr * sizeof(double));
         CU(cudaMemcpyAsync(h->target, pt, h->nr * sizeof(double), cudaMemcpyHostToDevice,
                            h->stream));
+        h->vgo_valid = false;
+    }
+    if (!h->vgo_valid) {
+        // vgo = T^T target, once per target
+        CU(cudaMemsetAsync(h->vgo, 0, h->qp * sizeof(double), h->stream));
+        wq_kernel<<<(unsigned)((h->nr + WQ_ROWS - 1) / WQ_ROWS), 352, 0, h->stream>>>(
+            h->T, h->target, (int)h->nr, (int)h->nq, (int)h->qp, 1.0, h->vgo);
+        ++h->launches;
+        CU(cudaGetLastError());
+        h->vgo_valid = true;
     }
     // The whole sequence (H2D, 7 kernels, 3 memsets, D2H) is replayed from a
     // CUDA graph once it has run twice with the same shape: at a few hundred
@@ -936,9 +963,24 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
         if ((rc2 = iid_fq_partial(h, h->pos, h->S, nullptr))) return rc2;
         if ((rc2 = iid_fq_finish(h, h->S, h->F, nullptr))) return rc2;
         if ((rc2 = iid_fq_to_gr(h, h->F, h->Gr, nullptr))) return rc2;
-        if ((rc2 = iid_potential(h, h->Gr, h->target, potential, conv, h->out4,
-                                 forces_host ? h->wq : nullptr, nullptr)))
-            return rc2;
+        // Rw / chi^2 in r space; the chain-rule weights in Q space:
+        // wq = conv T^T c = conv (coef0 T^T go - coef1 (T^T T) F)
+        if (!h->qspace_wq) {
+            if ((rc2 = iid_potential(h, h->Gr, h->target, potential, conv, h->out4,
+                                     forces_host ? h->wq : nullptr, nullptr)))
+                return rc2;
+        } else {
+            potential_kernel<<<1, 1024, 0, h->stream>>>(h->Gr, h->target, (int)h->nr, potential,
+                                                        conv, h->out4, h->cr, h->coef);
+            ++h->launches;
+            CU(cudaGetLastError());
+        }
+        if (forces_host && h->qspace_wq) {
+            wq_from_q_kernel<<<(unsigned)((h->nq + 31) / 32), 1024, 0, h->stream>>>(
+                h->Mq, h->F, h->vgo, h->coef, (int)h->nq, (int)h->qp, conv, h->wq);
+            ++h->launches;
+            CU(cudaGetLastError());
+        }
         if (forces_host) {
             // positions are already staged by iid_fq_partial; enqueue the force pass
             CU(cudaMemsetAsync(h->force, 0, (size_t)h->n * 3 * sizeof(double), h->stream));
@@ -1010,7 +1052,7 @@ extern "C" int iid_rw_host(iid_handle *h, const double *gcalc_host, const double
                             cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
         potential_kernel<<<1, 1024, 0, h->stream>>>(buf, buf + len, (int)len, potential, conv,
-                                                    buf + 3 * len, buf + 2 * len);
+                                                    buf + 3 * len, buf + 2 * len, nullptr);
         ++h->launches;
         e = cudaGetLastError();
     }
@@ -1102,6 +1144,7 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "force_table_min_n") h->force_table_min_n = value;
     else if (k == "graph") h->use_graph = value != 0;
     else if (k == "cheb") h->cheb = value != 0;
+    else if (k == "qspace_wq") h->qspace_wq = value != 0;
     else if (k == "nw_max") h->nw_max = (int)std::max<int64_t>(1, std::min<int64_t>(12, value));
     else return fail(IID_E_BADARG, "unknown option: " + k);
     drop_graph(h);

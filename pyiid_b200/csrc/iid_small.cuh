@@ -107,7 +107,8 @@ __global__ void potential_kernel(const double *__restrict__ gc,
                                  const double *__restrict__ go, int nr,
                                  int potential, double conv,
                                  double *__restrict__ out,
-                                 double *__restrict__ cr)
+                                 double *__restrict__ cr,
+                                 double *__restrict__ coef)
 {
     __shared__ double sm[96];
     double a = 0.0, b = 0.0, c = 0.0;
@@ -146,6 +147,58 @@ __global__ void potential_kernel(const double *__restrict__ gc,
         out[1] = scale;
         out[2] = value;
         out[3] = scale_true;
+        if (coef) {
+            // c = coef[0] * go - coef[1] * gc  (the chain-rule vector as a
+            // combination of the target and the model, see wq_from_q_kernel)
+            coef[0] = pref * (scale + gdb);
+            coef[1] = pref * (scale * scale + 2.0 * gdb * scale_true);
+        }
+    }
+}
+
+// M = T^T T [qp x qp], once per transform: with it
+//   wq = conv T^T c = conv (coef0 T^T go - coef1 M F)
+// needs no pass over the R x Q matrix per evaluation.
+__global__ void __launch_bounds__(256) ttt_kernel(const double *__restrict__ T, int nr, int nq,
+                                                  int qp, double *__restrict__ M)
+{
+    __shared__ double sa[16][17], sb[16][17];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+    double acc = 0.0;
+    for (int r0 = 0; r0 < nr; r0 += 16) {
+        // tile rows r0..r0+15: sa[r][col-of-block-y], sb[r][col-of-block-x]
+        const int r = r0 + ty;
+        const int ca = blockIdx.y * 16 + tx, cb = blockIdx.x * 16 + tx;
+        sa[ty][tx] = (r < nr && ca < nq) ? T[(size_t)r * qp + ca] : 0.0;
+        sb[ty][tx] = (r < nr && cb < nq) ? T[(size_t)r * qp + cb] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc = fma(sa[k][ty], sb[k][tx], acc);
+        __syncthreads();
+    }
+    if (m < qp && n < qp) M[(size_t)m * qp + n] = (m < nq && n < nq) ? acc : 0.0;
+}
+
+// wq[m] = conv * (coef0 * vgo[m] - coef1 * sum_n M[n][m] F[n]); M is symmetric,
+// so the loads are coalesced along m.  Block = 32 bins m x 32 slices of n.
+__global__ void __launch_bounds__(1024) wq_from_q_kernel(
+    const double *__restrict__ M, const double *__restrict__ F, const double *__restrict__ vgo,
+    const double *__restrict__ coef, int nq, int qp, double conv, double *__restrict__ wq)
+{
+    __shared__ double part[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int m = blockIdx.x * 32 + tx;
+    double acc = 0.0;
+    if (m < nq)
+        for (int n = ty; n < nq; n += 32) acc = fma(M[(size_t)n * qp + m], F[n], acc);
+    part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && m < nq) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += part[k][tx];
+        wq[m] = conv * (coef[0] * vgo[m] - coef[1] * t);
     }
 }
 

@@ -596,3 +596,28 @@ def test_tabulated_force_pass_equals_direct_force_pass():
     e, scale, f, _ = bp.energy_forces(g['positions'], g['target_pdf_f32'], 'rw', 1.0)
     bp.set_option('force_table_min_n', 1500)
     assert nerr(f, g['rw_forces_f32']) < TOL32
+
+
+@pytest.mark.parametrize('potential', ['rw', 'chi_sq'])
+@pytest.mark.parametrize('precision', ['fp32', 'fp64'])
+def test_qspace_chain_rule_weights_equal_rspace(potential, precision):
+    """The fused host path forms wq = conv T^T c from T^T T and T^T target
+    (no pass over the R x Q matrix per evaluation); it must give the forces of
+    the r-space contraction, including after a change of target."""
+    g = golden('au55_ico')
+    sc = ElasticScatter(precision=precision)
+    a = wrapped(sc, atoms_from(g), g)
+    be = sc._load(a, sc.pdf_qbin, 'PDF')
+    be.set_transform(sc.exp['rstep'], sc.pdf_qbin, sc.get_r(), 0.0)
+    pos = g['positions'] * 1.02
+    targets = [g['target_pdf_f32'], 0.5 * g['target_pdf_f32'][::-1].copy()]
+    for tg in targets:
+        res = {}
+        for q in (1, 0):
+            be.set_option('qspace_wq', q)
+            for _ in range(4):  # eager calls, capture, graph replay
+                res[q] = be.energy_forces(pos, tg, potential, 10.)
+        be.set_option('qspace_wq', 1)
+        (e1, s1, f1, _), (e0, s0, f0, _) = res[1], res[0]
+        assert abs(e1 - e0) <= 1e-12 * abs(e0) and abs(s1 - s0) <= 1e-12 * abs(s0)
+        assert nerr(f1, f0) < (1e-9 if precision == 'fp64' else 2e-6)
