@@ -184,6 +184,44 @@ int iid_contract_host(iid_handle *h, const void *A_host, int a_is_f32,
  * elasticscatter/__init__.py:371-390). */
 int iid_fq_to_gr_host(iid_handle *h, const double *F_host, double *pdf_host);
 
+/* --- Spring restraints (reference calc/spring_calc.py) ---------------------
+ * The restraint calculators a refinement sums with the Rw / chi^2 potential
+ * (calc/multi_calc.py:58-83).  sp_type: rep = pairs closer than rt repel
+ * (spring_nrg / spring_force :107-147), att = pairs further than rt attract
+ * (:269-311), com = atoms further than rt from the centre of mass `com`
+ * (host, 3 doubles, COM only; :188-236).  Energies are sums over ORDERED pairs
+ * as in the reference.  FP32 handles reproduce the reference's float32
+ * arithmetic per pair; FP64 handles use float64 throughout.  These calls do
+ * not need iid_set_structure. */
+#define IID_SPRING_REP 0
+#define IID_SPRING_COM 1
+#define IID_SPRING_ATT 2
+#define IID_MAX_RESTRAINTS 4
+/* This rank's share (rows of 128 atoms rank, rank+world, ...) of energy[1],
+ * force[n,3] and atomwise[n] (atomwise_spring_nrg :171-185; any may be NULL);
+ * the outputs are zeroed first, partial results are summed by the caller. */
+int iid_spring_partial(iid_handle *h, const double *pos_dev, int64_t n,
+                       int sp_type, double k, double rt, const double *com,
+                       double *energy_dev, double *force_dev,
+                       double *atomwise_dev, void *stream);
+/* Host arrays in and out; world must be 1. */
+int iid_spring_host(iid_handle *h, const double *pos_host, int64_t n,
+                    int sp_type, double k, double rt, const double *com,
+                    double *energy_host, double *forces_host,
+                    double *atomwise_host);
+/* Energy a probe atom adds at each voxel centre ((i+.5) resolution, C order
+ * [nx,ny,nz]); voxel_spring_nrg :150-168, :240-256, :314-332. */
+int iid_spring_voxel_host(iid_handle *h, const double *pos_host, int64_t n,
+                          int sp_type, double k, double rt, const double *com,
+                          double resolution, int64_t nx, int64_t ny,
+                          int64_t nz, double *voxels_host);
+/* rep / att restraints evaluated inside iid_energy_forces_host (same CUDA
+ * graph): their forces are added to forces_host, their summed energy is read
+ * with iid_get_restraint_energy after the call.  count = 0 clears. */
+int iid_set_restraints(iid_handle *h, int count, const int *sp_type,
+                       const double *k, const double *rt);
+int iid_get_restraint_energy(iid_handle *h, double *energy);
+
 /* Device array -> pageable host memory through pipelined pinned staging,
  * ordered after the work already enqueued on the handle's stream; complete on
  * return.  (The multi-GPU host layer uses it after the NCCL all-reduce.) */

@@ -25,6 +25,37 @@ _ES = 'pyiid/experiments/elasticscatter'
 _mods = {}
 
 
+_ref_namespace = {}   # the reference's modules and their stub parents
+
+
+def _is_ref_name(k):
+    return k == 'pyiid' or k.startswith('pyiid.') or k == 'ase' or k.startswith('ase.')
+
+
+def _isolated(fn):
+    """Run a loader with the reference's module names in ``sys.modules`` and
+    put back whatever was registered under those names before (this
+    repository ships a ``pyiid`` alias package and an ``ase`` shim that must
+    not be shadowed by the stubs once the loader returns)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        if getattr(_isolated, 'depth', 0):
+            return fn(*args, **kw)
+        saved = {k: sys.modules.pop(k) for k in list(sys.modules) if _is_ref_name(k)}
+        sys.modules.update(_ref_namespace)
+        _isolated.depth = 1
+        try:
+            return fn(*args, **kw)
+        finally:
+            _isolated.depth = 0
+            for k in [k for k in sys.modules if _is_ref_name(k)]:
+                _ref_namespace[k] = sys.modules.pop(k)
+            sys.modules.update(saved)
+    return wrapper
+
+
 def available():
     return os.path.isdir(os.path.join(REF_ROOT, _ES, 'kernels'))
 
@@ -66,6 +97,7 @@ def _ensure_parents():
             sys.modules[pkg] = m
 
 
+@_isolated
 def kernels(precision='fp32'):
     """Return (kernels/__init__, cpu_flat, cpu_experimental, master_kernel)."""
     if not available():
@@ -83,6 +115,7 @@ def kernels(precision='fp32'):
     return base, flat, exp, mk
 
 
+@_isolated
 def nxn_kernels():
     _ensure_parents()
     kernels()
@@ -155,3 +188,28 @@ def ref_grad_fq(positions, scatter, qbin, precision='fp32'):
 
 def master():
     return kernels()[3]
+
+
+@_isolated
+def spring():
+    """The reference's pyiid/calc/spring_calc.py as a module (its Calculator
+    base class is stubbed when ASE is absent; the module-level functions take
+    any object with get_positions / get_center_of_mass / get_cell / __len__)."""
+    if not available():
+        raise RuntimeError('reference mount not present: ' + REF_ROOT)
+    nxn_kernels()
+    if 'ase.calculators.calculator' not in sys.modules:
+        ase = types.ModuleType('ase')
+        ase.__path__ = []
+        calcs = types.ModuleType('ase.calculators')
+        calcs.__path__ = []
+        calc = types.ModuleType('ase.calculators.calculator')
+        calc.Calculator = type('Calculator', (object,), {})
+        sys.modules.setdefault('ase', ase)
+        sys.modules['ase.calculators'] = calcs
+        sys.modules['ase.calculators.calculator'] = calc
+    if 'pyiid.calc' not in sys.modules:
+        m = types.ModuleType('pyiid.calc')
+        m.__path__ = []
+        sys.modules['pyiid.calc'] = m
+    return _load('pyiid.calc.spring_calc_reference', 'pyiid/calc/spring_calc.py')

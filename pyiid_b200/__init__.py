@@ -7,6 +7,8 @@ alias package at the repository root):
   (reference ``pyiid.experiments.elasticscatter.ElasticScatter``)
 * :class:`pyiid_b200.calc.Calc1D`, :func:`pyiid_b200.calc.PDFCalc`
   (reference ``pyiid.calc.calc_1d.Calc1D``)
+* :class:`pyiid_b200.spring_calc.Spring`, :class:`pyiid_b200.multi_calc.MultiCalc`
+  (reference ``pyiid.calc.spring_calc`` / ``pyiid.calc.multi_calc``)
 * :mod:`pyiid_b200.sim` -- ``leapfrog``, ``NUTSCanonicalEnsemble``
   (reference ``pyiid.sim``)
 
@@ -21,6 +23,8 @@ ase_shim.install()
 
 from .elasticscatter import ElasticScatter, wrap_atoms  # noqa: E402
 from .calc import Calc1D, PDFCalc  # noqa: E402
+from .spring_calc import Spring  # noqa: E402
+from .multi_calc import MultiCalc  # noqa: E402
 
-__all__ = ['ElasticScatter', 'wrap_atoms', 'Calc1D', 'PDFCalc']
+__all__ = ['ElasticScatter', 'wrap_atoms', 'Calc1D', 'PDFCalc', 'Spring', 'MultiCalc']
 __version__ = '0.1.0'

@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_HERE, 'libiid_b200.so')
 
 IID_FP32, IID_FP64 = 0, 1
 IID_POT_RW, IID_POT_CHI_SQ = 0, 1
+IID_SPRING_REP, IID_SPRING_COM, IID_SPRING_ATT = 0, 1, 2
+IID_MAX_RESTRAINTS = 4
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -51,6 +53,11 @@ SIGNATURES = {
     'iid_contract_host': [_vp, _vp, _int, _i64, _i64, _vp, _vp],
     'iid_fq_to_gr_host': [_vp, _vp, _vp],
     'iid_download_host': [_vp, _vp, _vp, _i64],
+    'iid_spring_partial': [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp],
+    'iid_spring_host': [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _vp, _vp, _vp],
+    'iid_spring_voxel_host': [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _dbl, _i64, _i64, _i64, _vp],
+    'iid_set_restraints': [_vp, _int, _vp, _vp, _vp],
+    'iid_get_restraint_energy': [_vp, _vp],
     'iid_set_option': [_vp, ctypes.c_char_p, _i64],
     'iid_launch_count': [_vp, _pi64],
     'iid_last_kernel_ms': [_vp, ctypes.POINTER(ctypes.c_float),

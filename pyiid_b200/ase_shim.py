@@ -63,10 +63,11 @@ def _parse_symbols(symbols):
 
 
 class Atom(object):
-    def __init__(self, symbol='X', position=(0, 0, 0)):
+    def __init__(self, symbol='X', position=(0, 0, 0), index=None):
         self.number = (atomic_numbers[symbol] if isinstance(symbol, str)
                        else int(symbol))
         self.position = np.array(position, dtype=float)
+        self.index = index
 
     @property
     def symbol(self):
@@ -202,6 +203,12 @@ class Atoms(object):
         p = self.arrays['positions']
         if len(p) == 0:
             return
+        if vacuum is not None:
+            # orthorhombic cell with `vacuum` on both sides of the atoms
+            extent = p.max(0) - p.min(0)
+            for a in np.atleast_1d(axis):
+                self.cell[a] = 0.0
+                self.cell[a, a] = extent[a] + 2.0 * vacuum
         box_centre = 0.5 * (p.min(0) + p.max(0))
         target = 0.5 * self.cell.sum(0) if about is None else np.array(about)
         shift = target - box_centre
@@ -231,6 +238,17 @@ class Atoms(object):
         new.extend(other)
         return new
 
+    def __iadd__(self, other):
+        self.extend(other)
+        return self
+
+    def get_cell(self):
+        return self.cell.copy()
+
+    def set_cell(self, cell):
+        cell = np.array(cell, float)
+        self.cell = np.diag(cell) if cell.shape == (3,) else cell
+
     def extend(self, other):
         if isinstance(other, Atom):
             other = Atoms(numbers=[other.number], positions=[other.position])
@@ -248,7 +266,11 @@ class Atoms(object):
 
     def __getitem__(self, i):
         if isinstance(i, (int, np.integer)):
-            return Atom(int(self.arrays['numbers'][i]), self.arrays['positions'][i])
+            n = len(self)
+            if i < -n or i >= n:
+                raise IndexError('Index out of range.')
+            return Atom(int(self.arrays['numbers'][i]), self.arrays['positions'][i],
+                        index=int(i) % n)
         new = self.__class__(numbers=self.arrays['numbers'][i],
                              positions=self.arrays['positions'][i],
                              cell=self.cell.copy(), pbc=self.pbc.copy(),

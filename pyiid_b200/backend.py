@@ -23,6 +23,9 @@ from . import _lib
 from ._lib import IID_FP32, IID_FP64, IID_POT_RW, IID_POT_CHI_SQ, check
 
 POTENTIALS = {'rw': IID_POT_RW, 'chi_sq': IID_POT_CHI_SQ}
+SPRING_TYPES = {'rep': _lib.IID_SPRING_REP, 'com': _lib.IID_SPRING_COM,
+                'att': _lib.IID_SPRING_ATT}
+SPRING_TYPES.update({v: v for v in list(SPRING_TYPES.values())})
 
 
 def _dist_state():
@@ -147,6 +150,8 @@ class Backend(object):
         self._last_numbers = None
         self._last_target = None
         self._target_key = None
+        self._restraints = []
+        self.restraint_energy = 0.0
         self.n = self.nq = self.nr = 0
         self.rank, self.world = 0, 1
         self._tensors = {}
@@ -347,6 +352,8 @@ class Backend(object):
                 forces.ctypes.data if want_forces else None,
                 pdf.ctypes.data if want_pdf else None))
             self._target_key = tkey
+            if self._restraints:
+                self._read_restraint_energy()
             return out[0], out[1], forces, pdf
         import torch
         import torch.distributed as dist
@@ -371,12 +378,96 @@ class Backend(object):
             if want_forces:
                 check(self.lib.iid_force_partial(self.h, p.data_ptr(), wq.data_ptr(),
                                                  fo.data_ptr(), st))
+            if self._restraints:
+                es = self._t('e_sp', (len(self._restraints),), torch.float64)
+                fs = self._t('force_sp', (self.n, 3), torch.float64)
+                for i, (ty, kk, rt) in enumerate(self._restraints):
+                    check(self.lib.iid_spring_partial(
+                        self.h, p.data_ptr(), self.n, ty, kk, rt, None,
+                        es.data_ptr() + 8 * i,
+                        fs.data_ptr() if want_forces else None, None, st))
+                    if want_forces:
+                        fo += fs
+                dist.all_reduce(es)
+                self.restraint_energy = float(es.sum().item())
+            if want_forces:
                 dist.all_reduce(fo)
                 forces = fo.cpu().numpy()
             out = o4.cpu().numpy()
             if want_pdf:
                 pdf = gr.cpu().numpy()
         return out[0], out[1], forces, pdf
+
+    # -- spring restraints (calc/spring_calc.py) -------------------------------
+    def set_restraints(self, springs):
+        """rep / att springs [(sp_type, k, rt), ...] evaluated inside
+        energy_forces (same CUDA graph, forces summed on the device)."""
+        springs = [(SPRING_TYPES[t], float(k), float(rt)) for t, k, rt in springs]
+        if springs != self._restraints:
+            ty = np.array([s[0] for s in springs], np.int32)
+            kk = np.array([s[1] for s in springs], np.float64)
+            rt = np.array([s[2] for s in springs], np.float64)
+            check(self.lib.iid_set_restraints(self.h, len(springs), ty.ctypes.data,
+                                              kk.ctypes.data, rt.ctypes.data))
+            self._restraints = springs
+        self.restraint_energy = 0.0
+
+    def _read_restraint_energy(self):
+        e = ctypes.c_double(0.0)
+        check(self.lib.iid_get_restraint_energy(self.h, ctypes.byref(e)))
+        self.restraint_energy = e.value
+
+    def spring(self, positions, sp_type, k, rt, com=None, want_energy=True,
+               want_forces=False, want_atomwise=False):
+        """(energy, forces[N,3], atomwise[N]) of one spring restraint; entries
+        not asked for are None."""
+        pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        n = len(pos)
+        ty = SPRING_TYPES[sp_type]
+        cm = None if com is None else np.ascontiguousarray(com, dtype=np.float64)
+        if ty == _lib.IID_SPRING_COM and (cm is None or cm.shape != (3,)):
+            raise ValueError('the com spring needs the centre of mass')
+        cptr = None if cm is None else cm.ctypes.data
+        self.sync_shard()
+        if self.world == 1:
+            e = ctypes.c_double(0.0)
+            f = np.zeros((n, 3), np.float64) if want_forces else None
+            a = np.zeros(n, np.float64) if want_atomwise else None
+            check(self.lib.iid_spring_host(
+                self.h, pos.ctypes.data, n, ty, float(k), float(rt), cptr,
+                ctypes.byref(e) if want_energy else None,
+                f.ctypes.data if want_forces else None,
+                a.ctypes.data if want_atomwise else None))
+            return (e.value if want_energy else None), f, a
+        import torch
+        import torch.distributed as dist
+        with torch.cuda.device(self.device), self._on_stream():
+            dev = 'cuda:%d' % self.device
+            p = torch.from_numpy(pos).to(dev)
+            buf = torch.zeros(4 * n + 1, dtype=torch.float64, device=dev)
+            base = buf.data_ptr()
+            check(self.lib.iid_spring_partial(
+                self.h, p.data_ptr(), n, ty, float(k), float(rt), cptr,
+                base + 32 * n if want_energy else None,
+                base if want_forces else None,
+                base + 24 * n if want_atomwise else None, self._stream()))
+            dist.all_reduce(buf)
+            out = buf.cpu().numpy()
+        return (float(out[4 * n]) if want_energy else None,
+                out[:3 * n].reshape(n, 3).copy() if want_forces else None,
+                out[3 * n:4 * n].copy() if want_atomwise else None)
+
+    def spring_voxels(self, positions, sp_type, k, rt, resolution, shape, com=None):
+        """Energy added by a probe atom at every voxel centre."""
+        pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        nx, ny, nz = (int(v) for v in shape)
+        cm = None if com is None else np.ascontiguousarray(com, dtype=np.float64)
+        vox = np.zeros((nx, ny, nz), np.float64)
+        check(self.lib.iid_spring_voxel_host(
+            self.h, pos.ctypes.data, len(pos), SPRING_TYPES[sp_type], float(k),
+            float(rt), None if cm is None else cm.ctypes.data, float(resolution),
+            nx, ny, nz, vox.ctypes.data))
+        return vox
 
     def grad_pdf(self, grad_fq):
         """[rows.., R] = grad_fq[rows.., Q] . T^T on the device

@@ -96,6 +96,17 @@ def _bound_to(func, name):
     return None
 
 
+def translation_aware_changes(calc, atoms, tol=1e-15):
+    """Calculator.check_state that ignores a rigid translation of the atoms."""
+    changes = Calculator.check_state(calc, atoms, tol)
+    if changes == ['positions'] and calc.atoms is not None and \
+            len(calc.atoms) == len(atoms) and len(atoms) > 0:
+        old, new = calc.atoms.positions, atoms.positions
+        if np.abs((new - new[0]) - (old - old[0])).max() <= 1e-10:
+            return []
+    return changes
+
+
 class Calc1D(Calculator):
     """PDF / F(Q) based Rw or chi^2 calculator (``calc/calc_1d.py:9-101``)."""
     implemented_properties = ['energy', 'forces']
@@ -147,13 +158,7 @@ class Calc1D(Calculator):
         rigid translation; leapfrog re-centres the atoms after its last force
         evaluation (pyiid/sim/__init__.py:36-37), which must not invalidate
         the cached results."""
-        changes = Calculator.check_state(self, atoms, tol)
-        if changes == ['positions'] and self.atoms is not None and \
-                len(self.atoms) == len(atoms) and len(atoms) > 0:
-            old, new = self.atoms.positions, atoms.positions
-            if np.abs((new - new[0]) - (old - old[0])).max() <= 1e-10:
-                return []
-        return changes
+        return translation_aware_changes(self, atoms, tol)
 
     def calculate(self, atoms=None, properties=['energy'],
                   system_changes=['positions', 'numbers', 'cell', 'pbc',

@@ -18,6 +18,7 @@
 #include "iid_debye64.cuh"
 #include "iid_force_table.cuh"
 #include "iid_small.cuh"
+#include "iid_spring.cuh"
 
 using namespace iid;
 
@@ -85,6 +86,13 @@ struct iid_handle {
     // M = T^T T, vgo = T^T target, coef from the potential kernel
     double *Mq = nullptr, *vgo = nullptr, *coef = nullptr;
     bool vgo_valid = false;
+    // spring restraints fused into iid_energy_forces_host (iid_spring.cuh)
+    int n_restraints = 0;
+    int rs_type[IID_MAX_RESTRAINTS] = {0};
+    double rs_k[IID_MAX_RESTRAINTS] = {0}, rs_rt[IID_MAX_RESTRAINTS] = {0};
+    // scratch of the stand-alone spring calls
+    double *sp_buf = nullptr;
+    size_t sp_count = 0;
     bool use_force_table = true;
     int64_t force_table_min_n = 1500;  // below this the direct kernel is faster
     // pinned staging for the gradient's way back to pageable host memory
@@ -163,7 +171,8 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
-    CU(cudaMalloc((void **)&h->out4, 4 * sizeof(double)));
+    CU(cudaMalloc((void **)&h->out4, 8 * sizeof(double)));
+    CU(cudaMemset(h->out4, 0, 8 * sizeof(double)));
     if (const char *s = getenv("IID_NW")) h->nw_max = std::max(1, std::min(12, atoi(s)));
     h->nw_max = std::min(h->nw_max, 12);
     if (const char *s = getenv("IID_GRAPH")) h->use_graph = atoi(s) != 0;
@@ -184,7 +193,7 @@ extern "C" int iid_destroy(iid_handle *h)
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
                     h->inv_na, h->inv_na_d, h->items_tri, h->items_sq, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
-                    h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef};
+                    h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pinG) cudaFreeHost(h->pinG);
@@ -917,6 +926,179 @@ extern "C" int iid_pdf_host(iid_handle *h, const double *pos_host, double *pdf_h
     return 0;
 }
 
+// --- spring restraints (iid_spring.cuh) ----------------------------------------
+static int launch_spring(iid_handle *h, const double *pos, int64_t n, int sp_type, double k,
+                         double rt, const double *com, double *energy, double *force,
+                         double *atomwise, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    const int rows = (int)((n + SP_BLOCK - 1) / SP_BLOCK);
+    const int my_rows = (rows - h->rank + h->world - 1) / h->world;  // rows rank, rank+W, ...
+    if (my_rows <= 0) return 0;
+    const bool f32 = h->precision == IID_FP32;
+    if (sp_type == SPRING_COM) {
+        if (!com) return fail(IID_E_BADARG, "the com spring needs the centre of mass");
+        if (f32)
+            spring_com_kernel<true><<<my_rows, SP_BLOCK, 0, st>>>(
+                pos, (int)n, k, rt, com[0], com[1], com[2], h->rank, h->world, energy, force,
+                atomwise);
+        else
+            spring_com_kernel<false><<<my_rows, SP_BLOCK, 0, st>>>(
+                pos, (int)n, k, rt, com[0], com[1], com[2], h->rank, h->world, energy, force,
+                atomwise);
+    } else {
+        // split the j range until the grid covers the SMs about twice
+        int jsplit = std::max(1, std::min(rows, (2 * h->sm_count + my_rows - 1) / my_rows));
+        const dim3 grid((unsigned)my_rows, (unsigned)jsplit);
+        const int att = sp_type == SPRING_ATT;
+        if (f32)
+            spring_pair_kernel<true><<<grid, SP_BLOCK, 0, st>>>(
+                pos, (int)n, att, k, rt, jsplit, h->rank, h->world, energy, force, atomwise);
+        else
+            spring_pair_kernel<false><<<grid, SP_BLOCK, 0, st>>>(
+                pos, (int)n, att, k, rt, jsplit, h->rank, h->world, energy, force, atomwise);
+    }
+    ++h->launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int check_spring(int sp_type, int64_t n)
+{
+    if (sp_type != SPRING_REP && sp_type != SPRING_COM && sp_type != SPRING_ATT)
+        return fail(IID_E_BADARG, "unknown spring type");
+    if (n < 0 || n > (int64_t)1 << 30) return fail(IID_E_BADARG, "bad atom count");
+    return 0;
+}
+
+extern "C" int iid_spring_partial(iid_handle *h, const double *pos_dev, int64_t n, int sp_type,
+                                  double k, double rt, const double *com, double *energy_dev,
+                                  double *force_dev, double *atomwise_dev, void *stream)
+{
+    NEED(h);
+    int rc;
+    if ((rc = check_spring(sp_type, n))) return rc;
+    if (n > 0 && !pos_dev) return fail(IID_E_BADARG, "null positions");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (energy_dev) CU(cudaMemsetAsync(energy_dev, 0, sizeof(double), st));
+    if (force_dev && n) CU(cudaMemsetAsync(force_dev, 0, (size_t)n * 3 * sizeof(double), st));
+    if (atomwise_dev && n) CU(cudaMemsetAsync(atomwise_dev, 0, (size_t)n * sizeof(double), st));
+    return launch_spring(h, pos_dev, n, sp_type, k, rt, com, energy_dev, force_dev, atomwise_dev,
+                         st);
+}
+
+static int spring_scratch(iid_handle *h, size_t count)
+{
+    if (count <= h->sp_count) return 0;
+    int rc = dev_alloc(&h->sp_buf, count);
+    h->sp_count = rc ? 0 : count;
+    return rc;
+}
+
+extern "C" int iid_spring_host(iid_handle *h, const double *pos_host, int64_t n, int sp_type,
+                               double k, double rt, const double *com, double *energy_host,
+                               double *forces_host, double *atomwise_host)
+{
+    NEED(h);
+    int rc;
+    if ((rc = check_spring(sp_type, n))) return rc;
+    if (n > 0 && !pos_host) return fail(IID_E_BADARG, "null positions");
+    if (h->world != 1)
+        return fail(IID_E_BADARG, "iid_spring_host needs all rows (world == 1)");
+    if (n == 0) {
+        if (energy_host) *energy_host = 0.0;
+        return 0;
+    }
+    // [0,3n) positions, [3n,6n) force, [6n,7n) atomwise, [7n] energy
+    if ((rc = spring_scratch(h, (size_t)7 * n + 1))) return rc;
+    double *b = h->sp_buf;
+    CU(cudaMemcpyAsync(b, pos_host, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice,
+                       h->stream));
+    if ((rc = iid_spring_partial(h, b, n, sp_type, k, rt, com, energy_host ? b + 7 * n : nullptr,
+                                 forces_host ? b + 3 * n : nullptr,
+                                 atomwise_host ? b + 6 * n : nullptr, nullptr)))
+        return rc;
+    if (energy_host)
+        CU(cudaMemcpyAsync(energy_host, b + 7 * n, sizeof(double), cudaMemcpyDeviceToHost,
+                           h->stream));
+    if (forces_host)
+        CU(cudaMemcpyAsync(forces_host, b + 3 * n, (size_t)3 * n * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->stream));
+    if (atomwise_host)
+        CU(cudaMemcpyAsync(atomwise_host, b + 6 * n, (size_t)n * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int iid_spring_voxel_host(iid_handle *h, const double *pos_host, int64_t n, int sp_type,
+                                     double k, double rt, const double *com, double resolution,
+                                     int64_t nx, int64_t ny, int64_t nz, double *voxels_host)
+{
+    NEED(h);
+    int rc;
+    if ((rc = check_spring(sp_type, n))) return rc;
+    if (!voxels_host || nx < 0 || ny < 0 || nz < 0 || !(resolution > 0.0))
+        return fail(IID_E_BADARG, "bad voxel grid");
+    if (n > 0 && !pos_host) return fail(IID_E_BADARG, "null positions");
+    if (sp_type == SPRING_COM && !com)
+        return fail(IID_E_BADARG, "the com spring needs the centre of mass");
+    const int64_t nv = nx * ny * nz;
+    if (nv == 0) return 0;
+    if (nx > 65535 || ny > 65535 || nz > 65535 || nv > (int64_t)1 << 31)
+        return fail(IID_E_BADARG, "voxel grid too large");
+    if ((rc = spring_scratch(h, (size_t)3 * n + (size_t)nv))) return rc;
+    double *b = h->sp_buf, *vox = b + 3 * n;
+    if (n)
+        CU(cudaMemcpyAsync(b, pos_host, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice,
+                           h->stream));
+    const unsigned blocks = (unsigned)((nv + SP_BLOCK - 1) / SP_BLOCK);
+    const double c0 = com ? com[0] : 0.0, c1 = com ? com[1] : 0.0, c2 = com ? com[2] : 0.0;
+    if (h->precision == IID_FP32)
+        spring_voxel_kernel<true><<<blocks, SP_BLOCK, 0, h->stream>>>(
+            b, (int)n, sp_type, k, rt, c0, c1, c2, resolution, (int)nx, (int)ny, (int)nz, vox);
+    else
+        spring_voxel_kernel<false><<<blocks, SP_BLOCK, 0, h->stream>>>(
+            b, (int)n, sp_type, k, rt, c0, c1, c2, resolution, (int)nx, (int)ny, (int)nz, vox);
+    ++h->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(voxels_host, vox, (size_t)nv * sizeof(double), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int iid_set_restraints(iid_handle *h, int count, const int *sp_type, const double *k,
+                                  const double *rt)
+{
+    if (!h) return fail(IID_E_BADARG, "null handle");
+    if (count < 0 || count > IID_MAX_RESTRAINTS)
+        return fail(IID_E_BADARG, "at most IID_MAX_RESTRAINTS restraints");
+    if (count && (!sp_type || !k || !rt)) return fail(IID_E_BADARG, "null pointer");
+    for (int s = 0; s < count; ++s)
+        if (sp_type[s] != SPRING_REP && sp_type[s] != SPRING_ATT)
+            return fail(IID_E_BADARG, "only rep / att springs can be fused");
+    bool same = count == h->n_restraints;
+    for (int s = 0; same && s < count; ++s)
+        same = sp_type[s] == h->rs_type[s] && k[s] == h->rs_k[s] && rt[s] == h->rs_rt[s];
+    if (same) return 0;
+    h->n_restraints = count;
+    for (int s = 0; s < count; ++s) {
+        h->rs_type[s] = sp_type[s];
+        h->rs_k[s] = k[s];
+        h->rs_rt[s] = rt[s];
+    }
+    drop_graph(h);  // k / rt are kernel arguments baked into the graph
+    return 0;
+}
+
+extern "C" int iid_get_restraint_energy(iid_handle *h, double *energy)
+{
+    if (!h || !energy) return fail(IID_E_BADARG, "null argument");
+    *energy = h->n_restraints && h->pin ? h->pin[6 * h->n + h->qp + 4] : 0.0;
+    return 0;
+}
+
 extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
                                       const double *target_host, int potential, double conv,
                                       double *out_host, double *forces_host, double *pdf_host)
@@ -975,6 +1157,13 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
             ++h->launches;
             CU(cudaGetLastError());
         }
+        if (!forces_host && h->n_restraints) {
+            CU(cudaMemsetAsync(h->out4 + 4, 0, sizeof(double), h->stream));
+            for (int s = 0; s < h->n_restraints; ++s)
+                if ((rc2 = launch_spring(h, h->pos, h->n, h->rs_type[s], h->rs_k[s], h->rs_rt[s],
+                                         nullptr, h->out4 + 4, nullptr, nullptr, h->stream)))
+                    return rc2;
+        }
         if (forces_host && h->qspace_wq) {
             wq_from_q_kernel<<<(unsigned)((h->nq + 31) / 32), 1024, 0, h->stream>>>(
                 h->Mq, h->F, h->vgo, h->coef, (int)h->nq, (int)h->qp, conv, h->wq);
@@ -985,10 +1174,18 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
             // positions are already staged by iid_fq_partial; enqueue the force pass
             CU(cudaMemsetAsync(h->force, 0, (size_t)h->n * 3 * sizeof(double), h->stream));
             if ((rc2 = launch_force(h, h->wq, h->force, h->stream))) return rc2;
+            if (h->n_restraints) {
+                CU(cudaMemsetAsync(h->out4 + 4, 0, sizeof(double), h->stream));
+                for (int s = 0; s < h->n_restraints; ++s)
+                    if ((rc2 = launch_spring(h, h->pos, h->n, h->rs_type[s], h->rs_k[s],
+                                             h->rs_rt[s], nullptr, h->out4 + 4, h->force, nullptr,
+                                             h->stream)))
+                        return rc2;
+            }
             CU(cudaMemcpyAsync(pfor, h->force, (size_t)3 * h->n * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
         }
-        CU(cudaMemcpyAsync(po, h->out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(po, h->out4, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         if (pdf_host)
             CU(cudaMemcpyAsync(pg, h->Gr, h->nr * sizeof(double), cudaMemcpyDeviceToHost,
                                h->stream));

@@ -325,17 +325,25 @@ class ElasticScatter(object):
 
     # -- fused path used by Calc1D ------------------------------------------------
     def get_pdf_energy_forces(self, atoms, target, potential='rw', conv=1.,
-                              want_forces=True):
+                              want_forces=True, restraints=None):
         """Rw / chi^2 of ``get_pdf(atoms)`` against ``target`` and its forces in
         one evaluation: what ``Calc1D`` computes from ``get_pdf`` +
         ``get_grad_pdf`` (``pyiid/calc/calc_1d.py:78-95``) without the
-        N x 3 x R gradient array.  Returns (energy, scale, forces)."""
+        N x 3 x R gradient array.  Returns (energy, scale, forces).
+
+        ``restraints``: [(sp_type, k, rt), ...] rep / att springs
+        (``pyiid/calc/spring_calc.py``) evaluated in the same device sequence;
+        their forces are included in ``forces`` and their energy is returned
+        as a fourth value."""
         self._ensure_wrapped(atoms)
         be = self._load(atoms, self.pdf_qbin, 'PDF')
         be.set_transform(self.exp['rstep'], self.pdf_qbin, self.get_r(),
                          self.exp['qmin'])
+        be.set_restraints(restraints or [])
         e, scale, forces, _ = be.energy_forces(
             atoms.get_positions(), target, potential, conv, want_forces)
+        if restraints is not None:
+            return e, scale, forces, be.restraint_energy
         return e, scale, forces
 
 

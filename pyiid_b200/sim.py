@@ -164,6 +164,11 @@ class _FastSystem(object):
 
     def __init__(self, atoms):
         calc = atoms.get_calculator()
+        # Calc1D alone, or a MultiCalc of one Calc1D + rep / att springs (the
+        # springs ride in the same device sequence, multi_calc.py)
+        plan = getattr(calc, '_plan', None)
+        self.springs = plan[1] if plan is not None else []
+        calc = plan[0] if plan is not None else calc
         self.calc = calc
         self.scat = calc._fused
         self.template = atoms
@@ -175,17 +180,21 @@ class _FastSystem(object):
     @staticmethod
     def usable(atoms):
         from .calc import Calc1D
+        from .multi_calc import MultiCalc
         calc = atoms.get_calculator() if hasattr(atoms, 'get_calculator') else None
+        if isinstance(calc, MultiCalc):
+            return calc._plan is not None
         return isinstance(calc, Calc1D) and calc._fused is not None
 
     def evaluate(self, q):
         scat, calc = self.scat, self.calc
         be = scat._load(self.template, scat.pdf_qbin, 'PDF')
         be.set_transform(scat.exp['rstep'], scat.pdf_qbin, scat.get_r(), scat.exp['qmin'])
+        be.set_restraints(self.springs)
         e, scale, f, _ = be.energy_forces(q, calc.target_data, calc.potential_name,
                                           calc.rw_to_eV, True)
         self.evals += 1
-        return float(e), f
+        return float(e) + be.restraint_energy, f
 
     def kinetic(self, p):
         return 0.5 * float(np.vdot(p, p / self.masses))
