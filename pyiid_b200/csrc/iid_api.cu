@@ -948,7 +948,8 @@ static int launch_spring(iid_handle *h, const double *pos, int64_t n, int sp_typ
                 atomwise);
     } else {
         // split the j range until the grid covers the SMs about twice
-        int jsplit = std::max(1, std::min(rows, (2 * h->sm_count + my_rows - 1) / my_rows));
+        const int units = (int)((n + SP_JUNIT - 1) / SP_JUNIT);
+        int jsplit = std::max(1, std::min(units, (2 * h->sm_count + my_rows - 1) / my_rows));
         const dim3 grid((unsigned)my_rows, (unsigned)jsplit);
         const int att = sp_type == SPRING_ATT;
         if (f32)
@@ -1148,6 +1149,8 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
         // Rw / chi^2 in r space; the chain-rule weights in Q space:
         // wq = conv T^T c = conv (coef0 T^T go - coef1 (T^T T) F)
         if (!h->qspace_wq) {
+            if (h->n_restraints)
+                CU(cudaMemsetAsync(h->out4 + 4, 0, sizeof(double), h->stream));
             if ((rc2 = iid_potential(h, h->Gr, h->target, potential, conv, h->out4,
                                      forces_host ? h->wq : nullptr, nullptr)))
                 return rc2;
@@ -1158,7 +1161,6 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
             CU(cudaGetLastError());
         }
         if (!forces_host && h->n_restraints) {
-            CU(cudaMemsetAsync(h->out4 + 4, 0, sizeof(double), h->stream));
             for (int s = 0; s < h->n_restraints; ++s)
                 if ((rc2 = launch_spring(h, h->pos, h->n, h->rs_type[s], h->rs_k[s], h->rs_rt[s],
                                          nullptr, h->out4 + 4, nullptr, nullptr, h->stream)))
@@ -1175,7 +1177,7 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
             CU(cudaMemsetAsync(h->force, 0, (size_t)h->n * 3 * sizeof(double), h->stream));
             if ((rc2 = launch_force(h, h->wq, h->force, h->stream))) return rc2;
             if (h->n_restraints) {
-                CU(cudaMemsetAsync(h->out4 + 4, 0, sizeof(double), h->stream));
+                // out4[4] was zeroed by potential_kernel (Q-space path) / the memset above
                 for (int s = 0; s < h->n_restraints; ++s)
                     if ((rc2 = launch_spring(h, h->pos, h->n, h->rs_type[s], h->rs_k[s],
                                              h->rs_rt[s], nullptr, h->out4 + 4, h->force, nullptr,

@@ -152,6 +152,7 @@ __global__ void potential_kernel(const double *__restrict__ gc,
             // combination of the target and the model, see wq_from_q_kernel)
             coef[0] = pref * (scale + gdb);
             coef[1] = pref * (scale * scale + 2.0 * gdb * scale_true);
+            out[4] = 0.0;  // fused host path (out has 8 slots): restraint energy, summed later
         }
     }
 }

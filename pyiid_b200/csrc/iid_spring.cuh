@@ -82,8 +82,17 @@ __device__ __forceinline__ double block_sum_128(double v, double *sh)
 
 // rep / att.  pos = [n,3] float64 in the caller's atom order.  Block row =
 // SP_BLOCK atoms i (rows row_begin, row_begin + row_stride, ... belong to this
-// rank); blockIdx.y splits the j range.  Results are ADDED to energy[0],
-// force[n,3] and atomwise[n] (each may be null).
+// rank); blockIdx.y takes a share of the j atoms in units of SP_JUNIT.  Results
+// are ADDED to energy[0], force[n,3] and atomwise[n] (each may be null).
+//
+// Most ordered pairs are no hit (rep with a short rt), so four j atoms are
+// screened at a time on the squared distance alone -- r = sqrt_rn(t) is
+// monotonic in t, so t beyond rt^2 (1 +- margin) decides the comparison
+// without the square root -- and only candidate pairs take the exact path.
+constexpr int SP_JUNIT = 32;
+template <bool F32> struct SpringVec { using type = double4; };
+template <> struct SpringVec<true> { using type = float4; };
+
 template <bool F32>
 __global__ void __launch_bounds__(SP_BLOCK) spring_pair_kernel(
     const double *__restrict__ pos, int n, int att, double k, double rt, int jsplit,
@@ -91,7 +100,8 @@ __global__ void __launch_bounds__(SP_BLOCK) spring_pair_kernel(
     double *__restrict__ atomwise)
 {
     using R = typename SpringReal<F32>::type;
-    __shared__ R sx[SP_BLOCK], sy[SP_BLOCK], sz[SP_BLOCK];
+    using V = typename SpringVec<F32>::type;
+    __shared__ V sq[SP_BLOCK];
     __shared__ double red[SP_BLOCK / 32];
     const int row = row_begin + blockIdx.x * row_stride;
     const int i = row * SP_BLOCK + threadIdx.x;
@@ -101,43 +111,79 @@ __global__ void __launch_bounds__(SP_BLOCK) spring_pair_kernel(
     const R zi = vi ? (R)pos[(size_t)i * 3 + 2] : (R)0;
     const R kk = (R)k, rtt = (R)rt;
     const R half_k = (R)(0.5 * k);
-    const int ntiles = (n + SP_BLOCK - 1) / SP_BLOCK;
-    const int per = (ntiles + jsplit - 1) / jsplit;
-    const int t0 = blockIdx.y * per, t1 = min(ntiles, t0 + per);
+    // screening bound on t = r^2: the margin is far above the rounding of
+    // t and of the square root (6e-8 / 1e-16), so no hit is ever screened out
+    const double margin = F32 ? 1e-5 : 1e-12;
+    const R thr = (R)((double)rtt * (double)rtt * (att ? 1.0 - margin : 1.0 + margin));
+    const int nunits = (n + SP_JUNIT - 1) / SP_JUNIT;
+    const int per = (nunits + jsplit - 1) / jsplit;
+    const int jb = blockIdx.y * per * SP_JUNIT, je = min(n, jb + per * SP_JUNIT);
     double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0, aw = 0.0;
-    for (int t = t0; t < t1; ++t) {
-        const int j0 = t * SP_BLOCK, gj = j0 + threadIdx.x;
+
+    auto exact = [&](const V &q, int j) {
+        const SpringPair<F32> p(xi, yi, zi, q.x, q.y, q.z, kk, rtt, att != 0, j == i);
+        if (!p.hit) return;
+        const double mag = (double)p.mag, dr = (double)p.dr;
+        e += mag / 2. * dr;  // spring_calc.py:121
+        if (p.r > (R)0) {    // 0/0 -> NaN -> 0 (spring_calc.py:143)
+            fx = fma(p.unit(p.dx), mag, fx);
+            fy = fma(p.unit(p.dy), mag, fy);
+            fz = fma(p.unit(p.dz), mag, fz);
+        }
+        // atomwise (spring_calc.py:171-185): .5 k (r - rt)^2 in R
+        if constexpr (F32) aw += (double)__fmul_rn(half_k, __fmul_rn(p.dr, p.dr));
+        else aw += __dmul_rn(half_k, __dmul_rn(p.dr, p.dr));
+    };
+    auto t_of = [&](const V &q) -> R {
+        if constexpr (F32) {
+            const float dx = __fsub_rn(q.x, xi), dy = __fsub_rn(q.y, yi), dz = __fsub_rn(q.z, zi);
+            return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        } else {
+            const double dx = __dsub_rn(q.x, xi), dy = __dsub_rn(q.y, yi),
+                         dz = __dsub_rn(q.z, zi);
+            return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        }
+    };
+    auto maybe = [&](R t) { return att ? t > thr : t < thr; };
+
+    for (int j0 = jb; j0 < je; j0 += SP_BLOCK) {
+        const int gj = j0 + threadIdx.x;
         __syncthreads();
-        sx[threadIdx.x] = gj < n ? (R)pos[(size_t)gj * 3 + 0] : (R)0;
-        sy[threadIdx.x] = gj < n ? (R)pos[(size_t)gj * 3 + 1] : (R)0;
-        sz[threadIdx.x] = gj < n ? (R)pos[(size_t)gj * 3 + 2] : (R)0;
+        if (gj < je) {
+            V q;
+            q.x = (R)pos[(size_t)gj * 3 + 0];
+            q.y = (R)pos[(size_t)gj * 3 + 1];
+            q.z = (R)pos[(size_t)gj * 3 + 2];
+            q.w = (R)0;
+            sq[threadIdx.x] = q;
+        }
         __syncthreads();
         if (!vi) continue;
-        const int cnt = min(SP_BLOCK, n - j0);
-#pragma unroll 4
-        for (int jj = 0; jj < cnt; ++jj) {
-            const SpringPair<F32> p(xi, yi, zi, sx[jj], sy[jj], sz[jj], kk, rtt, att != 0,
-                                    j0 + jj == i);
-            if (!p.hit) continue;
-            const double mag = (double)p.mag, dr = (double)p.dr;
-            e += mag / 2. * dr;  // spring_calc.py:121
-            if (p.r > (R)0) {    // 0/0 -> NaN -> 0 (spring_calc.py:143)
-                fx = fma(p.unit(p.dx), mag, fx);
-                fy = fma(p.unit(p.dy), mag, fy);
-                fz = fma(p.unit(p.dz), mag, fz);
+        const int cnt = min(SP_BLOCK, je - j0);
+        int jj = 0;
+        for (; jj + 4 <= cnt; jj += 4) {
+            const V q0 = sq[jj], q1 = sq[jj + 1], q2 = sq[jj + 2], q3 = sq[jj + 3];
+            const R t0 = t_of(q0), t1 = t_of(q1), t2 = t_of(q2), t3 = t_of(q3);
+            const bool m0 = maybe(t0), m1 = maybe(t1), m2 = maybe(t2), m3 = maybe(t3);
+            if (m0 | m1 | m2 | m3) {
+                if (m0) exact(q0, j0 + jj);
+                if (m1) exact(q1, j0 + jj + 1);
+                if (m2) exact(q2, j0 + jj + 2);
+                if (m3) exact(q3, j0 + jj + 3);
             }
-            // atomwise (spring_calc.py:171-185): .5 k (r - rt)^2 in R
-            if constexpr (F32) aw += (double)__fmul_rn(half_k, __fmul_rn(p.dr, p.dr));
-            else aw += __dmul_rn(half_k, __dmul_rn(p.dr, p.dr));
+        }
+        for (; jj < cnt; ++jj) {
+            const V q = sq[jj];
+            if (maybe(t_of(q))) exact(q, j0 + jj);
         }
     }
     if (vi) {
-        if (force) {
+        if (force && (fx != 0.0 || fy != 0.0 || fz != 0.0)) {
             atomicAdd(&force[(size_t)i * 3 + 0], fx);
             atomicAdd(&force[(size_t)i * 3 + 1], fy);
             atomicAdd(&force[(size_t)i * 3 + 2], fz);
         }
-        if (atomwise) atomicAdd(&atomwise[i], -2.0 * aw);
+        if (atomwise && aw != 0.0) atomicAdd(&atomwise[i], -2.0 * aw);
     }
     if (energy) {
         const double tot = block_sum_128(e, red);

@@ -49,6 +49,38 @@ for prec, tol in (('fp32', 1e-5), ('fp64', 1e-10)):
     lo, hi = t.clone(), t.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     assert torch.equal(lo, hi)
+# spring restraints: rows of 128 atoms are dealt to the ranks, partial energies
+# and forces all-reduced; MultiCalc sums them with the sharded Calc1D
+from oracle import spring as osp
+from pyiid_b200.spring_calc import Spring
+from pyiid_b200.multi_calc import MultiCalc
+from pyiid_b200.backend import Backend
+pos = atoms.get_positions(); com = atoms.get_center_of_mass()
+for prec in ('fp32', 'fp64'):
+    be = Backend.get(prec, None, 'fq')
+    assert be.world == 2
+    for t, k, rt in (('rep', 10., 3.2), ('att', .5, 9.), ('com', 2., 8.)):
+        e, f, aw = be.spring(pos, t, k, rt, com, True, True, True)
+        if t == 'com':
+            eo, fo = osp.com_energy(pos, com, k, rt, prec), osp.com_force(pos, com, k, rt, prec)
+        else:
+            eo, fo = osp.pair_energy(pos, k, rt, t, prec), osp.pair_force(pos, k, rt, t, prec)
+        assert abs(e - eo) <= 1e-12 * max(1., abs(eo)), (t, e, eo)
+        assert np.abs(f - fo).max() <= 1e-11 * max(1., np.abs(fo).max())
+    scat = ElasticScatter(precision=prec)
+    target = scat.get_pdf(ideal)
+    c1 = Calc1D(target_data=target, exp_function=scat.get_pdf,
+                exp_grad_function=scat.get_grad_pdf, conv=10., potential='rw')
+    s1 = Spring(k=10., rt=3.2, sp_type='rep', precision=prec)
+    multi = MultiCalc(calc_list=[c1, s1])
+    assert multi._plan is not None
+    a = atoms.copy(); a.set_calculator(multi)
+    b = atoms.copy(); b.set_calculator(Calc1D(target_data=target, exp_function=scat.get_pdf,
+                                              exp_grad_function=scat.get_grad_pdf, conv=10.))
+    c = atoms.copy(); c.set_calculator(Spring(k=10., rt=3.2, sp_type='rep', precision=prec))
+    e_sum = b.get_potential_energy() + c.get_potential_energy()
+    assert abs(a.get_potential_energy() - e_sum) <= 1e-10 * abs(e_sum)
+    assert nerr(a.get_forces(), b.get_forces() + c.get_forces()) < 1e-9
 dist.barrier()
 if rank == 0:
     print('MULTIGPU_OK')
