@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -245,7 +246,7 @@ extern "C" int iid_set_shard(iid_handle *h, int rank, int world)
 // diagonal item; square lists (full gradient) take every j.
 static void build_items(const std::vector<int> &run_begin,
                         const std::vector<int> &run_end, int np, int slab,
-                        bool triangle, std::vector<WorkItem> &out)
+                        bool triangle, std::vector<WorkItem> &out, int gran = TILE_I)
 {
     const int ntile = np / TILE_I;
     out.clear();
@@ -254,10 +255,11 @@ static void build_items(const std::vector<int> &run_begin,
         for (size_t b = 0; b < run_begin.size(); ++b) {
             const int rb = run_begin[b], re = std::min(run_end[b], jlimit);
             if (re <= rb) continue;
-            // equal slabs of at most `slab` atoms, multiples of 32
+            // equal slabs of at most `slab` atoms, multiples of `gran` (32, or
+            // the 8-atom j tile of the F(Q) / force kernels for small structures)
             const int len = re - rb;
             const int nsl = (len + slab - 1) / slab;
-            const int per = ((len + nsl - 1) / nsl + TILE_I - 1) / TILE_I * TILE_I;
+            const int per = ((len + nsl - 1) / nsl + gran - 1) / gran * gran;
             for (int j0 = rb; j0 < re; j0 += per)
                 out.push_back({it, j0, std::min(re, j0 + per), (int)b});
         }
@@ -274,6 +276,50 @@ static void build_items(const std::vector<int> &run_begin,
     std::stable_sort(out.begin(), out.end(), [](const WorkItem &a, const WorkItem &b) {
         return (a.jend - a.jbegin) > (b.jend - b.jbegin);
     });
+}
+
+// Small structures (a few waves of blocks at most): the triangle list of
+// 32-atom slabs leaves the machine half idle in its last wave (Au561: 171
+// items on 148 SMs).  Choose the slab cap, in units of the 8-atom j tile, that
+// minimises the makespan of a longest-first schedule on `slots` SMs, counting
+// a fixed per-item cost (prologue + flush, about one and a half j tiles).
+static int pick_small_slab(const std::vector<int> &run_begin, const std::vector<int> &run_end,
+                           int np, int slots)
+{
+    constexpr int GRAN = 8, FIXED = 12;
+    const int ntile = np / TILE_I;
+    int best = TILE_I;
+    long best_cost = -1;
+    std::vector<int> lens;
+    std::vector<long> load;
+    for (int cap = GRAN; cap <= 512; cap += GRAN) {
+        lens.clear();
+        for (int it = 0; it < ntile; ++it) {
+            const int jlimit = it * TILE_I;
+            for (size_t b = 0; b < run_begin.size(); ++b) {
+                const int rb = run_begin[b], re = std::min(run_end[b], jlimit);
+                if (re <= rb) continue;
+                const int len = re - rb, nsl = (len + cap - 1) / cap;
+                const int per = ((len + nsl - 1) / nsl + GRAN - 1) / GRAN * GRAN;
+                for (int j0 = 0; j0 < len; j0 += per) lens.push_back(std::min(per, len - j0));
+            }
+            lens.push_back(TILE_I);  // diagonal item
+        }
+        std::sort(lens.begin(), lens.end(), std::greater<int>());
+        load.assign((size_t)slots, 0);
+        std::make_heap(load.begin(), load.end(), std::greater<long>());
+        for (int l : lens) {  // the next block goes to the SM that frees up first
+            std::pop_heap(load.begin(), load.end(), std::greater<long>());
+            load.back() += l + FIXED;
+            std::push_heap(load.begin(), load.end(), std::greater<long>());
+        }
+        const long cost = *std::max_element(load.begin(), load.end());
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = cap;
+        }
+    }
+    return best;
 }
 
 // Host-side plan of one structure: element-sorted, per-element padded atom
@@ -331,7 +377,12 @@ static int build_layout(int64_t n, const int32_t *type_index, int64_t n_types, i
         return (int)s;
     };
     build_items(run_begin, run_end, (int)np, pick(ntile * np), false, L.sq);
-    build_items(run_begin, run_end, (int)np, pick(ntile * np / 2), true, L.tri);
+    if (ntile <= 64 && slab_override <= 0) {
+        const int cap = pick_small_slab(run_begin, run_end, (int)np, std::max(1, sm_count));
+        build_items(run_begin, run_end, (int)np, cap, true, L.tri, 8);
+    } else {
+        build_items(run_begin, run_end, (int)np, pick(ntile * np / 2), true, L.tri);
+    }
     // the item info field stores the run's ELEMENT type
     for (auto *v : {&L.tri, &L.sq})
         for (auto &w : *v) {
@@ -549,8 +600,10 @@ static int launch_debye2_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
     } else {
         // F(Q) / force: few accumulators, short dependent chains -> two blocks
         // per SM (8-j tiles keep two blocks' pair tables in shared memory)
+        // (F(Q) also with 12 warps: 80 registers, 2 x 111 KB of pair tables)
+        constexpr int MINB12 = MODE == MODE_FQ ? 2 : 1;
         rc = nw <= 8 ? launch_debye2_v<C, MODE, 256, 2, 8, CHEB>(h, p, grid, block, nw, st)
-                     : launch_debye2_v<C, MODE, 384, 1, 8, CHEB>(h, p, grid, block, nw, st);
+                     : launch_debye2_v<C, MODE, 384, MINB12, 8, CHEB>(h, p, grid, block, nw, st);
     }
     if (rc) return rc;
     ++h->launches;

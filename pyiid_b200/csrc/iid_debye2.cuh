@@ -334,25 +334,45 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
     } else {
         const double fweight = (MODE == MODE_GRAD || diag) ? 0.5 : 1.0;
         float *G = reinterpret_cast<float *>(p.G);
+        if constexpr (MODE == MODE_GRAD) {
 #pragma unroll
-        for (int m = 0; m < C; ++m) {
-            const int bin = m0 + m;
-            if (bin < p.nq) {  // warp-uniform
-                const int k = m % H;
-                const bool hi = m >= H;
-                const float ff = fa[bin] * fb[bin];
-                if constexpr (MODE == MODE_GRAD) if (oi >= 0) {
-                    const float sc = ff * inv_na[bin];
+            for (int m = 0; m < C; ++m) {
+                const int bin = m0 + m;
+                if (bin < p.nq && oi >= 0) {  // bin < nq is warp-uniform
+                    const int k = m % H;
+                    const bool hi = m >= H;
+                    const float sc = fa[bin] * fb[bin] * inv_na[bin];
                     float *row = G + (size_t)oi * 3 * p.nq + bin;
                     atomicAdd(row, (hi ? accX[k].y : accX[k].x) * sc);
                     atomicAdd(row + p.nq, (hi ? accY[k].y : accY[k].x) * sc);
                     atomicAdd(row + 2 * (size_t)p.nq, (hi ? accZ[k].y : accZ[k].x) * sc);
                 }
-                if (p.S != nullptr) {
-                    const float fv = hi ? accF[k].y : accF[k].x;
-                    const double v = warp_sum((double)fv * (double)ff);
-                    if (lane == 0) atomicAdd(&p.S[bin], fweight * v);
+            }
+        }
+        if (p.S != nullptr) {
+            // S[bin] += sum over the 32 atoms i of this warp.  Transpose the
+            // warp's (bin x atom) accumulators through its own slice of the
+            // (now idle) pair-record buffers, so that lane L sums bin m0 + L
+            // in float64 and the warp issues ONE 32-wide atomic instead of 32
+            // butterfly reductions (the flush was 1/3 of the instructions of a
+            // 32 x 32-atom item).
+            static_assert(C <= 32, "one lane per bin of the chunk");
+            float *tr = reinterpret_cast<float *>(smem_raw) + warp * (C * 33);
+#pragma unroll
+            for (int m = 0; m < C; ++m) {
+                const int k = m % H;
+                tr[m * 33 + lane] = m >= H ? accF[k].y : accF[k].x;
+            }
+            __syncwarp();
+            const int bin = m0 + lane;
+            if (lane < C && bin < p.nq) {
+                double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                for (int a = 0; a < 32; a += 2) {
+                    v0 += (double)tr[lane * 33 + a];
+                    v1 += (double)tr[lane * 33 + a + 1];
                 }
+                atomicAdd(&p.S[bin], fweight * (v0 + v1) * (double)(fa[bin] * fb[bin]));
             }
         }
     }

@@ -232,22 +232,36 @@ __global__ void __launch_bounds__(MAXT, 1) debye64_kernel(const DebyeParams p)
     } else {
         const double fweight = (MODE == MODE_GRAD || diag) ? 0.5 : 1.0;
         double *G = reinterpret_cast<double *>(p.G);
+        if constexpr (MODE == MODE_GRAD) {
 #pragma unroll
-        for (int k = 0; k < C; ++k) {
-            const int bin = m0 + k;
-            if (bin < p.nq) {  // warp-uniform
-                const double ff = fa[bin] * fb[bin];
-                if constexpr (MODE == MODE_GRAD) if (oi >= 0) {
-                    const double sc = ff * inv_na[bin];
+            for (int k = 0; k < C; ++k) {
+                const int bin = m0 + k;
+                if (bin < p.nq && oi >= 0) {  // bin < nq is warp-uniform
+                    const double sc = fa[bin] * fb[bin] * inv_na[bin];
                     double *row = G + (size_t)oi * 3 * p.nq + bin;
                     atomicAdd(row, accX[k] * sc);
                     atomicAdd(row + p.nq, accY[k] * sc);
                     atomicAdd(row + 2 * (size_t)p.nq, accZ[k] * sc);
                 }
-                if (p.S != nullptr) {
-                    const double v = warp_sum(accF[k] * ff);
-                    if (lane == 0) atomicAdd(&p.S[bin], fweight * v);
+            }
+        }
+        if (p.S != nullptr) {
+            // transpose the warp's (bin x atom) accumulators through its slice of
+            // the idle record buffers: lane L sums bin m0 + L, one atomic per bin
+            static_assert(C <= 32, "one lane per bin of the chunk");
+            double *tr = reinterpret_cast<double *>(smem_raw64) + warp * (C * 33);
+#pragma unroll
+            for (int k = 0; k < C; ++k) tr[k * 33 + lane] = accF[k];
+            __syncwarp();
+            const int bin = m0 + lane;
+            if (lane < C && bin < p.nq) {
+                double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                for (int a = 0; a < 32; a += 2) {
+                    v0 += tr[lane * 33 + a];
+                    v1 += tr[lane * 33 + a + 1];
                 }
+                atomicAdd(&p.S[bin], fweight * (v0 + v1) * (fa[bin] * fb[bin]));
             }
         }
     }
