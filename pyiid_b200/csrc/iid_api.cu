@@ -95,7 +95,7 @@ struct iid_handle {
     double *sp_buf = nullptr;
     size_t sp_count = 0;
     bool use_force_table = true;
-    int64_t force_table_min_n = 1500;  // below this the direct kernel is faster
+    int64_t force_table_min_n = 600;  // below this the direct kernel is faster
     // pinned staging for the gradient's way back to pageable host memory
     unsigned char *pinG = nullptr;
     size_t pinG_bytes = 0;
@@ -701,7 +701,7 @@ static int launch_force(iid_handle *h, const double *wq, double *force, cudaStre
     h->last_pairq = 0.5 * (double)h->n * (double)(h->n - 1) * (double)h->nq / h->world;
     if (h->timing) CU(cudaEventRecord(h->ev0, st));
     phi_grid_kernel<<<1, 1024, 0, st>>>(h->x, h->y, h->z, h->valid, np, h_target, h->phi_info);
-    phi_table_kernel<<<dim3((unsigned)((tstride + 127) / 128), (unsigned)(E * E)), 128,
+    phi_table_kernel<<<dim3((unsigned)(4 * h->sm_count), (unsigned)(E * E)), 128,
                        h->nq * sizeof(double), st>>>(wq, (const float *)h->ftab,
                                                      (const float *)h->inv_na, (int)h->nq,
                                                      (int)h->qp, E, h->qbin, h->phi_info,
@@ -709,7 +709,8 @@ static int launch_force(iid_handle *h, const double *wq, double *force, cudaStre
     const int rows = (np + FT_BLOCK - 1) / FT_BLOCK;
     const int mine = rows > h->rank ? (rows - h->rank + h->world - 1) / h->world : 0;
     if (mine > 0) {
-        const int jsplit = std::max(1, std::min(rows, (4 * h->sm_count + mine - 1) / mine));
+        const int jsplit =
+            std::max(1, std::min(np / TILE_I, (4 * h->sm_count + mine - 1) / mine));
         force_table_kernel<<<dim3((unsigned)mine, (unsigned)jsplit), FT_BLOCK, 0, st>>>(
             h->x, h->y, h->z, h->valid, h->orig, h->tile_type, np, E, h->phi_info, h->phi_tab,
             jsplit, h->rank, h->world, force);

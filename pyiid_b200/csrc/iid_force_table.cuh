@@ -66,7 +66,12 @@ __global__ void phi_grid_kernel(const double *__restrict__ x, const double *__re
     }
 }
 
-// One thread per table entry and element pair (blockIdx.y = a * ntypes + b).
+// PT_G lanes per table entry, each summing a contiguous share of the Q bins
+// from its own phase seed (a 330-step sequential float64 recurrence per thread
+// left small structures latency bound); blockIdx.y = a * ntypes + b, the blocks
+// of a row stride over the groups of PT_EPB entries in use.
+constexpr int PT_G = 8;
+constexpr int PT_EPB = 128 / PT_G;  // entries per block and pass
 __global__ void __launch_bounds__(128) phi_table_kernel(const double *__restrict__ wq,
                                                         const float *__restrict__ ftab,
                                                         const float *__restrict__ inv_na,
@@ -76,40 +81,51 @@ __global__ void __launch_bounds__(128) phi_table_kernel(const double *__restrict
 {
     extern __shared__ double wab[];  // [nq] weights of this element pair
     const int a = blockIdx.y / ntypes, b = blockIdx.y % ntypes;
-    const int kused = (int)info[2];
-    if ((int)(blockIdx.x * blockDim.x) > kused + PHI_PAD) return;  // block-uniform
+    const int last = (int)info[2] + 2 * PHI_PAD;  // last entry in use
+    if ((int)blockIdx.x * PT_EPB > last) return;  // block-uniform
     for (int m = threadIdx.x; m < nq; m += blockDim.x)
         wab[m] = wq[m] * (double)ftab[(size_t)a * qp + m] * (double)ftab[(size_t)b * qp + m] *
                  (double)inv_na[m];
     __syncthreads();
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;  // entry, r = (e - PHI_PAD) h
-    if (e > kused + 2 * PHI_PAD) return;
-    const double r = fabs((double)(e - PHI_PAD)) * info[0];  // Phi is even in r
-    double phi = 0.0;
-    const double qmax_r = qbin * (double)nq * r;
-    if (qmax_r < 0.05) {
-        // (x cos x - sin x)/r^3 = Q^3 (-1/3 + x^2/30 - x^4/840), x = Q r
-        for (int m = 0; m < nq; ++m) {
-            const double q = qbin * (double)m, xx = q * r * q * r;
-            phi += wab[m] * q * q * q * (-1.0 / 3.0 + xx * (1.0 / 30.0 - xx / 840.0));
+    const int g = threadIdx.x & (PT_G - 1);
+    const int per = (nq + PT_G - 1) / PT_G;
+    const int mb = min(nq, g * per), me = min(nq, mb + per);
+    const double h = info[0];
+    for (int e0 = blockIdx.x * PT_EPB; e0 <= last; e0 += gridDim.x * PT_EPB) {
+        const int e = e0 + (threadIdx.x / PT_G);               // entry, r = (e - PHI_PAD) h
+        const double r = fabs((double)(e - PHI_PAD)) * h;      // Phi is even in r
+        const bool series = qbin * (double)nq * r < 0.05;      // uniform over the PT_G lanes
+        double phi = 0.0;
+        if (series) {
+            // (x cos x - sin x)/r^3 = Q^3 (-1/3 + x^2/30 - x^4/840), x = Q r
+            for (int m = mb; m < me; ++m) {
+                const double q = qbin * (double)m, xx = q * r * q * r;
+                phi += wab[m] * q * q * q *
+                       (-1.0 / 3.0 + xx * (1.0 / 30.0 - xx * (1.0 / 840.0)));
+            }
+        } else {
+            const double turns = qbin * r * 0.15915494309189533577;  // theta / 2 pi
+            double sth, cth, s, c;
+            sincospi(2.0 * (turns - rint(turns)), &sth, &cth);
+            const double ph = turns * (double)mb;
+            sincospi(2.0 * (ph - rint(ph)), &s, &c);
+            const double kap = qbin * r;
+            double mk = kap * (double)mb;
+            for (int m = mb; m < me; ++m) {
+                phi = fma(wab[m], fma(mk, c, -s), phi);
+                const double sn = fma(s, cth, c * sth);
+                const double cn = fma(c, cth, -(s * sth));
+                s = sn;
+                c = cn;
+                mk += kap;
+            }
         }
-    } else {
-        double sth, cth;
-        const double turns = qbin * r * 0.15915494309189533577;  // theta / 2 pi
-        sincospi(2.0 * (turns - rint(turns)), &sth, &cth);
-        const double kap = qbin * r;
-        double s = 0.0, c = 1.0, mk = 0.0;
-        for (int m = 0; m < nq; ++m) {
-            phi = fma(wab[m], fma(mk, c, -s), phi);
-            const double sn = fma(s, cth, c * sth);
-            const double cn = fma(c, cth, -(s * sth));
-            s = sn;
-            c = cn;
-            mk += kap;
-        }
-        phi /= r * r * r;
+#pragma unroll
+        for (int o = PT_G / 2; o > 0; o >>= 1) phi += __shfl_xor_sync(0xffffffffu, phi, o);
+        if (!series) phi /= r * r * r;
+        if (g == 0 && e <= last)
+            tab[(size_t)blockIdx.y * (PHI_KMAX + 2 * PHI_PAD) + e] = (float)phi;
     }
-    tab[(size_t)blockIdx.y * (PHI_KMAX + 2 * PHI_PAD) + e] = (float)phi;
 }
 
 // force[i] = sum_j Phi_{ab}(r_ij) (q_j - q_i): thread = atom i (sorted/padded
@@ -133,23 +149,24 @@ __global__ void __launch_bounds__(FT_BLOCK) force_table_kernel(
     const double inv_h = info[1];
     const size_t tstride = PHI_KMAX + 2 * PHI_PAD;
     const float *taba = tab + (size_t)ta * ntypes * tstride + PHI_PAD;
-    // this block's share of the j atoms, in whole staging tiles
-    const int ntiles = (np + FT_BLOCK - 1) / FT_BLOCK;
-    const int per = (ntiles + jsplit - 1) / jsplit;
-    const int t0 = blockIdx.y * per, t1 = min(ntiles, t0 + per);
+    // this block's share of the j atoms, in units of one 32-atom tile
+    const int nunits = np / TILE_I;
+    const int per = (nunits + jsplit - 1) / jsplit;
+    const int jb = blockIdx.y * per * TILE_I, je = min(np, jb + per * TILE_I);
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    for (int t = t0; t < t1; ++t) {
-        const int gj = t * FT_BLOCK + threadIdx.x;
+    for (int j0 = jb; j0 < je; j0 += FT_BLOCK) {
+        const int gj = j0 + threadIdx.x;
         __syncthreads();
-        const bool vj = gj < np && valid[gj] != 0.f;
+        const bool vj = gj < je && valid[gj] != 0.f;
         sx[threadIdx.x] = vj ? x[gj] : 0.0;
         sy[threadIdx.x] = vj ? y[gj] : 0.0;
         sz[threadIdx.x] = vj ? z[gj] : 0.0;
         st[threadIdx.x] = vj ? tile_type[gj / TILE_I] : -1;
         __syncthreads();
         if (!vi) continue;
+        const int cnt = min(FT_BLOCK, je - j0);
 #pragma unroll 4
-        for (int jj = 0; jj < FT_BLOCK; ++jj) {
+        for (int jj = 0; jj < cnt; ++jj) {
             const int tb = st[jj];
             const double dx = sx[jj] - xi, dy = sy[jj] - yi, dz = sz[jj] - zi;
             const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));

@@ -573,7 +573,7 @@ def test_tabulated_force_pass_equals_direct_force_pass():
         be.set_option('force_table_min_n', 2)
         res[table] = be.energy_forces(pos, target, 'rw', 100.)
     be.set_option('force_table', 1)
-    be.set_option('force_table_min_n', 1500)
+    be.set_option('force_table_min_n', 600)
     (e1, s1, f1, _), (e0, s0, f0, _) = res[1], res[0]
     # the F(Q) pass is the same kernel both times (atomic order: last bits only)
     assert abs(e1 - e0) < 1e-12 * abs(e0) and abs(s1 - s0) < 1e-12 * abs(s0)
@@ -594,7 +594,7 @@ def test_tabulated_force_pass_equals_direct_force_pass():
     bp.set_transform(sc.exp['rstep'], sc.pdf_qbin, sc.get_r(), 0.0)
     bp.set_option('force_table_min_n', 2)
     e, scale, f, _ = bp.energy_forces(g['positions'], g['target_pdf_f32'], 'rw', 1.0)
-    bp.set_option('force_table_min_n', 1500)
+    bp.set_option('force_table_min_n', 600)
     assert nerr(f, g['rw_forces_f32']) < TOL32
 
 
