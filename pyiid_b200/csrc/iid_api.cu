@@ -116,6 +116,7 @@ struct iid_handle {
     int64_t ef_launches = 0;  // kernels per replay of the graph
     bool use_graph = true;
     bool cheb = true;
+    bool grad_split = true;  // full gradient: F(Q) from the lower-triangle items only
     // instrumentation
     int64_t launches = 0;
     bool timing = false;
@@ -180,6 +181,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_FORCE_TABLE")) h->use_force_table = atoi(s) != 0;
     if (const char *s = getenv("IID_FORCE_TABLE_MIN_N")) h->force_table_min_n = atoll(s);
     if (const char *s = getenv("IID_CHEB")) h->cheb = atoi(s) != 0;
+    if (const char *s = getenv("IID_GRAD_SPLIT")) h->grad_split = atoi(s) != 0;
     if (const char *s = getenv("IID_QSPACE_WQ")) h->qspace_wq = atoi(s) != 0;
     if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
     *out = h;
@@ -243,33 +245,39 @@ extern "C" int iid_set_shard(iid_handle *h, int rank, int world)
 
 // Work items: (i-tile, j-slab) with one element type per slab.  Triangle
 // lists (F(Q), force) take the j tiles strictly below the i-tile plus one
-// diagonal item; square lists (full gradient) take every j.
+// diagonal item; square lists (full gradient) add the j tiles above it as
+// gradient-only items (ITEM_NOF): F(Q) is summed once per pair, below the
+// diagonal, and the kernels run a shorter bin loop above it.
 static void build_items(const std::vector<int> &run_begin,
                         const std::vector<int> &run_end, int np, int slab,
                         bool triangle, std::vector<WorkItem> &out, int gran = TILE_I)
 {
     const int ntile = np / TILE_I;
     out.clear();
+    // equal slabs of at most `slab` atoms, multiples of `gran` (32, or the
+    // 8-atom j tile of the F(Q) / force kernels for small structures)
+    auto slabs = [&](int it, int rb, int re, int info) {
+        if (re <= rb) return;
+        const int len = re - rb;
+        const int nsl = (len + slab - 1) / slab;
+        const int per = ((len + nsl - 1) / nsl + gran - 1) / gran * gran;
+        for (int j0 = rb; j0 < re; j0 += per)
+            out.push_back({it, j0, std::min(re, j0 + per), info});
+    };
     for (int it = 0; it < ntile; ++it) {
-        const int jlimit = triangle ? it * TILE_I : np;
+        const int lo = it * TILE_I, hi = lo + TILE_I;
         for (size_t b = 0; b < run_begin.size(); ++b) {
-            const int rb = run_begin[b], re = std::min(run_end[b], jlimit);
-            if (re <= rb) continue;
-            // equal slabs of at most `slab` atoms, multiples of `gran` (32, or
-            // the 8-atom j tile of the F(Q) / force kernels for small structures)
-            const int len = re - rb;
-            const int nsl = (len + slab - 1) / slab;
-            const int per = ((len + nsl - 1) / nsl + gran - 1) / gran * gran;
-            for (int j0 = rb; j0 < re; j0 += per)
-                out.push_back({it, j0, std::min(re, j0 + per), (int)b});
+            // below the i-tile: every pair once, F counts 1
+            slabs(it, run_begin[b], std::min(run_end[b], lo), (int)b);
+            // above it (square lists): the same pairs again from the other
+            // side; they only add to the gradient rows of this i-tile
+            if (!triangle) slabs(it, std::max(run_begin[b], hi), run_end[b], (int)b | ITEM_NOF);
         }
-        if (triangle) {
-            // the i-tile against itself: both orders present, F counts 1/2
-            int b = 0;
-            for (size_t k = 0; k < run_begin.size(); ++k)
-                if (it * TILE_I >= run_begin[k] && it * TILE_I < run_end[k]) b = (int)k;
-            out.push_back({it, it * TILE_I, (it + 1) * TILE_I, b | ITEM_DIAG});
-        }
+        // the i-tile against itself: both orders present, F counts 1/2
+        int b = 0;
+        for (size_t k = 0; k < run_begin.size(); ++k)
+            if (lo >= run_begin[k] && lo < run_end[k]) b = (int)k;
+        out.push_back({it, lo, hi, b | ITEM_DIAG});
     }
     // longest first: the hardware block scheduler then fills the tail with
     // short items
@@ -387,7 +395,7 @@ static int build_layout(int64_t n, const int32_t *type_index, int64_t n_types, i
     for (auto *v : {&L.tri, &L.sq})
         for (auto &w : *v) {
             const int b = w.info & 0xffff;
-            w.info = (w.info & ITEM_DIAG) | L.run_type[b];
+            w.info = (w.info & (ITEM_DIAG | ITEM_NOF)) | L.run_type[b];
         }
     return 0;
 }
@@ -664,6 +672,7 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     p.qbin = h->qbin;
     p.qbin_turns = h->qbin / 6.283185307179586476925286766559;
     p.G = G; p.S = S; p.force = force;
+    p.grad_split = h->grad_split ? 1 : 0;
     const int64_t mine = nitems > h->rank ? (nitems - h->rank + h->world - 1) / h->world : 0;
     h->last_pairq = 0.5 * (double)h->n * (double)(h->n - 1) * (double)h->nq / h->world;
     if (mine == 0) return 0;
@@ -1397,6 +1406,7 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "force_table_min_n") h->force_table_min_n = value;
     else if (k == "graph") h->use_graph = value != 0;
     else if (k == "cheb") h->cheb = value != 0;
+    else if (k == "grad_split") h->grad_split = value != 0;
     else if (k == "qspace_wq") h->qspace_wq = value != 0;
     else if (k == "nw_max") h->nw_max = (int)std::max<int64_t>(1, std::min<int64_t>(12, value));
     else return fail(IID_E_BADARG, "unknown option: " + k);

@@ -41,6 +41,7 @@ struct WorkItem {
     int info;    // bits 0..15 element type of the j-slab, bit 16 diagonal item
 };
 constexpr int ITEM_DIAG = 1 << 16;
+constexpr int ITEM_NOF = 1 << 17;  // square list: item above the diagonal, gradient only
 
 enum Mode { MODE_FQ = 0, MODE_GRAD = 1, MODE_FORCE = 2 };
 
@@ -59,6 +60,7 @@ struct DebyeParams {
     void *G;        // [n][3][nq] kernel precision (MODE_GRAD)
     double *S;      // [qp] (MODE_FQ, MODE_GRAD; may be null in MODE_GRAD)
     double *force;  // [n][3] (MODE_FORCE)
+    int grad_split;  // MODE_GRAD: 1 = F(Q) from the lower triangle only (ITEM_NOF items skip it)
 };
 
 // sin(2 pi f), cos(2 pi f) for |f| <= 1/8 turn: float32 minimax polynomials on

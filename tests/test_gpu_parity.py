@@ -598,6 +598,35 @@ def test_tabulated_force_pass_equals_direct_force_pass():
     assert nerr(f, g['rw_forces_f32']) < TOL32
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'fp64'])
+def test_gradient_only_items_equal_full_items(precision):
+    """The full-gradient pass sums F(Q) over the items below the diagonal only
+    and runs the items above it with a shorter bin loop (coefficient
+    a_k = k C_k + t_k in a basis without the running m*kappa).  It must
+    reproduce the pass that treats every item alike (grad_split = 0), F(Q) of
+    the triangle pass, and the float64 mode."""
+    atoms = structures.alloy_sphere(700, seed=5)
+    scat = ElasticScatter(precision=precision)
+    scat._ensure_wrapped(atoms)
+    be = scat._load(atoms, scat.exp['qbin'], 'fq')
+    pos = atoms.get_positions()
+    res = {}
+    for split in (1, 0):
+        be.set_option('grad_split', split)
+        res[split] = be.grad_fq(pos, with_fq=True)
+    be.set_option('grad_split', 1)
+    (g1, f1), (g0, f0) = res[1], res[0]
+    tol = 1e-10 if precision == 'fp64' else 2e-6
+    assert nerr(f1, f0) < tol and nerr(g1, g0) < tol
+    assert nerr(f1, be.fq(pos)) < tol
+    if precision == 'fp32':
+        s64 = ElasticScatter(precision='fp64')
+        s64._ensure_wrapped(atoms)
+        b64 = s64._load(atoms, s64.exp['qbin'], 'fq')
+        g64, f64 = b64.grad_fq(pos.astype(np.float32).astype(np.float64), with_fq=True)
+        assert nerr(f1, f64) < TOL32 and nerr(g1, g64) < TOL32
+
+
 @pytest.mark.parametrize('potential', ['rw', 'chi_sq'])
 @pytest.mark.parametrize('precision', ['fp32', 'fp64'])
 def test_qspace_chain_rule_weights_equal_rspace(potential, precision):
