@@ -55,6 +55,23 @@ static int dev_alloc(X **p, size_t count)
     return 0;
 }
 
+// A CUDA graph of one fixed launch sequence, instantiated once the sequence
+// has run twice with the same key.
+struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    int key_pot = -1;
+    double key_conv = 0.0;
+    bool key_flag = false;
+    int warm = 0;
+    int64_t launches = 0;  // kernels per replay
+    void drop()
+    {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr;
+        warm = 0;
+    }
+};
+
 struct iid_handle {
     int device = 0;
     int precision = IID_FP32;
@@ -108,13 +125,19 @@ struct iid_handle {
     bool qspace_wq = true;  // fused host path: chain-rule weights from T^T T (no R x Q pass)
     int slab_override = 0;
     // CUDA graph of the fused energy+forces sequence (small-N latency)
-    cudaGraphExec_t ef_graph = nullptr;
-    int ef_key_pot = -1;
-    double ef_key_conv = 0.0;
-    bool ef_key_pdf = false;
-    int ef_warm = 0;
-    int64_t ef_launches = 0;  // kernels per replay of the graph
+    GraphSlot ef;  // iid_energy_forces_host
+    GraphSlot lf;  // iid_leapfrog_host
     bool use_graph = true;
+    // device-resident sampler states (iid_leapfrog_host): slot = (q, p, f)
+    double *lf_slab = nullptr;   // [lf_slots][3][3n]
+    int64_t lf_slots = 0;
+    double *lf_mass = nullptr;   // [n]
+    double *lf_ctl = nullptr;    // step, src, dst, centre flag, cell centre xyz
+    double *lf_out = nullptr;    // kinetic energy, shift xyz
+    double *lf_mirror = nullptr; // [2][3n] q and p of the new state, contiguous for one D2H
+    double *lf_pin = nullptr;    // pinned: ctl [8] | mirror [6n] | out [16]
+    size_t lf_pin_count = 0;
+    bool lf_system = false;
     bool cheb = true;
     bool grad_split = true;  // full gradient: F(Q) from the lower-triangle items only
     // instrumentation
@@ -196,14 +219,17 @@ extern "C" int iid_destroy(iid_handle *h)
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
                     h->inv_na, h->inv_na_d, h->items_tri, h->items_sq, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
-                    h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf};
+                    h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf,
+                    h->lf_slab, h->lf_mass, h->lf_ctl, h->lf_out, h->lf_mirror};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pinG) cudaFreeHost(h->pinG);
     for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->ef_graph) cudaGraphExecDestroy(h->ef_graph);
+    h->ef.drop();
+    h->lf.drop();
+    if (h->lf_pin) cudaFreeHost(h->lf_pin);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -225,11 +251,8 @@ extern "C" int iid_synchronize(iid_handle *h)
 
 static void drop_graph(iid_handle *h)
 {
-    if (h->ef_graph) {
-        cudaGraphExecDestroy(h->ef_graph);
-        h->ef_graph = nullptr;
-    }
-    h->ef_warm = 0;
+    h->ef.drop();
+    h->lf.drop();
 }
 
 extern "C" int iid_set_shard(iid_handle *h, int rank, int world)
@@ -1163,6 +1186,124 @@ extern "C" int iid_get_restraint_energy(iid_handle *h, double *energy)
     return 0;
 }
 
+// The device part of one Calc1D evaluation, positions already in h->pos:
+// F(Q) pass -> F -> G(r) -> Rw / chi^2 (h->out4) -> chain-rule weights -> force
+// pass (h->force) -> fused restraints.  Enqueued on the handle's stream; shared
+// by iid_energy_forces_host and iid_leapfrog_host (both replay it from a graph).
+static int enqueue_eval_device(iid_handle *h, int potential, double conv, bool want_forces)
+{
+    int rc2;
+    if ((rc2 = iid_fq_partial(h, h->pos, h->S, nullptr))) return rc2;
+    if ((rc2 = iid_fq_finish(h, h->S, h->F, nullptr))) return rc2;
+    if ((rc2 = iid_fq_to_gr(h, h->F, h->Gr, nullptr))) return rc2;
+    // Rw / chi^2 in r space; the chain-rule weights in Q space:
+    // wq = conv T^T c = conv (coef0 T^T go - coef1 (T^T T) F)
+    if (!h->qspace_wq) {
+        if (h->n_restraints)
+            CU(cudaMemsetAsync(h->out4 + 4, 0, sizeof(double), h->stream));
+        if ((rc2 = iid_potential(h, h->Gr, h->target, potential, conv, h->out4,
+                                 want_forces ? h->wq : nullptr, nullptr)))
+            return rc2;
+    } else {
+        potential_kernel<<<1, 1024, 0, h->stream>>>(h->Gr, h->target, (int)h->nr, potential,
+                                                    conv, h->out4, h->cr, h->coef);
+        ++h->launches;
+        CU(cudaGetLastError());
+    }
+    if (!want_forces && h->n_restraints) {
+        for (int s = 0; s < h->n_restraints; ++s)
+            if ((rc2 = launch_spring(h, h->pos, h->n, h->rs_type[s], h->rs_k[s], h->rs_rt[s],
+                                     nullptr, h->out4 + 4, nullptr, nullptr, h->stream)))
+                return rc2;
+    }
+    if (want_forces && h->qspace_wq) {
+        wq_from_q_kernel<<<(unsigned)((h->nq + 31) / 32), 1024, 0, h->stream>>>(
+            h->Mq, h->F, h->vgo, h->coef, (int)h->nq, (int)h->qp, conv, h->wq);
+        ++h->launches;
+        CU(cudaGetLastError());
+    }
+    if (want_forces) {
+        // positions are already staged by iid_fq_partial; enqueue the force pass
+        CU(cudaMemsetAsync(h->force, 0, (size_t)h->n * 3 * sizeof(double), h->stream));
+        if ((rc2 = launch_force(h, h->wq, h->force, h->stream))) return rc2;
+        if (h->n_restraints) {
+            // out4[4] was zeroed by potential_kernel (Q-space path) / the memset above
+            for (int s = 0; s < h->n_restraints; ++s)
+                if ((rc2 = launch_spring(h, h->pos, h->n, h->rs_type[s], h->rs_k[s],
+                                         h->rs_rt[s], nullptr, h->out4 + 4, h->force, nullptr,
+                                         h->stream)))
+                    return rc2;
+        }
+    }
+    return 0;
+}
+
+// Upload a new target PDF (nullptr = the resident one) and keep T^T target
+// current (Q-space chain-rule weights, once per target).
+static int refresh_target(iid_handle *h, const double *target_host, double *pinned)
+{
+    if (target_host) {
+        memcpy(pinned, target_host, h->nr * sizeof(double));
+        CU(cudaMemcpyAsync(h->target, pinned, h->nr * sizeof(double), cudaMemcpyHostToDevice,
+                           h->stream));
+        h->vgo_valid = false;
+    }
+    if (!h->vgo_valid) {
+        CU(cudaMemsetAsync(h->vgo, 0, h->qp * sizeof(double), h->stream));
+        wq_kernel<<<(unsigned)((h->nr + WQ_ROWS - 1) / WQ_ROWS), 352, 0, h->stream>>>(
+            h->T, h->target, (int)h->nr, (int)h->nq, (int)h->qp, 1.0, h->vgo);
+        ++h->launches;
+        CU(cudaGetLastError());
+        h->vgo_valid = true;
+    }
+    return 0;
+}
+
+// Run `enqueue` on the handle's stream: eagerly the first two times, then
+// captured into a graph (key: potential, conv, flag) and replayed.  At a few
+// hundred atoms the evaluation is bound by launch latency, not by arithmetic.
+template <class F>
+static int run_graphed(iid_handle *h, GraphSlot &g, bool graphable, int potential, double conv,
+                       bool flag, F &&enqueue)
+{
+    int rc;
+    if (graphable && g.exec &&
+        (g.key_pot != potential || g.key_conv != conv || g.key_flag != flag))
+        g.drop();
+    if (graphable && g.exec) {
+        CU(cudaGraphLaunch(g.exec, h->stream));
+        h->launches += g.launches;
+    } else if (graphable && g.warm >= 2) {
+        cudaGraph_t graph = nullptr;
+        const int64_t launches0 = h->launches;
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue();
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        g.launches = h->launches - launches0;  // counted while capturing, not yet run
+        h->launches = launches0;
+        if (rc == 0 && ce == cudaSuccess && graph &&
+            cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+            g.key_pot = potential;
+            g.key_conv = conv;
+            g.key_flag = flag;
+            cudaGraphDestroy(graph);
+            CU(cudaGraphLaunch(g.exec, h->stream));
+            h->launches += g.launches;
+        } else {
+            // capture refused: fall back to plain launches for good
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            g.exec = nullptr;
+            h->use_graph = false;
+            if ((rc = enqueue())) return rc;
+        }
+    } else {
+        if ((rc = enqueue())) return rc;
+        ++g.warm;
+    }
+    return 0;
+}
+
 extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
                                       const double *target_host, int potential, double conv,
                                       double *out_host, double *forces_host, double *pdf_host)
@@ -1179,74 +1320,18 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
     double *po = pf + h->qp;
     double *pg = po + 8;
     double *pt = pg + h->nr;
-    if (target_host) {
-        memcpy(pt, target_host, h->nr * sizeof(double));
-        CU(cudaMemcpyAsync(h->target, pt, h->nr * sizeof(double), cudaMemcpyHostToDevice,
-                           h->stream));
-        h->vgo_valid = false;
-    }
-    if (!h->vgo_valid) {
-        // vgo = T^T target, once per target
-        CU(cudaMemsetAsync(h->vgo, 0, h->qp * sizeof(double), h->stream));
-        wq_kernel<<<(unsigned)((h->nr + WQ_ROWS - 1) / WQ_ROWS), 352, 0, h->stream>>>(
-            h->T, h->target, (int)h->nr, (int)h->nq, (int)h->qp, 1.0, h->vgo);
-        ++h->launches;
-        CU(cudaGetLastError());
-        h->vgo_valid = true;
-    }
+    if ((rc = refresh_target(h, target_host, pt))) return rc;
     // The whole sequence (H2D, 7 kernels, 3 memsets, D2H) is replayed from a
     // CUDA graph once it has run twice with the same shape: at a few hundred
     // atoms the evaluation is bound by launch latency, not by arithmetic.
     const bool graphable = h->use_graph && !h->timing && forces_host != nullptr;
-    if (graphable && h->ef_graph &&
-        (h->ef_key_pot != potential || h->ef_key_conv != conv || h->ef_key_pdf != (pdf_host != nullptr)))
-        drop_graph(h);
     memcpy(h->pin, pos_host, (size_t)3 * h->n * sizeof(double));
     auto enqueue = [&]() -> int {
         int rc2;
         CU(cudaMemcpyAsync(h->pos, h->pin, (size_t)3 * h->n * sizeof(double),
                            cudaMemcpyHostToDevice, h->stream));
-        if ((rc2 = iid_fq_partial(h, h->pos, h->S, nullptr))) return rc2;
-        if ((rc2 = iid_fq_finish(h, h->S, h->F, nullptr))) return rc2;
-        if ((rc2 = iid_fq_to_gr(h, h->F, h->Gr, nullptr))) return rc2;
-        // Rw / chi^2 in r space; the chain-rule weights in Q space:
-        // wq = conv T^T c = conv (coef0 T^T go - coef1 (T^T T) F)
-        if (!h->qspace_wq) {
-            if (h->n_restraints)
-                CU(cudaMemsetAsync(h->out4 + 4, 0, sizeof(double), h->stream));
-            if ((rc2 = iid_potential(h, h->Gr, h->target, potential, conv, h->out4,
-                                     forces_host ? h->wq : nullptr, nullptr)))
-                return rc2;
-        } else {
-            potential_kernel<<<1, 1024, 0, h->stream>>>(h->Gr, h->target, (int)h->nr, potential,
-                                                        conv, h->out4, h->cr, h->coef);
-            ++h->launches;
-            CU(cudaGetLastError());
-        }
-        if (!forces_host && h->n_restraints) {
-            for (int s = 0; s < h->n_restraints; ++s)
-                if ((rc2 = launch_spring(h, h->pos, h->n, h->rs_type[s], h->rs_k[s], h->rs_rt[s],
-                                         nullptr, h->out4 + 4, nullptr, nullptr, h->stream)))
-                    return rc2;
-        }
-        if (forces_host && h->qspace_wq) {
-            wq_from_q_kernel<<<(unsigned)((h->nq + 31) / 32), 1024, 0, h->stream>>>(
-                h->Mq, h->F, h->vgo, h->coef, (int)h->nq, (int)h->qp, conv, h->wq);
-            ++h->launches;
-            CU(cudaGetLastError());
-        }
+        if ((rc2 = enqueue_eval_device(h, potential, conv, forces_host != nullptr))) return rc2;
         if (forces_host) {
-            // positions are already staged by iid_fq_partial; enqueue the force pass
-            CU(cudaMemsetAsync(h->force, 0, (size_t)h->n * 3 * sizeof(double), h->stream));
-            if ((rc2 = launch_force(h, h->wq, h->force, h->stream))) return rc2;
-            if (h->n_restraints) {
-                // out4[4] was zeroed by potential_kernel (Q-space path) / the memset above
-                for (int s = 0; s < h->n_restraints; ++s)
-                    if ((rc2 = launch_spring(h, h->pos, h->n, h->rs_type[s], h->rs_k[s],
-                                             h->rs_rt[s], nullptr, h->out4 + 4, h->force, nullptr,
-                                             h->stream)))
-                        return rc2;
-            }
             CU(cudaMemcpyAsync(pfor, h->force, (size_t)3 * h->n * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
         }
@@ -1256,37 +1341,8 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
                                h->stream));
         return 0;
     };
-    if (graphable && h->ef_graph) {
-        CU(cudaGraphLaunch(h->ef_graph, h->stream));
-        h->launches += h->ef_launches;
-    } else if (graphable && h->ef_warm >= 2) {
-        cudaGraph_t graph = nullptr;
-        const int64_t launches0 = h->launches;
-        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        rc = enqueue();
-        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-        h->ef_launches = h->launches - launches0;  // counted while capturing, not yet run
-        h->launches = launches0;
-        if (rc == 0 && ce == cudaSuccess && graph &&
-            cudaGraphInstantiate(&h->ef_graph, graph, 0) == cudaSuccess) {
-            h->ef_key_pot = potential;
-            h->ef_key_conv = conv;
-            h->ef_key_pdf = pdf_host != nullptr;
-            cudaGraphDestroy(graph);
-            CU(cudaGraphLaunch(h->ef_graph, h->stream));
-            h->launches += h->ef_launches;
-        } else {
-            // capture refused: fall back to plain launches for good
-            if (graph) cudaGraphDestroy(graph);
-            cudaGetLastError();
-            h->ef_graph = nullptr;
-            h->use_graph = false;
-            if ((rc = enqueue())) return rc;
-        }
-    } else {
-        if ((rc = enqueue())) return rc;
-        ++h->ef_warm;
-    }
+    if ((rc = run_graphed(h, h->ef, graphable, potential, conv, pdf_host != nullptr, enqueue)))
+        return rc;
     CU(cudaStreamSynchronize(h->stream));
     memcpy(out_host, po, 4 * sizeof(double));
     if (forces_host) memcpy(forces_host, pfor, (size_t)3 * h->n * sizeof(double));
