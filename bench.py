@@ -268,11 +268,15 @@ def hmc_extra():
                        'NUTS(T=1000, escape_level=8, seed=0)',
            'energy_force_evals_per_s': evals_per_s,
            'pairq_per_eval': 561 * 560 // 2 * 330}
-    for fast, tag in ((True, ''), (False, '_atoms_level_path')):
+    # default: tree states resident on the device (one native call per leapfrog);
+    # then the array-level host path and the Atoms-level (reference-style) path
+    for fast, dev, tag in ((True, True, ''), (True, False, '_array_level_path'),
+                           (False, False, '_atoms_level_path')):
         np.random.seed(0)
         a = atoms.copy()
         a.set_calculator(calc)
-        ens = sim.NUTSCanonicalEnsemble(a, temperature=1000, escape_level=8, seed=0, fast=fast)
+        ens = sim.NUTSCanonicalEnsemble(a, temperature=1000, escape_level=8, seed=0, fast=fast,
+                                        device_states=dev)
         lf0, t = ens.leapfrogs, time.perf_counter()
         iters = 6 if fast else 3
         ens.run(iters)

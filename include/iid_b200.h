@@ -222,6 +222,28 @@ int iid_set_restraints(iid_handle *h, int count, const int *sp_type,
                        const double *k, const double *rt);
 int iid_get_restraint_energy(iid_handle *h, double *energy);
 
+/* Device-resident sampler states (pyiid/sim/__init__.py:10-38 leapfrog;
+ * nuts_hmc.py:15-88 buildtree keeps one Atoms object per tree node).  A state
+ * is a numbered slot (q[n,3], p[n,3], f[n,3] float64) on the device.
+ * iid_sampler_setup allocates n_slots zeroed slots and stores the masses [n]
+ * and the cell centre [3] that Atoms.center() moves the bounding box to. */
+int iid_sampler_setup(iid_handle *h, int64_t n_slots, const double *masses_host,
+                      const double *cell_centre);
+int iid_state_upload(iid_handle *h, int slot, const double *q_host,
+                     const double *p_host, const double *f_host);
+/* any of the three outputs may be NULL */
+int iid_state_download(iid_handle *h, int slot, double *q_host, double *p_host,
+                       double *f_host);
+/* One leapfrog step src -> dst entirely on the device: p += step/2 f,
+ * q += step p/m, energy + forces at the new q (as iid_energy_forces_host,
+ * fused restraints included), p += step/2 f, optional centring.  Returns
+ * out_host[9] = potential energy, scale, -, -, restraint energy, kinetic
+ * energy, centring shift x y z, and (optionally) the new q and p.
+ * target_host NULL = the target already resident.  world must be 1. */
+int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, int centre,
+                      const double *target_host, int potential, double conv,
+                      double *out_host, double *q_host, double *p_host);
+
 /* Device array -> pageable host memory through pipelined pinned staging,
  * ordered after the work already enqueued on the handle's stream; complete on
  * return.  (The multi-GPU host layer uses it after the NCCL all-reduce.) */

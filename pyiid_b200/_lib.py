@@ -58,6 +58,10 @@ SIGNATURES = {
     'iid_spring_voxel_host': [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _dbl, _i64, _i64, _i64, _vp],
     'iid_set_restraints': [_vp, _int, _vp, _vp, _vp],
     'iid_get_restraint_energy': [_vp, _vp],
+    'iid_sampler_setup': [_vp, _i64, _vp, _vp],
+    'iid_state_upload': [_vp, _int, _vp, _vp, _vp],
+    'iid_state_download': [_vp, _int, _vp, _vp, _vp],
+    'iid_leapfrog_host': [_vp, _int, _int, _dbl, _int, _vp, _int, _dbl, _vp, _vp, _vp],
     'iid_set_option': [_vp, ctypes.c_char_p, _i64],
     'iid_launch_count': [_vp, _pi64],
     'iid_last_kernel_ms': [_vp, ctypes.POINTER(ctypes.c_float),

@@ -187,6 +187,7 @@ class Backend(object):
             self.nr = 0
         self._skey = key
         self._target_key = None
+        self._last_target = None
         self.n, self.nq = n, nq
         self._tensors = {}
 
@@ -200,6 +201,7 @@ class Backend(object):
                                          t.ctypes.data))
         self._tkey = key
         self._target_key = None
+        self._last_target = None
         self.nr = t.shape[0]
         self._tensors = {}
 
@@ -339,14 +341,7 @@ class Backend(object):
         pdf = np.empty(self.nr, np.float64) if want_pdf else None
         pot = POTENTIALS[potential]
         if self.world == 1:
-            tptr = target.ctypes.data
-            if target is self._last_target:
-                tkey = self._target_key  # same (read-only) array object as last time
-            else:
-                tkey = target.tobytes()
-            self._last_target = target
-            if tkey == self._target_key:
-                tptr = None  # already resident on the device
+            tptr, tkey = self._target_ptr(target)
             check(self.lib.iid_energy_forces_host(
                 self.h, pos.ctypes.data, tptr, pot, float(conv), out.ctypes.data,
                 forces.ctypes.data if want_forces else None,
@@ -397,6 +392,60 @@ class Backend(object):
             if want_pdf:
                 pdf = gr.cpu().numpy()
         return out[0], out[1], forces, pdf
+
+    def _target_ptr(self, target):
+        """(pointer or None, key): None when this target is already resident on
+        the device."""
+        if target is self._last_target:
+            tkey = self._target_key  # same (read-only) array object as last time
+        else:
+            tkey = target.tobytes()
+        self._last_target = target
+        return (None if tkey == self._target_key else target.ctypes.data), tkey
+
+    # -- device-resident sampler states (pyiid/sim/__init__.py:10-38) ------------
+    def sampler_setup(self, n_slots, masses, cell_centre):
+        """Allocate ``n_slots`` phase-space slots (q, p, f) on the device."""
+        m = np.ascontiguousarray(masses, dtype=np.float64).reshape(-1)
+        c = np.ascontiguousarray(cell_centre, dtype=np.float64).reshape(3)
+        if m.shape != (self.n,):
+            raise ValueError('masses must have one entry per atom')
+        check(self.lib.iid_sampler_setup(self.h, int(n_slots), m.ctypes.data, c.ctypes.data))
+        self.n_slots = int(n_slots)
+
+    def state_upload(self, slot, q, p, f):
+        q, p, f = (np.ascontiguousarray(a, dtype=np.float64).reshape(self.n, 3)
+                   for a in (q, p, f))
+        check(self.lib.iid_state_upload(self.h, int(slot), q.ctypes.data, p.ctypes.data,
+                                        f.ctypes.data))
+
+    def state_download(self, slot, want=('q', 'p', 'f')):
+        out = {k: np.empty((self.n, 3), np.float64) for k in want}
+        check(self.lib.iid_state_download(
+            self.h, int(slot), *[out[k].ctypes.data if k in out else None for k in 'qpf']))
+        return out
+
+    def leapfrog(self, src, dst, step, center, target, potential='rw', conv=1.):
+        """One kick-drift-kick step from slot ``src`` into slot ``dst`` on the
+        device; returns (energy, scale, restraint energy, kinetic energy, q, p)
+        of the new state (q, p are host mirrors for the U-turn test)."""
+        if potential not in POTENTIALS:
+            raise NotImplementedError('Potential not implemented')
+        if self.world != 1:
+            raise _lib.IIDError('the device-resident leapfrog needs world == 1')
+        target = np.ascontiguousarray(target, dtype=np.float64)
+        if target.shape != (self.nr,):
+            raise ValueError('target must have the r-grid length %d' % self.nr)
+        self.sync_shard()
+        tptr, tkey = self._target_ptr(target)
+        out = np.empty(9, np.float64)
+        q = np.empty((self.n, 3), np.float64)
+        p = np.empty((self.n, 3), np.float64)
+        check(self.lib.iid_leapfrog_host(
+            self.h, int(src), int(dst), float(step), int(bool(center)), tptr,
+            POTENTIALS[potential], float(conv), out.ctypes.data, q.ctypes.data, p.ctypes.data))
+        self._target_key = tkey
+        return out[0], out[1], out[4], out[5], q, p
 
     # -- spring restraints (calc/spring_calc.py) -------------------------------
     def set_restraints(self, springs):

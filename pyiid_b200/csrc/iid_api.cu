@@ -18,6 +18,7 @@
 #include "iid_debye2.cuh"
 #include "iid_debye64.cuh"
 #include "iid_force_table.cuh"
+#include "iid_sampler.cuh"
 #include "iid_small.cuh"
 #include "iid_spring.cuh"
 
@@ -140,6 +141,7 @@ struct iid_handle {
     bool lf_system = false;
     bool cheb = true;
     bool grad_split = true;  // full gradient: F(Q) from the lower-triangle items only
+    bool prod_unroll = true; // gradient kernel: two pair set-ups per producer iteration
     // instrumentation
     int64_t launches = 0;
     bool timing = false;
@@ -205,6 +207,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_FORCE_TABLE_MIN_N")) h->force_table_min_n = atoll(s);
     if (const char *s = getenv("IID_CHEB")) h->cheb = atoi(s) != 0;
     if (const char *s = getenv("IID_GRAD_SPLIT")) h->grad_split = atoi(s) != 0;
+    if (const char *s = getenv("IID_PROD_UNROLL")) h->prod_unroll = atoi(s) != 0;
     if (const char *s = getenv("IID_QSPACE_WQ")) h->qspace_wq = atoi(s) != 0;
     if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
     *out = h;
@@ -456,6 +459,7 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
         return fail(IID_E_BADARG, "bad structure arguments");
     CU(cudaStreamSynchronize(h->stream));
     drop_graph(h);
+    h->lf_system = false;  // state slots are sized for the previous structure
     Layout L;
     {
         int rc0 = build_layout(n, type_index, n_types, h->sm_count, h->slab_override, L);
@@ -592,7 +596,7 @@ static int stage_positions(iid_handle *h, const double *pos_dev, cudaStream_t st
     return 0;
 }
 
-template <int C, int MODE, int MAXT, int MINB, int TJ, bool CHEB>
+template <int C, int MODE, int MAXT, int MINB, int TJ, bool CHEB, int PU = 1>
 static int launch_debye2_v(iid_handle *h, const DebyeParams &p, dim3 grid, dim3 block, int nw,
                            cudaStream_t st)
 {
@@ -601,11 +605,11 @@ static int launch_debye2_v(iid_handle *h, const DebyeParams &p, dim3 grid, dim3 
     // function attributes are per device: remember which devices are done
     static bool attr_done[64] = {false};
     if (!attr_done[h->device & 63]) {
-        CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, MAXT, MINB, TJ, CHEB>,
+        CU(cudaFuncSetAttribute(debye2_kernel<C, MODE, MAXT, MINB, TJ, CHEB, PU>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done[h->device & 63] = true;
     }
-    debye2_kernel<C, MODE, MAXT, MINB, TJ, CHEB><<<grid, block, smem, st>>>(p);
+    debye2_kernel<C, MODE, MAXT, MINB, TJ, CHEB, PU><<<grid, block, smem, st>>>(p);
     return 0;
 }
 
@@ -626,8 +630,11 @@ static int launch_debye2_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
     int rc;
     if constexpr (MODE == MODE_GRAD) {
         // 4C accumulators: one block of <= 8 warps (255 registers) or <= 12 (168)
-        rc = nw <= 8 ? launch_debye2_v<C, MODE, 256, 1, 16, CHEB>(h, p, grid, block, nw, st)
-                     : launch_debye2_v<C, MODE, 384, 1, 8, CHEB>(h, p, grid, block, nw, st);
+        // two pair set-ups side by side in the producer (prod_unroll, default on)
+        rc = nw > 8 ? launch_debye2_v<C, MODE, 384, 1, 8, CHEB>(h, p, grid, block, nw, st)
+             : h->prod_unroll
+                 ? launch_debye2_v<C, MODE, 256, 1, 16, CHEB, 2>(h, p, grid, block, nw, st)
+                 : launch_debye2_v<C, MODE, 256, 1, 16, CHEB, 1>(h, p, grid, block, nw, st);
     } else {
         // F(Q) / force: few accumulators, short dependent chains -> two blocks
         // per SM (8-j tiles keep two blocks' pair tables in shared memory)
@@ -1350,6 +1357,136 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
     return 0;
 }
 
+// --- device-resident sampler states ------------------------------------------
+// pyiid/sim/__init__.py:10-38 (leapfrog) keeps an Atoms object per phase-space
+// point; here a point is a slot (q, p, f) of a device slab and one leapfrog is
+// one graph replay: kick + drift, the fused energy + forces sequence, kick +
+// kinetic energy + centring, one device-to-host copy of (q, p, scalars).
+extern "C" int iid_sampler_setup(iid_handle *h, int64_t n_slots, const double *masses_host,
+                                 const double *cell_centre)
+{
+    NEED(h);
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (n_slots < 2 || n_slots > 4096 || !masses_host || !cell_centre)
+        return fail(IID_E_BADARG, "need 2 <= n_slots <= 4096, masses and the cell centre");
+    for (int64_t i = 0; i < h->n; ++i)
+        if (!(masses_host[i] > 0.0)) return fail(IID_E_BADARG, "masses must be positive");
+    CU(cudaStreamSynchronize(h->stream));
+    h->lf.drop();
+    const size_t n3 = (size_t)3 * h->n;
+    int rc;
+    if (h->lf_slab) { cudaFree(h->lf_slab); h->lf_slab = nullptr; }
+    if ((rc = dev_alloc(&h->lf_slab, (size_t)n_slots * 3 * n3)) ||
+        (rc = dev_alloc(&h->lf_mass, h->n)) || (rc = dev_alloc(&h->lf_ctl, LF_CTL)) ||
+        (rc = dev_alloc(&h->lf_out, 4)) || (rc = dev_alloc(&h->lf_mirror, 2 * n3)))
+        return rc;
+    h->lf_slots = n_slots;
+    const size_t need = LF_CTL + 2 * n3 + 16;
+    if (need > h->lf_pin_count) {
+        if (h->lf_pin) cudaFreeHost(h->lf_pin);
+        h->lf_pin = nullptr;
+        CU(cudaMallocHost((void **)&h->lf_pin, need * sizeof(double)));
+        h->lf_pin_count = need;
+    }
+    CU(cudaMemcpy(h->lf_mass, masses_host, h->n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemset(h->lf_slab, 0, (size_t)n_slots * 3 * n3 * sizeof(double)));
+    for (int w = 0; w < 3; ++w) h->lf_pin[4 + w] = cell_centre[w];
+    h->lf_system = true;
+    return 0;
+}
+
+static int check_slot(iid_handle *h, int slot)
+{
+    if (!h->lf_system) return fail(IID_E_BADARG, "call iid_sampler_setup first");
+    if (slot < 0 || slot >= h->lf_slots) return fail(IID_E_BADARG, "state slot out of range");
+    return 0;
+}
+
+extern "C" int iid_state_upload(iid_handle *h, int slot, const double *q_host,
+                                const double *p_host, const double *f_host)
+{
+    NEED(h);
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (!q_host || !p_host || !f_host) return fail(IID_E_BADARG, "null pointer");
+    const size_t n3 = (size_t)3 * h->n, bytes = n3 * sizeof(double);
+    double *base = h->lf_slab + (size_t)slot * 3 * n3;
+    // ordered after the steps already enqueued; pageable source: synchronous
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(base, q_host, bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(base + n3, p_host, bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(base + 2 * n3, f_host, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int iid_state_download(iid_handle *h, int slot, double *q_host, double *p_host,
+                                  double *f_host)
+{
+    NEED(h);
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    const size_t n3 = (size_t)3 * h->n, bytes = n3 * sizeof(double);
+    const double *base = h->lf_slab + (size_t)slot * 3 * n3;
+    CU(cudaStreamSynchronize(h->stream));
+    if (q_host) CU(cudaMemcpy(q_host, base, bytes, cudaMemcpyDeviceToHost));
+    if (p_host) CU(cudaMemcpy(p_host, base + n3, bytes, cudaMemcpyDeviceToHost));
+    if (f_host) CU(cudaMemcpy(f_host, base + 2 * n3, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, int centre,
+                                 const double *target_host, int potential, double conv,
+                                 double *out_host, double *q_host, double *p_host)
+{
+    NEED(h);
+    if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
+    if (h->world != 1)
+        return fail(IID_E_BADARG, "iid_leapfrog_host needs the whole pair list (world == 1)");
+    int rc;
+    if ((rc = check_slot(h, src)) || (rc = check_slot(h, dst))) return rc;
+    if (src == dst) return fail(IID_E_BADARG, "source and destination slot must differ");
+    if (!out_host) return fail(IID_E_BADARG, "null pointer");
+    const size_t n3 = (size_t)3 * h->n;
+    double *pt = h->pin + 6 * h->n + h->qp + 8 + h->nr;  // target staging of the handle
+    if ((rc = refresh_target(h, target_host, pt))) return rc;
+    double *ctl = h->lf_pin, *mir = ctl + LF_CTL, *po = mir + 2 * n3;
+    ctl[0] = step;
+    ctl[1] = (double)src;
+    ctl[2] = (double)dst;
+    ctl[3] = centre ? 1.0 : 0.0;
+    const int n = (int)h->n;
+    auto enqueue = [&]() -> int {
+        int rc2;
+        CU(cudaMemcpyAsync(h->lf_ctl, ctl, LF_CTL * sizeof(double), cudaMemcpyHostToDevice,
+                           h->stream));
+        lf_kick_drift_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, h->stream>>>(
+            h->lf_ctl, h->lf_slab, h->lf_mass, n, h->pos);
+        ++h->launches;
+        CU(cudaGetLastError());
+        if ((rc2 = enqueue_eval_device(h, potential, conv, true))) return rc2;
+        lf_finish_kernel<<<1, 1024, 0, h->stream>>>(h->lf_ctl, h->lf_slab, h->lf_mass, n, h->pos,
+                                                    h->force, h->lf_mirror, h->lf_out);
+        ++h->launches;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(mir, h->lf_mirror, 2 * n3 * sizeof(double), cudaMemcpyDeviceToHost,
+                           h->stream));
+        CU(cudaMemcpyAsync(po, h->out4, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(po + 8, h->lf_out, 4 * sizeof(double), cudaMemcpyDeviceToHost,
+                           h->stream));
+        return 0;
+    };
+    const bool graphable = h->use_graph && !h->timing;
+    if ((rc = run_graphed(h, h->lf, graphable, potential, conv, false, enqueue))) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    // out: energy, scale, -, -, restraint energy, kinetic energy, shift x y z
+    for (int k = 0; k < 5; ++k) out_host[k] = po[k];
+    if (!h->n_restraints) out_host[4] = 0.0;
+    for (int k = 0; k < 4; ++k) out_host[5 + k] = po[8 + k];
+    if (q_host) memcpy(q_host, mir, n3 * sizeof(double));
+    if (p_host) memcpy(p_host, mir + n3, n3 * sizeof(double));
+    return 0;
+}
+
 // Rw / chi^2 of two host vectors and the chain-rule vector c (calc/__init__.py
 // wrap_rw / wrap_chi_sq :10-54 and the c of wrap_grad_* :56-105).
 extern "C" int iid_rw_host(iid_handle *h, const double *gcalc_host, const double *gobs_host,
@@ -1463,6 +1600,7 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "graph") h->use_graph = value != 0;
     else if (k == "cheb") h->cheb = value != 0;
     else if (k == "grad_split") h->grad_split = value != 0;
+    else if (k == "prod_unroll") h->prod_unroll = value != 0;
     else if (k == "qspace_wq") h->qspace_wq = value != 0;
     else if (k == "nw_max") h->nw_max = (int)std::max<int64_t>(1, std::min<int64_t>(12, value));
     else return fail(IID_E_BADARG, "unknown option: " + k);

@@ -68,7 +68,7 @@ __device__ __forceinline__ void sincos_turns(double u, float &s, float &c)
 // second one is the half-chunk seed rotated by C/4 bins) and takes its first
 // step with the rotation; over 8 bins the error is 1.3-2.5e-7 rms, the same
 // as the rotation ("recurrences").
-template <int C, int MODE, int MAXT, int MINB, int TJ2, bool CHEB>
+template <int C, int MODE, int MAXT, int MINB, int TJ2, bool CHEB, int PU = 1>
 __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -136,43 +136,76 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
     }
 
     // ---- producer: the pair records of one j tile -----------------------------
+    // PU pairs per thread are set up side by side (PU = 2 for the 16-j tiles of
+    // the gradient kernel): the set-up of one pair is a single dependent chain
+    // (global load -> float64 distance -> range reductions -> polynomials ->
+    // the seed rotations), and the ncu source view showed a producing warp at
+    // ~0.16 instructions per cycle; two independent chains halve that time.
+    // The seeds advance by ONE rotation per warp (e^{i C theta} = the square of
+    // the half-chunk rotation) with the half-chunk seed off the critical path.
     auto produce = [&](int jt, int b) {
         float *T = tab(b);
         float *S = T + NREC * NPAIR;
-        for (int pr = threadIdx.x; pr < NPAIR; pr += blockDim.x) {
-            const int jj = pr >> 5;  // (pr & 31) == lane: this thread's own atom i
-            const int gj = jt + jj;
-            const double dxd = p.x[gj] - xi, dyd = p.y[gj] - yi, dzd = p.z[gj] - zi;
-            const bool keep = vi && p.valid[gj] != 0.f;
-            const double r2 = fma(dxd, dxd, fma(dyd, dyd, dzd * dzd));
-            const float r2f = (float)r2;
-            double y = (double)rsqrtf(r2f);
-            y = y * fma(-0.5 * r2, y * y, 1.5);  // one Newton step in float64
-            if (!(keep && r2f > 0.f)) y = 0.0;   // self pair, ghost atom, r == 0
-            const double r = r2 * y;
-            const double u = r * p.qbin_turns;   // turns per Q bin
-            float sth, cth, sC, cC, sQ, cQ, s, c;
-            sincos_turns(u, sth, cth);
-            sincos_turns(u * (double)H, sC, cC);        // rotation by one half-chunk
-            sincos_turns(u * (double)(H / 2), sQ, cQ);  // rotation by one quarter-chunk
-            if (chunk0 == 0) { s = 0.f; c = 1.f; }
-            else sincos_turns(u * (double)(chunk0 * C), s, c);
-            const float invr = (float)y;
-            const float b3 = invr * invr * invr;
-            s *= b3;
-            c *= b3;
-            float4 *RA = reinterpret_cast<float4 *>(T);
-            RA[pr] = make_float4(cth, sth, (float)(p.qbin * r), r2f);
-            RA[NPAIR + pr] = make_float4((float)dxd, (float)dyd, (float)dzd, cQ);
-            T[8 * NPAIR + pr] = sQ;
-            float2 *S2 = reinterpret_cast<float2 *>(S);
+        float4 *RA = reinterpret_cast<float4 *>(T);
+        float2 *S2 = reinterpret_cast<float2 *>(S);
+        for (int pr0 = threadIdx.x; pr0 < NPAIR; pr0 += PU * blockDim.x) {
+            int pr[PU];
+            bool live[PU];
+            float s[PU], c[PU], sC[PU], cC[PU], sW[PU], cW[PU];
+#pragma unroll
+            for (int u = 0; u < PU; ++u) {
+                const int want = pr0 + u * blockDim.x;
+                live[u] = want < NPAIR;
+                pr[u] = live[u] ? want : pr0;  // a dead slot recomputes pair pr0, stores nothing
+                const int jj = pr[u] >> 5;     // (pr & 31) == lane: this thread's own atom i
+                const int gj = jt + jj;
+                const double dxd = p.x[gj] - xi, dyd = p.y[gj] - yi, dzd = p.z[gj] - zi;
+                const bool keep = vi && p.valid[gj] != 0.f;
+                const double r2 = fma(dxd, dxd, fma(dyd, dyd, dzd * dzd));
+                const float r2f = (float)r2;
+                double y = (double)rsqrtf(r2f);
+                y = y * fma(-0.5 * r2, y * y, 1.5);  // one Newton step in float64
+                if (!(keep && r2f > 0.f)) y = 0.0;   // self pair, ghost atom, r == 0
+                const double r = r2 * y;
+                const double ut = r * p.qbin_turns;  // turns per Q bin
+                float sth, cth, sQ, cQ;
+                sincos_turns(ut, sth, cth);
+                sincos_turns(ut * (double)H, sC[u], cC[u]);   // rotation by one half-chunk
+                sincos_turns(ut * (double)(H / 2), sQ, cQ);   // rotation by one quarter-chunk
+                if (chunk0 == 0) { s[u] = 0.f; c[u] = 1.f; }
+                else sincos_turns(ut * (double)(chunk0 * C), s[u], c[u]);
+                const float invr = (float)y;
+                const float b3 = invr * invr * invr;
+                s[u] *= b3;
+                c[u] *= b3;
+                if (live[u]) {
+                    RA[pr[u]] = make_float4(cth, sth, (float)(p.qbin * r), r2f);
+                    RA[NPAIR + pr[u]] = make_float4((float)dxd, (float)dyd, (float)dzd, cQ);
+                    T[8 * NPAIR + pr[u]] = sQ;
+                }
+                if constexpr (PU > 1) {  // rotation by a whole chunk
+                    cW[u] = fmaf(cC[u], cC[u], -(sC[u] * sC[u]));
+                    sW[u] = 2.f * sC[u] * cC[u];
+                }
+            }
             for (int w = 0; w < nwarp; ++w) {
-                const float s1 = fmaf(s, cC, c * sC);
-                const float c1 = fmaf(c, cC, -(s * sC));
-                S2[(2 * w) * NPAIR + pr] = make_float2(s, s1);      // sin at m0, m0+H
-                S2[(2 * w + 1) * NPAIR + pr] = make_float2(c, c1);  // cos at m0, m0+H
-                s = fmaf(s1, cC, c1 * sC);
-                c = fmaf(c1, cC, -(s1 * sC));
+#pragma unroll
+                for (int u = 0; u < PU; ++u) {
+                    const float s1 = fmaf(s[u], cC[u], c[u] * sC[u]);
+                    const float c1 = fmaf(c[u], cC[u], -(s[u] * sC[u]));
+                    if (live[u]) {
+                        S2[(2 * w) * NPAIR + pr[u]] = make_float2(s[u], s1);      // sin at m0, m0+H
+                        S2[(2 * w + 1) * NPAIR + pr[u]] = make_float2(c[u], c1);  // cos at m0, m0+H
+                    }
+                    if constexpr (PU > 1) {
+                        const float sn = fmaf(s[u], cW[u], c[u] * sW[u]);
+                        c[u] = fmaf(c[u], cW[u], -(s[u] * sW[u]));
+                        s[u] = sn;
+                    } else {
+                        s[u] = fmaf(s1, cC[u], c1 * sC[u]);
+                        c[u] = fmaf(c1, cC[u], -(s1 * sC[u]));
+                    }
+                }
             }
         }
     };

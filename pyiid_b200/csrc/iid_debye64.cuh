@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(MAXT, 1) debye64_kernel(const DebyeParams p)
     const int nactive = min(nwarp, (p.nq - chunk0 * C + C - 1) / C);
 
     double accF[MODE != MODE_FORCE ? C : 1];
-    double accX[MODE == MODE_GRAD ? C : 1], accY[MODE == MODE_GRAD ? C : 1],
-        accZ[MODE == MODE_GRAD ? C : 1];
+    double accX[MODE == MODE_GRAD ? C : 1] = {}, accY[MODE == MODE_GRAD ? C : 1] = {},
+           accZ[MODE == MODE_GRAD ? C : 1] = {};
     double w0[MODE == MODE_FORCE ? C : 1], w1[MODE == MODE_FORCE ? C : 1];
     double fix = 0.0, fiy = 0.0, fiz = 0.0;
 #pragma unroll
@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(MAXT, 1) debye64_kernel(const DebyeParams p)
     };
     auto bins = [&](auto nof_tag, const Rec &rec, int jj) {
         constexpr bool NOF = decltype(nof_tag)::value;
-        const double cth = rec.cs.x, sth = rec.cs.y, kap = rec.kr.x, r2 = rec.kr.y;
+        const double cth = rec.cs.x, sth = rec.cs.y, kap = rec.kr.x;
+        [[maybe_unused]] const double r2 = rec.kr.y;
         const double dx = rec.dxy.x, dy = rec.dxy.y, dz = rec.dz.x;
         const double tc = cth + cth;
         double s = rec.seed.x, c = rec.seed.y, sp = s, cp = c;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(MAXT, 1) debye64_kernel(const DebyeParams p)
             }
             return;
         }
-        double p0[2] = {0.0, 0.0}, p1[2] = {0.0, 0.0};
+        [[maybe_unused]] double p0[2] = {0.0, 0.0}, p1[2] = {0.0, 0.0};
 #pragma unroll
         for (int k = 0; k < C; ++k) {
             if constexpr (MODE != MODE_FORCE) accF[k] = fma(s, r2, accF[k]);

@@ -1,0 +1,138 @@
+// iid_sampler.cuh -- device-resident leapfrog step for the HMC / NUTS samplers
+// (sm_100a).  Replaces the host arithmetic of pyiid/sim/__init__.py:10-38
+// (leapfrog: half kick, drift, force evaluation, half kick, centre) around the
+// fused energy + forces sequence, so that a phase-space point (q, p, f) never
+// leaves the GPU between leapfrog steps.
+//
+// States live in numbered slots of one slab: slot s = q [n][3], p [n][3],
+// f [n][3] float64.  The per-step parameters (step size, source and
+// destination slot, centring) are read from a small device buffer that the
+// captured graph refreshes from pinned host memory, so one instantiated graph
+// serves every step of a trajectory.
+//
+// The arithmetic follows numpy's operation order (separate multiply and add,
+// true division by the mass) so that positions and momenta equal the
+// array-level host path bit for bit; only the kinetic-energy sum has a
+// different summation order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace iid {
+
+constexpr int LF_CTL = 8;  // step, src, dst, centre flag, cell centre x y z, -
+
+__device__ __forceinline__ double *lf_slot(double *slab, int n, int slot, int which)
+{
+    return slab + ((size_t)slot * 3 + which) * 3 * (size_t)n;
+}
+
+// p_half = p + (step/2) f;  q' = q + step (p_half / m).  Writes p_half into the
+// destination slot and q' into `pos` (the evaluation's input).
+__global__ void lf_kick_drift_kernel(const double *__restrict__ ctl, double *__restrict__ slab,
+                                     const double *__restrict__ mass, int n,
+                                     double *__restrict__ pos)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 3 * n) return;
+    const double step = ctl[0];
+    const int src = (int)ctl[1], dst = (int)ctl[2];
+    const double *q = lf_slot(slab, n, src, 0), *p = lf_slot(slab, n, src, 1),
+                 *f = lf_slot(slab, n, src, 2);
+    const double half = __dmul_rn(0.5, step);
+    const double ph = __dadd_rn(p[k], __dmul_rn(half, f[k]));
+    lf_slot(slab, n, dst, 1)[k] = ph;
+    pos[k] = __dadd_rn(q[k], __dmul_rn(step, __ddiv_rn(ph, mass[k / 3])));
+}
+
+// p = p_half + (step/2) f_new;  KE = sum p.p/m / 2;  q = q' + (cell centre -
+// (min + max)/2) when centring.  One block: the sampler's structures are small
+// and the three reductions need the whole array.  Mirrors q and p into one
+// contiguous buffer for the single device-to-host copy of the step.
+__global__ void __launch_bounds__(1024) lf_finish_kernel(const double *__restrict__ ctl,
+                                                         double *__restrict__ slab,
+                                                         const double *__restrict__ mass, int n,
+                                                         const double *__restrict__ pos,
+                                                         const double *__restrict__ force,
+                                                         double *__restrict__ mirror,
+                                                         double *__restrict__ out)
+{
+    __shared__ double red[7][32];
+    __shared__ double shift[3];
+    const double step = ctl[0];
+    const int dst = (int)ctl[2];
+    const bool centre = ctl[3] != 0.0;
+    double *q = lf_slot(slab, n, dst, 0), *p = lf_slot(slab, n, dst, 1),
+           *f = lf_slot(slab, n, dst, 2);
+    const double half = __dmul_rn(0.5, step);
+    double ke = 0.0;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+        const double m = mass[a];
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const int k = 3 * a + w;
+            const double fk = force[k];
+            const double pn = __dadd_rn(p[k], __dmul_rn(half, fk));
+            p[k] = pn;
+            f[k] = fk;
+            mirror[3 * (size_t)n + k] = pn;
+            ke = fma(pn, __ddiv_rn(pn, m), ke);
+            const double x = pos[k];
+            lo[w] = fmin(lo[w], x);
+            hi[w] = fmax(hi[w], x);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v[7] = {ke, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            v[1 + w] = fmin(v[1 + w], __shfl_xor_sync(0xffffffffu, v[1 + w], o));
+            v[4 + w] = fmax(v[4 + w], __shfl_xor_sync(0xffffffffu, v[4 + w], o));
+        }
+    }
+    if (lane == 0)
+#pragma unroll
+        for (int c = 0; c < 7; ++c) red[c][warp] = v[c];
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        double r[7];
+        r[0] = lane < nw ? red[0][lane] : 0.0;
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            r[1 + w] = lane < nw ? red[1 + w][lane] : 1e300;
+            r[4 + w] = lane < nw ? red[4 + w][lane] : -1e300;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            r[0] += __shfl_xor_sync(0xffffffffu, r[0], o);
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                r[1 + w] = fmin(r[1 + w], __shfl_xor_sync(0xffffffffu, r[1 + w], o));
+                r[4 + w] = fmax(r[4 + w], __shfl_xor_sync(0xffffffffu, r[4 + w], o));
+            }
+        }
+        if (lane == 0) {
+            out[0] = 0.5 * r[0];
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                // numpy: q + (centre - 0.5 * (min + max))
+                const double s = centre ? __dsub_rn(ctl[4 + w], __dmul_rn(0.5, __dadd_rn(r[1 + w], r[4 + w]))) : 0.0;
+                shift[w] = s;
+                out[1 + w] = s;
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 3 * n; k += blockDim.x) {
+        const double x = centre ? __dadd_rn(pos[k], shift[k % 3]) : pos[k];
+        q[k] = x;
+        mirror[k] = x;
+    }
+}
+
+}  // namespace iid

@@ -227,6 +227,95 @@ class _FastSystem(object):
         return atoms
 
 
+class _SlotPool(object):
+    """Free list of the device slots that hold phase-space points."""
+
+    def __init__(self, n):
+        self.free = list(range(n - 1, -1, -1))
+
+    def take(self):
+        if not self.free:
+            raise RuntimeError('out of device state slots (tree deeper than planned)')
+        return self.free.pop()
+
+    def give(self, slot):
+        self.free.append(slot)
+
+
+class _DevState(_State):
+    """A :class:`_State` whose (q, p, f) also live in a device slot; ``q`` and
+    ``p`` are host mirrors (U-turn test, proposals), ``f`` stays on the device
+    until an accepted sample needs it.  The slot returns to the pool when the
+    last reference to the state goes away."""
+    __slots__ = ('slot', 'pool')
+
+    def __init__(self, q, p, pe, f, ke, slot, pool):
+        _State.__init__(self, q, p, pe, f, ke)
+        self.slot, self.pool = slot, pool
+
+    def __del__(self):
+        if self.slot is not None:
+            self.pool.give(self.slot)
+            self.slot = None
+
+
+class _DeviceSystem(_FastSystem):
+    """:class:`_FastSystem` with the integrator on the device: a leapfrog step
+    is ONE native call (``iid_leapfrog_host``: kick, drift, fused energy +
+    forces, kick, centring, kinetic energy, replayed from a CUDA graph) between
+    device-resident states; only q, p and three scalars come back per step.
+    Same operation order as the host arithmetic (positions and momenta are
+    bit-identical to :meth:`_FastSystem.leapfrog`); the kinetic-energy sum is
+    reduced in a different order (last-bit differences)."""
+    N_SLOTS = 256  # >= 3 live states per tree level; escape_level <= 13 in practice
+
+    def __init__(self, atoms):
+        _FastSystem.__init__(self, atoms)
+        scat = self.scat
+        be = scat._load(self.template, scat.pdf_qbin, 'PDF')
+        be.set_transform(scat.exp['rstep'], scat.pdf_qbin, scat.get_r(), scat.exp['qmin'])
+        be.set_restraints(self.springs)
+        masses = np.ascontiguousarray(self.masses.reshape(-1), dtype=np.float64)
+        key = (be.n, be._skey, masses.tobytes(), self.cell_centre.tobytes())
+        if getattr(be, '_sampler_key', None) != key:
+            be.sampler_setup(self.N_SLOTS, masses, self.cell_centre)
+            be._sampler_key = key
+            be._slot_pool = _SlotPool(self.N_SLOTS)
+        self.be = be
+        self.pool = be._slot_pool
+
+    @staticmethod
+    def usable(atoms):
+        """The fused calculator on a single rank (the sharded evaluation goes
+        through torch.distributed collectives on the host path)."""
+        from .backend import _dist_state
+        return _FastSystem.usable(atoms) and _dist_state()[1] == 1
+
+    def state_of(self, atoms):
+        st = _FastSystem.state_of(self, atoms)
+        slot = self.pool.take()
+        self.be.state_upload(slot, st.q, st.p, st.f)
+        return _DevState(st.q, st.p, st.pe, st.f, st.ke, slot, self.pool)
+
+    def leapfrog(self, st, step, center=True):
+        calc = self.calc
+        dst = self.pool.take()
+        try:
+            e, _, e_spring, ke, q, p = self.be.leapfrog(
+                st.slot, dst, step, center, calc.target_data, calc.potential_name,
+                calc.rw_to_eV)
+        except Exception:
+            self.pool.give(dst)
+            raise
+        self.evals += 1
+        return _DevState(q, p, float(e) + float(e_spring), None, float(ke), dst, self.pool)
+
+    def to_atoms(self, st):
+        if st.f is None:
+            st.f = self.be.state_download(st.slot, want=('f',))['f']
+        return _FastSystem.to_atoms(self, st)
+
+
 def _no_u_turn_states(minus, plus, masses):
     span = (plus.q - minus.q).ravel()
     return (span.dot((minus.p / masses).ravel()) >= 0) and \
@@ -268,16 +357,25 @@ class NUTSCanonicalEnsemble(Ensemble):
     ``fast`` (default: automatic) selects the array-level path
     (:class:`_FastSystem`) when the atoms carry the fused device ``Calc1D``;
     it draws the same random numbers and performs the same arithmetic as the
-    Atoms-level path, so both produce the same trajectory."""
+    Atoms-level path, so both produce the same trajectory.  ``device_states``
+    (default: automatic) additionally keeps every phase-space point of the
+    tree on the device (:class:`_DeviceSystem`)."""
 
     def __init__(self, atoms, restart=None, logfile=None, trajectory=None,
                  temperature=100, escape_level=13, accept_target=.65,
-                 momentum=None, seed=None, verbose=False, fast=None):
+                 momentum=None, seed=None, verbose=False, fast=None,
+                 device_states=None):
         Ensemble.__init__(self, atoms, restart, logfile, trajectory, seed,
                           verbose)
         if fast is None:
             fast = _FastSystem.usable(atoms)
         self.fast = bool(fast) and _FastSystem.usable(atoms)
+        # phase-space points resident on the device (one native call per
+        # leapfrog) whenever the array-level path runs on a single rank
+        if device_states is None:
+            device_states = True
+        self.device_states = self.fast and bool(device_states) and \
+            _DeviceSystem.usable(atoms)
         self.accept_target = accept_target
         self.temp = temperature
         self.thermal_nrg = self.temp * kB
@@ -331,7 +429,7 @@ class NUTSCanonicalEnsemble(Ensemble):
 
     def _step_fast(self):
         current = self.traj[-1]
-        system = _FastSystem(current)
+        system = (_DeviceSystem if self.device_states else _FastSystem)(current)
         accepted = []
         if self.verbose:
             print('\ttime step size', self.step_size / fs, 'fs')

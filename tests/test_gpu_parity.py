@@ -519,6 +519,76 @@ def test_array_level_nuts_equals_atoms_level_nuts():
         assert abs(x.get_potential_energy() - y.get_potential_energy()) < 1e-5
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'fp64'])
+def test_device_resident_leapfrog_equals_array_level_leapfrog(precision):
+    """iid_leapfrog_host (kick, drift, fused energy + forces, kick, centring on
+    the device, states in device slots) against the host arithmetic of the
+    array-level path (pyiid/sim/__init__.py:10-38): positions and momenta bit
+    for bit, energies to the summation order; eager calls, graph capture and
+    replays; forward then backward returns to the start."""
+    atoms, scat = make_hmc_atoms(2, precision)
+    atoms.set_momenta(np.random.RandomState(0).normal(0, 1, (55, 3)))
+    atoms.get_forces()
+    host = sim._FastSystem(atoms)
+    dev = sim._DeviceSystem(atoms)
+    free0 = len(dev.pool.free)
+    sh, sd = host.state_of(atoms), dev.state_of(atoms)
+    assert sd.slot is not None and len(dev.pool.free) == free0 - 1
+    tol = 1e-12 if precision == 'fp64' else 2e-6  # atomics order; FP32 pair sums
+    for k, (step, centre) in enumerate([(0.05, True), (0.05, True), (0.02, False),
+                                        (-0.03, True), (0.05, True), (0.01, False)]):
+        nh, nd = host.leapfrog(sh, step, centre), dev.leapfrog(sd, step, centre)
+        assert np.abs(nd.q - nh.q).max() <= tol * np.abs(nh.q).max(), k
+        assert np.abs(nd.p - nh.p).max() <= tol * np.abs(nh.p).max(), k
+        assert abs(nd.pe - nh.pe) <= tol * abs(nh.pe), k
+        assert abs(nd.ke - nh.ke) <= 1e-12 * abs(nh.ke) + tol * abs(nh.ke), k
+        if precision == 'fp64' and k == 0:
+            # same operation order as numpy: the integrator itself adds no error
+            # beyond the force evaluation (atomics: last bits)
+            assert np.abs(nd.q - nh.q).max() < 1e-13
+        # the device state carries its forces: the next step starts from them
+        f = dev.be.state_download(nd.slot, want=('f',))['f']
+        assert np.abs(f - nh.f).max() <= tol * np.abs(nh.f).max(), k
+        sh, sd = nh, nd
+    # accepted samples: an Atoms object with cached energy and forces
+    a = dev.to_atoms(sd)
+    assert np.array_equal(a.get_positions(), sd.q) and a.get_potential_energy() == sd.pe
+    assert np.abs(a.get_forces() - sh.f).max() <= tol * np.abs(sh.f).max()
+    # reversibility on the device (tests/test_sim/test_leapfrog.py:58-73)
+    start = dev.state_of(atoms)
+    fwd = dev.leapfrog(start, 0.05, False)
+    back = dev.leapfrog(fwd, -0.05, False)
+    assert np.abs(back.q - start.q).max() < (1e-9 if precision == 'fp64' else 1e-5)
+    assert np.abs(back.p - start.p).max() < (1e-9 if precision == 'fp64' else 1e-4)
+    # slots return to the pool with their states
+    del nh, nd, sd, a, start, fwd, back
+    import gc
+    gc.collect()
+    assert len(dev.pool.free) == free0
+
+
+def test_device_state_nuts_equals_array_level_nuts():
+    """NUTS with the tree's states resident on the device draws the same random
+    numbers and follows the same trajectory as the array-level path."""
+    runs = []
+    for dev in (False, True):
+        atoms, scat = make_hmc_atoms(2, 'fp64')
+        np.random.seed(3)
+        ens = sim.NUTSCanonicalEnsemble(atoms, temperature=1000, escape_level=4, seed=5,
+                                        fast=True, device_states=dev)
+        assert ens.fast and ens.device_states is dev
+        traj, meta = ens.run(5)
+        runs.append((traj, dict(meta), ens.step_size, ens.leapfrogs))
+    (ta, ma, sa, la), (tb, mb, sb, lb) = runs
+    assert ma == mb and la == lb and len(ta) == len(tb) and ma['samples_total'] > 0
+    assert abs(sa - sb) < 1e-6 * abs(sa), (sa, sb)
+    for x, y in zip(ta, tb):
+        assert np.allclose(x.positions, y.positions, rtol=0, atol=1e-5)
+        assert np.allclose(x.get_momenta(), y.get_momenta(), rtol=0, atol=1e-5)
+        assert abs(x.get_potential_energy() - y.get_potential_energy()) < 1e-5
+        assert np.allclose(x.get_forces(), y.get_forces(), rtol=0, atol=1e-4)
+
+
 def test_example_workflow_and_coincident_atoms():
     """examples/au_np_pdf.py (the reference's Au_NP_PDF.py flow through the
     `pyiid` import paths) runs; coincident atoms contribute 0 instead of NaN."""
