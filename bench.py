@@ -277,6 +277,7 @@ def hmc_extra():
         a.set_calculator(calc)
         ens = sim.NUTSCanonicalEnsemble(a, temperature=1000, escape_level=8, seed=0, fast=fast,
                                         device_states=dev)
+        ens.run(1)  # graph capture, state slots, step-size adaptation start
         lf0, t = ens.leapfrogs, time.perf_counter()
         iters = 6 if fast else 3
         ens.run(iters)

@@ -188,6 +188,7 @@ class Backend(object):
         self._skey = key
         self._target_key = None
         self._last_target = None
+        self._sampler_key = None  # the native state slots are sized per structure
         self.n, self.nq = n, nq
         self._tensors = {}
 

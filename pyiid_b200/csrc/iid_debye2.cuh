@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
     const int ntile = (it.jend - it.jbegin) / TJ2;  // slabs are multiples of 32
     // warps w and w+4 share a scheduler: one produces the next tile before its
     // consume phase, the other after it, so one of them always feeds the FP32 pipe
+    // (measured: pairing by warp & 1, or no stagger at all, costs 6 %)
     const bool early = ((warp >> 2) & 1) == 0;
     produce(it.jbegin, 0);
     __syncthreads();
