@@ -134,8 +134,7 @@ struct iid_handle {
     int64_t lf_slots = 0;
     double *lf_mass = nullptr;   // [n]
     double *lf_ctl = nullptr;    // step, src, dst, centre flag, cell centre xyz
-    double *lf_out = nullptr;    // kinetic energy, shift xyz
-    double *lf_mirror = nullptr; // [2][3n] q and p of the new state, contiguous for one D2H
+    double *lf_mirror = nullptr; // q [3n] | p [3n] | scalars [16] of the new state: one D2H
     double *lf_pin = nullptr;    // pinned: ctl [8] | mirror [6n] | out [16]
     size_t lf_pin_count = 0;
     bool lf_system = false;
@@ -223,7 +222,7 @@ extern "C" int iid_destroy(iid_handle *h)
                     h->inv_na, h->inv_na_d, h->items_tri, h->items_sq, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
                     h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf,
-                    h->lf_slab, h->lf_mass, h->lf_ctl, h->lf_out, h->lf_mirror};
+                    h->lf_slab, h->lf_mass, h->lf_ctl, h->lf_mirror};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pinG) cudaFreeHost(h->pinG);
@@ -1197,12 +1196,31 @@ extern "C" int iid_get_restraint_energy(iid_handle *h, double *energy)
 // F(Q) pass -> F -> G(r) -> Rw / chi^2 (h->out4) -> chain-rule weights -> force
 // pass (h->force) -> fused restraints.  Enqueued on the handle's stream; shared
 // by iid_energy_forces_host and iid_leapfrog_host (both replay it from a graph).
-static int enqueue_eval_device(iid_handle *h, int potential, double conv, bool want_forces)
+static int enqueue_eval_device(iid_handle *h, int potential, double conv, bool want_forces,
+                               bool staged = false)
 {
     int rc2;
-    if ((rc2 = iid_fq_partial(h, h->pos, h->S, nullptr))) return rc2;
-    if ((rc2 = iid_fq_finish(h, h->S, h->F, nullptr))) return rc2;
-    if ((rc2 = iid_fq_to_gr(h, h->F, h->Gr, nullptr))) return rc2;
+    cudaStream_t st = h->stream;
+    // staging also clears S and the force accumulator (no memset nodes); a
+    // caller that staged the positions itself (leapfrog) has done both
+    if (!staged) {
+        const int np = (int)h->np;
+        prep_kernel<<<(np + 255) / 256, 256, 0, st>>>(h->pos, h->orig, np,
+                                                      h->precision == IID_FP32, h->x, h->y, h->z,
+                                                      h->valid, h->S, (int)h->qp, h->force,
+                                                      want_forces ? 3 * (int)h->n : 0);
+        ++h->launches;
+        CU(cudaGetLastError());
+    }
+    if ((rc2 = launch_debye(h, MODE_FQ, nullptr, h->S, nullptr, nullptr, st))) return rc2;
+    // F = 2 S / na and G = T F in one launch
+    {
+        const int64_t threads = h->nr * 32;
+        gr_from_s_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+            h->T, h->S, h->inv_na_d, h->nr, (int)h->nq, (int)h->qp, h->F, h->Gr);
+        ++h->launches;
+        CU(cudaGetLastError());
+    }
     // Rw / chi^2 in r space; the chain-rule weights in Q space:
     // wq = conv T^T c = conv (coef0 T^T go - coef1 (T^T T) F)
     if (!h->qspace_wq) {
@@ -1211,6 +1229,12 @@ static int enqueue_eval_device(iid_handle *h, int potential, double conv, bool w
         if ((rc2 = iid_potential(h, h->Gr, h->target, potential, conv, h->out4,
                                  want_forces ? h->wq : nullptr, nullptr)))
             return rc2;
+    } else if (want_forces) {
+        potential_kernel<<<1, 1024, 0, h->stream>>>(h->Gr, h->target, (int)h->nr, potential,
+                                                    conv, h->out4, h->cr, h->coef, h->Mq, h->F,
+                                                    h->vgo, (int)h->nq, (int)h->qp, h->wq);
+        ++h->launches;
+        CU(cudaGetLastError());
     } else {
         potential_kernel<<<1, 1024, 0, h->stream>>>(h->Gr, h->target, (int)h->nr, potential,
                                                     conv, h->out4, h->cr, h->coef);
@@ -1223,15 +1247,8 @@ static int enqueue_eval_device(iid_handle *h, int potential, double conv, bool w
                                      nullptr, h->out4 + 4, nullptr, nullptr, h->stream)))
                 return rc2;
     }
-    if (want_forces && h->qspace_wq) {
-        wq_from_q_kernel<<<(unsigned)((h->nq + 31) / 32), 1024, 0, h->stream>>>(
-            h->Mq, h->F, h->vgo, h->coef, (int)h->nq, (int)h->qp, conv, h->wq);
-        ++h->launches;
-        CU(cudaGetLastError());
-    }
     if (want_forces) {
-        // positions are already staged by iid_fq_partial; enqueue the force pass
-        CU(cudaMemsetAsync(h->force, 0, (size_t)h->n * 3 * sizeof(double), h->stream));
+        // positions are staged and h->force is cleared: enqueue the force pass
         if ((rc2 = launch_force(h, h->wq, h->force, h->stream))) return rc2;
         if (h->n_restraints) {
             // out4[4] was zeroed by potential_kernel (Q-space path) / the memset above
@@ -1378,7 +1395,7 @@ extern "C" int iid_sampler_setup(iid_handle *h, int64_t n_slots, const double *m
     if (h->lf_slab) { cudaFree(h->lf_slab); h->lf_slab = nullptr; }
     if ((rc = dev_alloc(&h->lf_slab, (size_t)n_slots * 3 * n3)) ||
         (rc = dev_alloc(&h->lf_mass, h->n)) || (rc = dev_alloc(&h->lf_ctl, LF_CTL)) ||
-        (rc = dev_alloc(&h->lf_out, 4)) || (rc = dev_alloc(&h->lf_mirror, 2 * n3)))
+        (rc = dev_alloc(&h->lf_mirror, 2 * n3 + 16)))
         return rc;
     h->lf_slots = n_slots;
     const size_t need = LF_CTL + 2 * n3 + 16;
@@ -1459,29 +1476,27 @@ extern "C" int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, i
         int rc2;
         CU(cudaMemcpyAsync(h->lf_ctl, ctl, LF_CTL * sizeof(double), cudaMemcpyHostToDevice,
                            h->stream));
-        lf_kick_drift_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, h->stream>>>(
-            h->lf_ctl, h->lf_slab, h->lf_mass, n, h->pos);
+        const int np = (int)h->np;
+        lf_stage_kernel<<<(np + 255) / 256, 256, 0, h->stream>>>(
+            h->lf_ctl, h->lf_slab, h->lf_mass, n, h->orig, np, h->precision == IID_FP32, h->pos,
+            h->x, h->y, h->z, h->valid, h->S, (int)h->qp, h->force, 3 * n);
         ++h->launches;
         CU(cudaGetLastError());
-        if ((rc2 = enqueue_eval_device(h, potential, conv, true))) return rc2;
+        if ((rc2 = enqueue_eval_device(h, potential, conv, true, true))) return rc2;
         lf_finish_kernel<<<1, 1024, 0, h->stream>>>(h->lf_ctl, h->lf_slab, h->lf_mass, n, h->pos,
-                                                    h->force, h->lf_mirror, h->lf_out);
+                                                    h->force, h->lf_mirror, h->out4);
         ++h->launches;
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(mir, h->lf_mirror, 2 * n3 * sizeof(double), cudaMemcpyDeviceToHost,
-                           h->stream));
-        CU(cudaMemcpyAsync(po, h->out4, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaMemcpyAsync(po + 8, h->lf_out, 4 * sizeof(double), cudaMemcpyDeviceToHost,
-                           h->stream));
+        CU(cudaMemcpyAsync(mir, h->lf_mirror, (2 * n3 + 16) * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->stream));
         return 0;
     };
     const bool graphable = h->use_graph && !h->timing;
     if ((rc = run_graphed(h, h->lf, graphable, potential, conv, false, enqueue))) return rc;
     CU(cudaStreamSynchronize(h->stream));
     // out: energy, scale, -, -, restraint energy, kinetic energy, shift x y z
-    for (int k = 0; k < 5; ++k) out_host[k] = po[k];
+    for (int k = 0; k < 9; ++k) out_host[k] = po[k];
     if (!h->n_restraints) out_host[4] = 0.0;
-    for (int k = 0; k < 4; ++k) out_host[5 + k] = po[8 + k];
     if (q_host) memcpy(q_host, mir, n3 * sizeof(double));
     if (p_host) memcpy(p_host, mir + n3, n3 * sizeof(double));
     return 0;

@@ -27,36 +27,63 @@ __device__ __forceinline__ double *lf_slot(double *slab, int n, int slot, int wh
     return slab + ((size_t)slot * 3 + which) * 3 * (size_t)n;
 }
 
-// p_half = p + (step/2) f;  q' = q + step (p_half / m).  Writes p_half into the
-// destination slot and q' into `pos` (the evaluation's input).
-__global__ void lf_kick_drift_kernel(const double *__restrict__ ctl, double *__restrict__ slab,
-                                     const double *__restrict__ mass, int n,
-                                     double *__restrict__ pos)
+// p_half = p + (step/2) f;  q' = q + step (p_half / m), fused with the staging of
+// the evaluation (prep_kernel): thread k = slot k of the element-sorted, padded
+// atom order.  Writes p_half into the destination slot, q' into `pos` (caller
+// order) and into the sorted x / y / z arrays (float32-rounded in FP32 mode),
+// and clears the accumulators S and force of the passes that follow.
+__global__ void lf_stage_kernel(const double *__restrict__ ctl, double *__restrict__ slab,
+                                const double *__restrict__ mass, int n,
+                                const int *__restrict__ orig, int np, int round_f32,
+                                double *__restrict__ pos, double *__restrict__ x,
+                                double *__restrict__ y, double *__restrict__ z,
+                                float *__restrict__ valid, double *__restrict__ zero_a, int na,
+                                double *__restrict__ zero_b, int nb)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= 3 * n) return;
-    const double step = ctl[0];
-    const int src = (int)ctl[1], dst = (int)ctl[2];
-    const double *q = lf_slot(slab, n, src, 0), *p = lf_slot(slab, n, src, 1),
-                 *f = lf_slot(slab, n, src, 2);
-    const double half = __dmul_rn(0.5, step);
-    const double ph = __dadd_rn(p[k], __dmul_rn(half, f[k]));
-    lf_slot(slab, n, dst, 1)[k] = ph;
-    pos[k] = __dadd_rn(q[k], __dmul_rn(step, __ddiv_rn(ph, mass[k / 3])));
+    for (int e = k; e < na; e += gridDim.x * blockDim.x) zero_a[e] = 0.0;
+    for (int e = k; e < nb; e += gridDim.x * blockDim.x) zero_b[e] = 0.0;
+    if (k >= np) return;
+    const int o = orig[k];
+    double c[3] = {0.0, 0.0, 0.0};
+    if (o >= 0) {
+        const double step = ctl[0];
+        const int src = (int)ctl[1], dst = (int)ctl[2];
+        const double *q = lf_slot(slab, n, src, 0), *p = lf_slot(slab, n, src, 1),
+                     *f = lf_slot(slab, n, src, 2);
+        double *pd = lf_slot(slab, n, dst, 1);
+        const double half = __dmul_rn(0.5, step), m = mass[o];
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const size_t e = 3 * (size_t)o + w;
+            const double ph = __dadd_rn(p[e], __dmul_rn(half, f[e]));
+            pd[e] = ph;
+            const double qn = __dadd_rn(q[e], __dmul_rn(step, __ddiv_rn(ph, m)));
+            pos[e] = qn;
+            c[w] = round_f32 ? (double)(float)qn : qn;
+        }
+    }
+    x[k] = c[0];
+    y[k] = c[1];
+    z[k] = c[2];
+    valid[k] = o >= 0 ? 1.f : 0.f;
 }
 
 // p = p_half + (step/2) f_new;  KE = sum p.p/m / 2;  q = q' + (cell centre -
 // (min + max)/2) when centring.  One block: the sampler's structures are small
-// and the three reductions need the whole array.  Mirrors q and p into one
-// contiguous buffer for the single device-to-host copy of the step.
+// and the three reductions need the whole array.  Mirrors q, p and the scalars
+// into one contiguous buffer for the single device-to-host copy of the step.
 __global__ void __launch_bounds__(1024) lf_finish_kernel(const double *__restrict__ ctl,
                                                          double *__restrict__ slab,
                                                          const double *__restrict__ mass, int n,
                                                          const double *__restrict__ pos,
                                                          const double *__restrict__ force,
                                                          double *__restrict__ mirror,
-                                                         double *__restrict__ out)
+                                                         const double *__restrict__ out4)
 {
+    // mirror = q [3n] | p [3n] | energy, scale, value, scale_true, restraint
+    // energy, kinetic energy, shift x y z: ONE device-to-host copy per step
+    double *out = mirror + 6 * (size_t)n;
     __shared__ double red[7][32];
     __shared__ double shift[3];
     const double step = ctl[0];
@@ -116,14 +143,15 @@ __global__ void __launch_bounds__(1024) lf_finish_kernel(const double *__restric
                 r[4 + w] = fmax(r[4 + w], __shfl_xor_sync(0xffffffffu, r[4 + w], o));
             }
         }
+        if (lane < 5) out[lane] = out4[lane];
         if (lane == 0) {
-            out[0] = 0.5 * r[0];
+            out[5] = 0.5 * r[0];
 #pragma unroll
             for (int w = 0; w < 3; ++w) {
                 // numpy: q + (centre - 0.5 * (min + max))
                 const double s = centre ? __dsub_rn(ctl[4 + w], __dmul_rn(0.5, __dadd_rn(r[1 + w], r[4 + w]))) : 0.0;
                 shift[w] = s;
-                out[1 + w] = s;
+                out[6 + w] = s;
             }
         }
     }

@@ -14,13 +14,19 @@ namespace iid {
 // SoA layout.  IID_FP32 rounds through float32 first, as wrap_fq does
 // (cpu_wrappers/flat_multi_cpu_wrap.py:11-12); the rounded value is then held
 // exactly in float64.
+// zero_a / zero_b (may be null): accumulators of the passes that follow (S,
+// force), cleared here so that the fused sequence needs no memset nodes.
 __global__ void prep_kernel(const double *__restrict__ pos,
                             const int *__restrict__ orig, int np,
                             int round_f32, double *__restrict__ x,
                             double *__restrict__ y, double *__restrict__ z,
-                            float *__restrict__ valid)
+                            float *__restrict__ valid,
+                            double *__restrict__ zero_a = nullptr, int na = 0,
+                            double *__restrict__ zero_b = nullptr, int nb = 0)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int e = k; e < na; e += gridDim.x * blockDim.x) zero_a[e] = 0.0;
+    for (int e = k; e < nb; e += gridDim.x * blockDim.x) zero_b[e] = 0.0;
     if (k >= np) return;
     const int o = orig[k];
     double px = 0.0, py = 0.0, pz = 0.0;
@@ -77,6 +83,25 @@ __global__ void gr_kernel(const TM *__restrict__ T,
     if (lane == 0) G[row] = acc;
 }
 
+// The same with F[m] = 2 S[m] / na[m] formed on the fly (finish_fq_kernel
+// folded in; block 0 also stores F): one launch less in the fused sequence,
+// identical arithmetic.
+__global__ void gr_from_s_kernel(const double *__restrict__ T, const double *__restrict__ S,
+                                 const double *__restrict__ inv_na, int64_t nr, int nq, int qp,
+                                 double *__restrict__ F, double *__restrict__ G)
+{
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0)
+        for (int m = threadIdx.x; m < nq; m += blockDim.x) F[m] = 2.0 * S[m] * inv_na[m];
+    if (row >= nr) return;
+    const double *t = T + (size_t)row * qp;
+    double acc = 0.0;
+    for (int m = lane; m < nq; m += 32) acc = fma(t[m], 2.0 * S[m] * inv_na[m], acc);
+    acc = warp_sum_d(acc);
+    if (lane == 0) G[row] = acc;
+}
+
 // Block-wide sum of up to three doubles (blockDim.x == 1024).
 __device__ __forceinline__ void block_sum3(double &a, double &b, double &c,
                                            double *sm)
@@ -103,14 +128,22 @@ __device__ __forceinline__ void block_sum3(double &a, double &b, double &c,
 //   grad = -rw/(d.d) * sum_r (scale dG + gc grad_a) d,  d = go - scale gc,
 //   grad_a = (-2 a (gc.dG) + (go.dG))/(gc.gc) with a the true scale.
 // get_chi_sq: scale <= 0 -> scale = 1; grad = -2 sum_r (...) d.
+// Mq / Fq / vgo / wq (may be null): the chain-rule weights in Q space,
+//   wq[m] = conv (coef0 vgo[m] - coef1 sum_n M[m][n] F[n]),   M = T^T T symmetric,
+// appended to the same launch (one warp per row m of M, coalesced along n).
 __global__ void potential_kernel(const double *__restrict__ gc,
                                  const double *__restrict__ go, int nr,
                                  int potential, double conv,
                                  double *__restrict__ out,
                                  double *__restrict__ cr,
-                                 double *__restrict__ coef)
+                                 double *__restrict__ coef,
+                                 const double *__restrict__ Mq = nullptr,
+                                 const double *__restrict__ Fq = nullptr,
+                                 const double *__restrict__ vgo = nullptr, int nq = 0,
+                                 int qp = 0, double *__restrict__ wq = nullptr)
 {
     __shared__ double sm[96];
+    __shared__ double scoef[2];
     double a = 0.0, b = 0.0, c = 0.0;
     for (int r = threadIdx.x; r < nr; r += blockDim.x) {
         const double x = gc[r], y = go[r];
@@ -149,11 +182,29 @@ __global__ void potential_kernel(const double *__restrict__ gc,
         out[3] = scale_true;
         if (coef) {
             // c = coef[0] * go - coef[1] * gc  (the chain-rule vector as a
-            // combination of the target and the model, see wq_from_q_kernel)
+            // combination of the target and the model, see the Q-space tail below)
             coef[0] = pref * (scale + gdb);
             coef[1] = pref * (scale * scale + 2.0 * gdb * scale_true);
             out[4] = 0.0;  // fused host path (out has 8 slots): restraint energy, summed later
         }
+        scoef[0] = pref * (scale + gdb);
+        scoef[1] = pref * (scale * scale + 2.0 * gdb * scale_true);
+    }
+    if (wq == nullptr) return;
+    __syncthreads();
+    const double c0 = scoef[0], c1 = scoef[1];
+    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int m = threadIdx.x >> 5; m < nq; m += nw) {
+        const double *row = Mq + (size_t)m * qp;
+        double t0 = 0.0, t1 = 0.0;
+        int n = lane;
+        for (; n + 32 < nq; n += 64) {
+            t0 = fma(row[n], Fq[n], t0);
+            t1 = fma(row[n + 32], Fq[n + 32], t1);
+        }
+        if (n < nq) t0 = fma(row[n], Fq[n], t0);
+        const double t = warp_sum_d(t0 + t1);
+        if (lane == 0) wq[m] = conv * (c0 * vgo[m] - c1 * t);
     }
 }
 
@@ -179,28 +230,6 @@ __global__ void __launch_bounds__(256) ttt_kernel(const double *__restrict__ T, 
         __syncthreads();
     }
     if (m < qp && n < qp) M[(size_t)m * qp + n] = (m < nq && n < nq) ? acc : 0.0;
-}
-
-// wq[m] = conv * (coef0 * vgo[m] - coef1 * sum_n M[n][m] F[n]); M is symmetric,
-// so the loads are coalesced along m.  Block = 32 bins m x 32 slices of n.
-__global__ void __launch_bounds__(1024) wq_from_q_kernel(
-    const double *__restrict__ M, const double *__restrict__ F, const double *__restrict__ vgo,
-    const double *__restrict__ coef, int nq, int qp, double conv, double *__restrict__ wq)
-{
-    __shared__ double part[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int m = blockIdx.x * 32 + tx;
-    double acc = 0.0;
-    if (m < nq)
-        for (int n = ty; n < nq; n += 32) acc = fma(M[(size_t)n * qp + m], F[n], acc);
-    part[ty][tx] = acc;
-    __syncthreads();
-    if (ty == 0 && m < nq) {
-        double t = 0.0;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) t += part[k][tx];
-        wq[m] = conv * (coef[0] * vgo[m] - coef[1] * t);
-    }
 }
 
 // wq[m] = conv * sum_r c[r] T[r][m].  Block = slab of WQ_ROWS rows, thread =
