@@ -226,7 +226,7 @@ def run_reference(args, rank, world):
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(world, note=None):
@@ -321,7 +321,31 @@ def config3_extra():
     return out
 
 
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """Keep the real stdout for the ONE JSON line: everything else that writes
+    to file descriptor 1 while the bench runs (NCCL's version banner, nvcc, C
+    libraries) goes to stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
@@ -482,7 +506,7 @@ def main():
                     line['extras'][key] = fn()
                 except Exception as exc:  # keep the headline line even if an extra fails
                     line['extras'][key + '_error'] = repr(exc)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
