@@ -432,12 +432,13 @@ class Backend(object):
         of the new state (q, p are host mirrors for the U-turn test)."""
         if potential not in POTENTIALS:
             raise NotImplementedError('Potential not implemented')
+        if target is not self._last_target:  # a new target object: validate it once
+            target = np.ascontiguousarray(target, dtype=np.float64)
+            if target.shape != (self.nr,):
+                raise ValueError('target must have the r-grid length %d' % self.nr)
+            self.sync_shard()
         if self.world != 1:
             raise _lib.IIDError('the device-resident leapfrog needs world == 1')
-        target = np.ascontiguousarray(target, dtype=np.float64)
-        if target.shape != (self.nr,):
-            raise ValueError('target must have the r-grid length %d' % self.nr)
-        self.sync_shard()
         tptr, tkey = self._target_ptr(target)
         out = np.empty(9, np.float64)
         q = np.empty((self.n, 3), np.float64)

@@ -14,6 +14,7 @@ stops at ``escape_level``.
 """
 from __future__ import print_function
 
+import math
 from collections import namedtuple
 from copy import deepcopy as dc
 from time import time
@@ -104,9 +105,13 @@ def _no_u_turn(minus, plus):
 
 
 def _safe_exp(x):
-    with np.errstate(over='ignore', invalid='ignore'):
-        v = np.exp(x)
-    return v if np.isfinite(v) else (np.inf if x > 0 else 0.0)
+    """exp(x) with overflow -> inf and a non-finite argument -> 0 (no numpy
+    error-state context per call: this runs three times per leapfrog)."""
+    try:
+        v = math.exp(x)
+    except OverflowError:
+        return np.inf
+    return v if v == v else 0.0
 
 
 def buildtree(input_atoms, u, v, j, e, e0, rs, beta=1):
@@ -143,10 +148,17 @@ def buildtree(input_atoms, u, v, j, e, e0, rs, beta=1):
 class _State(object):
     """Phase-space point of the array-level sampler path: positions, momenta,
     potential energy, forces, kinetic energy (no Atoms object per leapfrog)."""
-    __slots__ = ('q', 'p', 'pe', 'f', 'ke')
+    __slots__ = ('q', 'p', 'pe', 'f', 'ke', '_v')
 
     def __init__(self, q, p, pe, f, ke):
         self.q, self.p, self.pe, self.f, self.ke = q, p, pe, f, ke
+        self._v = None
+
+    def velocities(self, masses):
+        """p / m, flattened; kept: a state is an end point of several sub-trees."""
+        if self._v is None:
+            self._v = (self.p / masses).ravel()
+        return self._v
 
     @property
     def total(self):
@@ -254,9 +266,12 @@ class _DevState(_State):
         self.slot, self.pool = slot, pool
 
     def __del__(self):
-        if self.slot is not None:
-            self.pool.give(self.slot)
-            self.slot = None
+        try:
+            if self.slot is not None:
+                self.pool.give(self.slot)
+                self.slot = None
+        except Exception:  # interpreter shutdown: the pool may be gone already
+            pass
 
 
 class _DeviceSystem(_FastSystem):
@@ -318,8 +333,8 @@ class _DeviceSystem(_FastSystem):
 
 def _no_u_turn_states(minus, plus, masses):
     span = (plus.q - minus.q).ravel()
-    return (span.dot((minus.p / masses).ravel()) >= 0) and \
-        (span.dot((plus.p / masses).ravel()) >= 0)
+    return (span.dot(minus.velocities(masses)) >= 0) and \
+        (span.dot(plus.velocities(masses)) >= 0)
 
 
 def _buildtree_states(system, st, u, v, j, e, e0, rs):

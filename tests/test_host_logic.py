@@ -223,3 +223,41 @@ def test_empty_and_single_atom_inputs_need_no_device():
         assert g.shape == (n, 3, 250) and not np.any(g)
         pdf = s.get_pdf(atoms)
         assert pdf.shape == (4000,) and not np.any(pdf)
+
+
+def test_sampler_state_slots_and_helpers():
+    """Host side of the device-resident sampler: slots return to the pool with
+    the last reference to their state, the U-turn test on cached velocities is
+    the Atoms-level test, exp() guards keep the reference's conventions."""
+    pool = sim._SlotPool(4)
+    q = np.arange(6.).reshape(2, 3)
+    a = sim._DevState(q, q + 1, 1.0, None, 2.0, pool.take(), pool)
+    b = sim._DevState(q, q + 1, 1.0, None, 2.0, pool.take(), pool)
+    assert (a.slot, b.slot) == (0, 1) and len(pool.free) == 2 and a.total == 3.0
+    alias = a
+    del a
+    assert len(pool.free) == 2  # still referenced
+    del alias, b
+    assert sorted(pool.free) == [0, 1, 2, 3]
+    for _ in range(4):
+        pool.take()
+    with pytest.raises(RuntimeError):
+        pool.take()
+    # U-turn criterion: array-level == Atoms-level (nuts_hmc.py:84-86)
+    rs = np.random.RandomState(0)
+    atoms = structures.random_atoms(7, 1)
+    masses = atoms.get_masses().reshape(-1, 1)
+    for _ in range(20):
+        ends = []
+        for _ in range(2):
+            x = atoms.copy()
+            x.positions += rs.normal(0, 1, (7, 3))
+            x.set_momenta(rs.normal(0, 1, (7, 3)))
+            ends.append(x)
+        sts = [sim._State(x.get_positions(), x.get_momenta(), 0., None, 0.) for x in ends]
+        assert sim._no_u_turn_states(sts[0], sts[1], masses) == sim._no_u_turn(*ends)
+        assert sts[0].velocities(masses) is sts[0].velocities(masses)
+        assert np.array_equal(sts[0].velocities(masses), ends[0].get_velocities().ravel())
+    assert sim._safe_exp(0.) == 1.0 and sim._safe_exp(1e4) == np.inf
+    assert sim._safe_exp(-1e4) == 0.0 and sim._safe_exp(float('nan')) == 0.0
+    assert abs(sim._safe_exp(-3.5) - np.exp(-3.5)) < 1e-16
