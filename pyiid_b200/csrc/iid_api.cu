@@ -141,6 +141,7 @@ struct iid_handle {
     bool cheb = true;
     bool grad_split = true;  // full gradient: F(Q) from the lower-triangle items only
     bool prod_unroll = true; // gradient kernel: two pair set-ups per producer iteration
+    int grad_nw_max = 12;    // warps per gradient block (12: one block covers the 330-bin PDF grid)
     // instrumentation
     int64_t launches = 0;
     bool timing = false;
@@ -207,6 +208,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_CHEB")) h->cheb = atoi(s) != 0;
     if (const char *s = getenv("IID_GRAD_SPLIT")) h->grad_split = atoi(s) != 0;
     if (const char *s = getenv("IID_PROD_UNROLL")) h->prod_unroll = atoi(s) != 0;
+    if (const char *s = getenv("IID_GRAD_NW")) h->grad_nw_max = std::max(1, std::min(12, atoi(s)));
     if (const char *s = getenv("IID_QSPACE_WQ")) h->qspace_wq = atoi(s) != 0;
     if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
     *out = h;
@@ -617,11 +619,12 @@ static int launch_debye2_t(iid_handle *h, const DebyeParams &p, int64_t nblocks,
                            cudaStream_t st)
 {
     // warps per block = Q chunks per block.  The gradient needs 4C accumulators
-    // per thread (<= 8 warps at 255 registers); F(Q) / force blocks may take up
-    // to 12 warps so that one block covers the whole PDF grid (11 chunks) and
-    // the pair records are produced once, not once per chunk group.
+    // per thread: 8 warps at 220 registers, or 9-12 warps at 168 (a few spilled
+    // words) when that lets ONE block cover the grid -- the 330-bin PDF grid is
+    // 11 chunks: 12.1 ms at Au 10k against 15.8 ms as two 6-warp blocks that
+    // each produce the pair records.  F(Q) / force blocks take up to 12 warps.
     const int nchunk = (int)((h->nq + C - 1) / C);
-    const int nwmax = MODE == MODE_GRAD ? std::min(h->nw_max, 8) : h->nw_max;
+    const int nwmax = MODE == MODE_GRAD ? std::min(h->nw_max, h->grad_nw_max) : h->nw_max;
     const int gy = (nchunk + nwmax - 1) / nwmax;
     const int nw = (nchunk + gy - 1) / gy;
     dim3 grid((unsigned)nblocks, (unsigned)gy, 1), block(32 * nw, 1, 1);
@@ -1616,6 +1619,7 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "cheb") h->cheb = value != 0;
     else if (k == "grad_split") h->grad_split = value != 0;
     else if (k == "prod_unroll") h->prod_unroll = value != 0;
+    else if (k == "grad_nw_max") h->grad_nw_max = (int)std::max<int64_t>(1, std::min<int64_t>(12, value));
     else if (k == "qspace_wq") h->qspace_wq = value != 0;
     else if (k == "nw_max") h->nw_max = (int)std::max<int64_t>(1, std::min<int64_t>(12, value));
     else return fail(IID_E_BADARG, "unknown option: " + k);
