@@ -91,16 +91,35 @@ __global__ void __launch_bounds__(MAXT, 1) debye64_kernel(const DebyeParams p)
             const int gj = jt + jj;
             const double dx = p.x[gj] - xi, dy = p.y[gj] - yi, dz = p.z[gj] - zi;
             const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
-            const bool ok = vi && p.valid[gj] != 0.f && r2 > 0.0;
-            const double r = sqrt(r2);
-            const double invr = ok ? 1.0 / r : 0.0;
+            const bool ok = vi && p.valid[gj] != 0.f && (float)r2 > 0.f;
+            // 1/r: MUFU.RSQ seed (2^-23) + two Newton steps (-> 1e-14, 1e-16);
+            // cheaper than the IEEE sqrt + divide sequences
+            double y = (double)rsqrtf((float)r2);
+            y = y * fma(-0.5 * r2, y * y, 1.5);
+            y = y * fma(-0.5 * r2, y * y, 1.5);
+            const double invr = ok ? y : 0.0;
+            const double r = r2 * invr;
             const double u = r * p.qbin_turns;  // turns per Q bin
             double sth, cth, sC, cC, s, c;
             sincospi(2.0 * (u - rint(u)), &sth, &cth);
-            double ph = u * (double)C;
-            sincospi(2.0 * (ph - rint(ph)), &sC, &cC);
-            ph = u * (double)(chunk0 * C);
-            sincospi(2.0 * (ph - rint(ph)), &s, &c);
+            // rotation by one chunk: e^{i C theta} by log2(C) squarings of
+            // e^{i theta} (float64: the doubling of the 1e-16 rounding is harmless)
+            sC = sth;
+            cC = cth;
+#pragma unroll
+            for (int d = 1; d < C; d <<= 1) {
+                const double s2 = 2.0 * sC * cC;
+                cC = fma(cC, cC, -(sC * sC));
+                sC = s2;
+            }
+            static_assert((C & (C - 1)) == 0, "C must be a power of two");
+            if (chunk0 == 0) {
+                s = 0.0;
+                c = 1.0;
+            } else {
+                const double ph = u * (double)(chunk0 * C);
+                sincospi(2.0 * (ph - rint(ph)), &s, &c);
+            }
             const double b3 = invr * invr * invr;
             s *= b3;
             c *= b3;
