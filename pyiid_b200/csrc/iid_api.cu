@@ -889,7 +889,14 @@ extern "C" int iid_grad_pdf(iid_handle *h, const void *grad_fq_dev, int64_t rows
 // data is complete when the function returns.
 static int download_pipelined(iid_handle *h, const void *dev, void *host, size_t bytes)
 {
-    const size_t CH = (size_t)8 << 20;
+    static const size_t CH = []() {
+        const char *e = getenv("IID_DL_CHUNK_MB");
+        return (size_t)std::max(1, e ? atoi(e) : 32) << 20;
+    }();
+    static const int nthreads = []() {
+        const char *e = getenv("IID_DL_THREADS");
+        return std::max(1, std::min(32, e ? atoi(e) : 8));
+    }();
     const size_t nchunks = (bytes + CH - 1) / CH;
     if (bytes > h->pinG_bytes) {
         if (h->pinG) cudaFreeHost(h->pinG);
@@ -910,11 +917,10 @@ static int download_pipelined(iid_handle *h, const void *dev, void *host, size_t
                                cudaMemcpyDeviceToHost, h->stream));
             CU(cudaEventRecord(h->chunk_ev[c], h->stream));
         }
-        const int nthreads = 4;
         for (size_t c = 0; c < nchunks; ++c) {
             const size_t off = c * CH, len = std::min(CH, bytes - off);
             CU(cudaEventSynchronize(h->chunk_ev[c]));
-            std::thread workers[nthreads];
+            std::vector<std::thread> workers((size_t)nthreads);
             const size_t part = (len + nthreads - 1) / nthreads;
             for (int t = 0; t < nthreads; ++t) {
                 const size_t o = (size_t)t * part;

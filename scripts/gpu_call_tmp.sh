@@ -1,3 +1,2 @@
-mkdir -p gpurun_out
-( time python -m pytest tests -m gpu -q --timeout 900 ) > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
-python scripts/gpu_time.py 2>&1 | grep fp64
+for cfg in "4 8" "8 8" "16 8" "8 4" "8 16" "16 32" "2 8"; do set -- $cfg; IID_DL_THREADS=$1 IID_DL_CHUNK_MB=$2 python scripts/gpu_e2e_time.py 2>&1 | tail -1; done
+nproc
