@@ -251,9 +251,13 @@ int iid_download_host(iid_handle *h, const void *dev, void *host, int64_t bytes)
 
 /* Tunables: "force_table" (0/1: tabulated radial force pass in FP32 mode),
  * "force_table_min_n" (atoms from which it is used), "graph" (0/1: CUDA-graph
- * replay of iid_energy_forces_host), "cheb" (0/1: three-term recurrence),
- * "nw_max" (warps per block).  Defaults can also be set with IID_* environment
- * variables before iid_create. */
+ * replay of iid_energy_forces_host / iid_leapfrog_host), "cheb" (0/1:
+ * three-term recurrence), "qspace_wq" (0/1: chain-rule weights in Q space),
+ * "nw_max" (warps per block), "grad_nw_max" (warps per full-gradient block),
+ * "grad_split" (0/1: F(Q) summed below the diagonal only, gradient-only bin
+ * loop above it), "prod_unroll" (0/1: two pair set-ups per producer
+ * iteration).  Defaults can also be set with IID_* environment variables
+ * before iid_create. */
 int iid_set_option(iid_handle *h, const char *key, int64_t value);
 
 /* instrumentation ---------------------------------------------------------- */

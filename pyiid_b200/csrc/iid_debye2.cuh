@@ -13,7 +13,9 @@
 // rotating with e^{i C theta}), double-buffered so that the records of tile
 // t+1 are produced while tile t is consumed.  The consumer's per-(pair, chunk)
 // overhead is a handful of shared-memory loads; its bin loop is pure FP32 pipe
-// work: 10 instructions per bin for F + grad F, 5 for F only, 6 for the force.
+// work on packed (two-bin) instructions: 8.25 per bin step for F + grad F, 6.7
+// for the gradient-only items of the square walk, ~2.6 for F only, ~4.3 for
+// the force.
 //
 // Packed arithmetic.  With one atom pair per lane every FFMA operand is a
 // per-lane register, and on sm_100 a scalar FFMA whose two multiplicands sit
