@@ -439,16 +439,19 @@ def main():
     kernel_ms_avg = max_over_ranks(float(np.mean(ks)))
 
     # ---- end to end through the public host-buffer API ------------------------
+    # with several ranks the reduced gradient is delivered to rank 0's host
+    # array (root_only), as the reference's one-process multi-GPU path does
     for _ in range(2):
-        be.grad_fq(pos, with_fq=True)
+        be.grad_fq(pos, with_fq=True, root_only=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        g_host, f_host2 = be.grad_fq(pos, with_fq=True)
+        g_host, f_host2 = be.grad_fq(pos, with_fq=True, root_only=True)
+    barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = pairq * args.steps / e2e_s
     h2d = pos.nbytes
-    d2h = g_host.nbytes + f_host2.nbytes
+    d2h = (g_host.nbytes if g_host is not None else 0) + f_host2.nbytes
 
     if rank != 0:
         if world > 1:
@@ -491,7 +494,8 @@ def main():
         dict(workload_config(world), atoms=n_atoms, note='non-default --atoms'),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                 'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * e2e_s / args.steps,
-                'api': 'ElasticScatter.grad (wrap_fq_grad) + F(Q), host numpy in/out'},
+                'api': 'ElasticScatter.grad (wrap_fq_grad) + F(Q), host numpy in/out'
+                       + (' (reduced to rank 0: Backend.grad_fq(root_only=True))' if world > 1 else '')},
         'gpu_launches': int(launches),
         'roofline': roofline,
         'clocks': clocks,

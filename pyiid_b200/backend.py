@@ -264,12 +264,17 @@ class Backend(object):
             check(self.lib.iid_fq_finish(self.h, s.data_ptr(), f.data_ptr(), st))
             return f.cpu().numpy()
 
-    def grad_fq(self, positions, with_fq=False):
+    def grad_fq(self, positions, with_fq=False, root_only=False):
         """grad F(Q) [N,3,nq] in the kernel precision
-        (flat_multi_cpu_wrap.wrap_fq_grad :63-102)."""
+        (flat_multi_cpu_wrap.wrap_fq_grad :63-102).  Sharded over ranks the
+        partial gradients are all-reduced and every rank returns the full
+        array; ``root_only`` reduces to rank 0 instead (the other ranks return
+        None for the gradient), as the reference's single-process multi-GPU
+        path delivers one host array (gpu_wrap.py:287-314)."""
         pos = self._pos(positions)
         self.sync_shard()
-        g = np.empty((self.n, 3, self.nq), self.gdtype)
+        want_g = self.world == 1 or not root_only or self.rank == 0
+        g = np.empty((self.n, 3, self.nq), self.gdtype) if want_g else None
         f = np.empty(self.nq, np.float64)
         if self.world == 1:
             check(self.lib.iid_grad_fq_host(self.h, pos.ctypes.data, g.ctypes.data,
@@ -287,10 +292,14 @@ class Backend(object):
             check(self.lib.iid_grad_fq_partial(self.h, p.data_ptr(), gt.data_ptr(),
                                                s.data_ptr(), st))
             dist.all_reduce(s)
-            dist.all_reduce(gt)
+            if root_only:
+                dist.reduce(gt, dst=0)
+            else:
+                dist.all_reduce(gt)
             check(self.lib.iid_fq_finish(self.h, s.data_ptr(), ft.data_ptr(), st))
-            check(self.lib.iid_download_host(self.h, gt.data_ptr(), g.ctypes.data,
-                                             g.nbytes))
+            if want_g:
+                check(self.lib.iid_download_host(self.h, gt.data_ptr(), g.ctypes.data,
+                                                 g.nbytes))
             f = ft.cpu().numpy()
         return (g, f) if with_fq else g
 
