@@ -525,6 +525,7 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
         CU(cudaMemcpy(h->ftab, ft.data(), ft.size() * esz, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->inv_na, inv_na.data(), qp * esz, cudaMemcpyHostToDevice));
     }
+    CU(cudaStreamSynchronize(0));  // NULL-stream copies done before the handle's stream runs
     // pinned staging: positions / forces (3n), F (qp), G(r) (nr, grown later), 4
     const size_t need = (size_t)6 * n + 2 * qp + 8 + 2 * (size_t)h->nr;
     if (need > h->pin_count) {
@@ -555,6 +556,9 @@ extern "C" int iid_set_transform(iid_handle *h, int64_t nr, int64_t nq, const do
     if ((rc = dev_alloc(&h->Mq, (size_t)h->qp * h->qp)) || (rc = dev_alloc(&h->vgo, h->qp)) ||
         (rc = dev_alloc(&h->coef, 2)))
         return rc;
+    // the copies above ran on the NULL stream; the handle's stream is
+    // non-blocking and does not order itself after them
+    CU(cudaStreamSynchronize(0));
     {
         const unsigned g = (unsigned)((h->qp + 15) / 16);
         ttt_kernel<<<dim3(g, g), 256, 0, h->stream>>>(h->T, (int)nr, (int)h->nq, (int)h->qp, h->Mq);
@@ -1416,6 +1420,7 @@ extern "C" int iid_sampler_setup(iid_handle *h, int64_t n_slots, const double *m
     }
     CU(cudaMemcpy(h->lf_mass, masses_host, h->n * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemset(h->lf_slab, 0, (size_t)n_slots * 3 * n3 * sizeof(double)));
+    CU(cudaStreamSynchronize(0));
     for (int w = 0; w < 3; ++w) h->lf_pin[4 + w] = cell_centre[w];
     h->lf_system = true;
     return 0;
@@ -1442,6 +1447,7 @@ extern "C" int iid_state_upload(iid_handle *h, int slot, const double *q_host,
     CU(cudaMemcpy(base, q_host, bytes, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(base + n3, p_host, bytes, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(base + 2 * n3, f_host, bytes, cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(0));  // pageable copies: the DMA may still be in flight
     return 0;
 }
 
