@@ -1242,17 +1242,19 @@ static int enqueue_eval_device(iid_handle *h, int potential, double conv, bool w
         if ((rc2 = iid_potential(h, h->Gr, h->target, potential, conv, h->out4,
                                  want_forces ? h->wq : nullptr, nullptr)))
             return rc2;
-    } else if (want_forces) {
-        potential_kernel<<<1, 1024, 0, h->stream>>>(h->Gr, h->target, (int)h->nr, potential,
-                                                    conv, h->out4, h->cr, h->coef, h->Mq, h->F,
-                                                    h->vgo, (int)h->nq, (int)h->qp, h->wq);
-        ++h->launches;
-        CU(cudaGetLastError());
     } else {
         potential_kernel<<<1, 1024, 0, h->stream>>>(h->Gr, h->target, (int)h->nr, potential,
                                                     conv, h->out4, h->cr, h->coef);
         ++h->launches;
         CU(cudaGetLastError());
+        if (want_forces) {
+            // a separate 11-block launch: appended to the one-block potential
+            // kernel the 0.9 MB mat-vec ran at one SM's bandwidth (39 us under ncu)
+            wq_from_q_kernel<<<(unsigned)((h->nq + 31) / 32), 1024, 0, h->stream>>>(
+                h->Mq, h->F, h->vgo, h->coef, (int)h->nq, (int)h->qp, conv, h->wq);
+            ++h->launches;
+            CU(cudaGetLastError());
+        }
     }
     if (!want_forces && h->n_restraints) {
         for (int s = 0; s < h->n_restraints; ++s)

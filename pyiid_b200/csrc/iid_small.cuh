@@ -128,22 +128,14 @@ __device__ __forceinline__ void block_sum3(double &a, double &b, double &c,
 //   grad = -rw/(d.d) * sum_r (scale dG + gc grad_a) d,  d = go - scale gc,
 //   grad_a = (-2 a (gc.dG) + (go.dG))/(gc.gc) with a the true scale.
 // get_chi_sq: scale <= 0 -> scale = 1; grad = -2 sum_r (...) d.
-// Mq / Fq / vgo / wq (may be null): the chain-rule weights in Q space,
-//   wq[m] = conv (coef0 vgo[m] - coef1 sum_n M[m][n] F[n]),   M = T^T T symmetric,
-// appended to the same launch (one warp per row m of M, coalesced along n).
 __global__ void potential_kernel(const double *__restrict__ gc,
                                  const double *__restrict__ go, int nr,
                                  int potential, double conv,
                                  double *__restrict__ out,
                                  double *__restrict__ cr,
-                                 double *__restrict__ coef,
-                                 const double *__restrict__ Mq = nullptr,
-                                 const double *__restrict__ Fq = nullptr,
-                                 const double *__restrict__ vgo = nullptr, int nq = 0,
-                                 int qp = 0, double *__restrict__ wq = nullptr)
+                                 double *__restrict__ coef)
 {
     __shared__ double sm[96];
-    __shared__ double scoef[2];
     double a = 0.0, b = 0.0, c = 0.0;
     for (int r = threadIdx.x; r < nr; r += blockDim.x) {
         const double x = gc[r], y = go[r];
@@ -182,29 +174,11 @@ __global__ void potential_kernel(const double *__restrict__ gc,
         out[3] = scale_true;
         if (coef) {
             // c = coef[0] * go - coef[1] * gc  (the chain-rule vector as a
-            // combination of the target and the model, see the Q-space tail below)
+            // combination of the target and the model, see wq_from_q_kernel)
             coef[0] = pref * (scale + gdb);
             coef[1] = pref * (scale * scale + 2.0 * gdb * scale_true);
             out[4] = 0.0;  // fused host path (out has 8 slots): restraint energy, summed later
         }
-        scoef[0] = pref * (scale + gdb);
-        scoef[1] = pref * (scale * scale + 2.0 * gdb * scale_true);
-    }
-    if (wq == nullptr) return;
-    __syncthreads();
-    const double c0 = scoef[0], c1 = scoef[1];
-    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int m = threadIdx.x >> 5; m < nq; m += nw) {
-        const double *row = Mq + (size_t)m * qp;
-        double t0 = 0.0, t1 = 0.0;
-        int n = lane;
-        for (; n + 32 < nq; n += 64) {
-            t0 = fma(row[n], Fq[n], t0);
-            t1 = fma(row[n + 32], Fq[n + 32], t1);
-        }
-        if (n < nq) t0 = fma(row[n], Fq[n], t0);
-        const double t = warp_sum_d(t0 + t1);
-        if (lane == 0) wq[m] = conv * (c0 * vgo[m] - c1 * t);
     }
 }
 
@@ -230,6 +204,28 @@ __global__ void __launch_bounds__(256) ttt_kernel(const double *__restrict__ T, 
         __syncthreads();
     }
     if (m < qp && n < qp) M[(size_t)m * qp + n] = (m < nq && n < nq) ? acc : 0.0;
+}
+
+// wq[m] = conv * (coef0 * vgo[m] - coef1 * sum_n M[n][m] F[n]); M is symmetric,
+// so the loads are coalesced along m.  Block = 32 bins m x 32 slices of n.
+__global__ void __launch_bounds__(1024) wq_from_q_kernel(
+    const double *__restrict__ M, const double *__restrict__ F, const double *__restrict__ vgo,
+    const double *__restrict__ coef, int nq, int qp, double conv, double *__restrict__ wq)
+{
+    __shared__ double part[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int m = blockIdx.x * 32 + tx;
+    double acc = 0.0;
+    if (m < nq)
+        for (int n = ty; n < nq; n += 32) acc = fma(M[(size_t)n * qp + m], F[n], acc);
+    part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && m < nq) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += part[k][tx];
+        wq[m] = conv * (coef[0] * vgo[m] - coef[1] * t);
+    }
 }
 
 // wq[m] = conv * sum_r c[r] T[r][m].  Block = slab of WQ_ROWS rows, thread =
