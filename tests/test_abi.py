@@ -80,3 +80,37 @@ def test_shard_plan_partitions_the_pair_list():
                 assert sum(slots) == expect
                 if total >= 16 * world:
                     assert max(slots) <= 1.15 * (sum(slots) / world) + 32 * 4096
+
+
+def test_shard_plan_property_random_structures():
+    """Property form of the test above (hypothesis): any element mix, any
+    world size -- the ranks' slices partition the work list, the triangle list
+    covers every unordered tile pair once and the square list every ordered
+    (i, j) slot once (lower items + diagonal tiles + gradient-only mirror
+    items above the diagonal)."""
+    from hypothesis import given, settings, strategies as st
+    lib = _lib.load()
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.integers(1, 900), min_size=1, max_size=4), st.integers(1, 9),
+           st.sampled_from([1, 37, 148]))
+    def check(counts, world, sms):
+        types = np.repeat(np.arange(len(counts)), counts).astype(np.int32)
+        n = len(types)
+        npad = int(sum((c + 31) // 32 * 32 for c in counts))
+        nt = npad // 32
+        for tri in (0, 1):
+            slots = items = 0
+            total = None
+            for rank in range(world):
+                v = [ctypes.c_int64(0) for _ in range(4)]
+                assert lib.iid_plan_shard(n, types.ctypes.data, len(counts), sms, tri, rank,
+                                          world, *[ctypes.byref(x) for x in v]) == 0
+                total = v[0].value
+                items += v[1].value
+                slots += v[2].value
+                assert v[3].value == npad
+            assert items == total
+            assert slots == (npad * npad if not tri else (nt * (nt - 1) // 2 + nt) * 1024)
+
+    check()
