@@ -33,7 +33,8 @@ else:
     MaxwellBoltzmannDistribution = ase_shim.MaxwellBoltzmannDistribution
     kB, fs = ase_shim.units.kB, ase_shim.units.fs
 
-__all__ = ['leapfrog', 'Ensemble', 'NUTSCanonicalEnsemble', 'buildtree']
+__all__ = ['leapfrog', 'Ensemble', 'NUTSCanonicalEnsemble', 'buildtree',
+           'classical_dynamics']
 
 Emax = 200  # energy error beyond which a trajectory counts as divergent
 
@@ -49,6 +50,25 @@ def leapfrog(atoms, step, center=True):
     if center:
         latoms.center()
     return latoms
+
+
+def classical_dynamics(atoms, stepsize, n_steps):
+    """Hamiltonian dynamics by repeated leapfrog steps; returns the list of
+    configurations, the start included (``pyiid/sim/dynamics.py:5-30``).  With
+    the fused device calculator the states stay on the device between steps
+    (:class:`_DeviceSystem`); an Atoms object is built per returned frame."""
+    atoms.get_forces()
+    traj = [atoms]
+    if _DeviceSystem.usable(atoms):
+        system = _DeviceSystem(atoms)
+        st = system.state_of(atoms)
+        for _ in range(n_steps):
+            st = system.leapfrog(st, stepsize)
+            traj.append(system.to_atoms(st))
+        return traj
+    for _ in range(n_steps):
+        traj.append(leapfrog(traj[-1], stepsize))
+    return traj
 
 
 class Ensemble(Optimizer):

@@ -180,6 +180,22 @@ def test_leapfrog_properties():
     assert np.allclose(sim.leapfrog(z, 1, False).positions, 0)
 
 
+def test_classical_dynamics_conserves_energy():
+    """pyiid/sim/dynamics.py: n leapfrog steps, n + 1 frames, start included;
+    the Hamiltonian of the harmonic stand-in is conserved to O(step^2)."""
+    from pyiid.sim.dynamics import classical_dynamics
+    a = ase_shim.Atoms('Au3', np.random.RandomState(2).normal(size=(3, 3)))
+    a.set_calculator(Harmonic())
+    a.set_momenta(np.random.RandomState(3).normal(size=(3, 3)))
+    traj = classical_dynamics(a, 0.05, 20)
+    assert len(traj) == 21 and traj[0] is a
+    # the first step re-centres the cluster in its cell (leapfrog's default),
+    # which the toy well -- unlike Rw -- is not invariant to
+    e = [t.get_total_energy() for t in traj[1:]]
+    assert max(e) - min(e) < 1e-2 * abs(e[0])
+    assert not np.allclose(traj[-1].positions, traj[0].positions)
+
+
 def test_nuts_samples_a_harmonic_well():
     a = ase_shim.Atoms('Au3', np.random.RandomState(0).normal(size=(3, 3)))
     a.set_calculator(Harmonic())
