@@ -589,6 +589,22 @@ def test_device_state_nuts_equals_array_level_nuts():
         assert np.allclose(x.get_forces(), y.get_forces(), rtol=0, atol=1e-4)
 
 
+def test_classical_dynamics_on_device_states_equals_atoms_level_leapfrogs():
+    """pyiid/sim/dynamics.py on the fused calculator: frames from the
+    device-resident states equal repeated Atoms-level leapfrog steps."""
+    atoms, scat = make_hmc_atoms(2, 'fp64')
+    atoms.set_momenta(np.random.RandomState(1).normal(0, 1, (55, 3)))
+    traj = sim.classical_dynamics(atoms, 0.02, 4)
+    assert len(traj) == 5 and traj[0] is atoms
+    ref = atoms
+    for frame in traj[1:]:
+        ref = sim.leapfrog(ref, 0.02)
+        assert np.allclose(frame.positions, ref.positions, rtol=0, atol=1e-9)
+        assert np.allclose(frame.get_momenta(), ref.get_momenta(), rtol=0, atol=1e-9)
+        assert abs(frame.get_potential_energy() - ref.get_potential_energy()) < 1e-9
+        assert np.allclose(frame.get_forces(), ref.get_forces(), rtol=0, atol=1e-8)
+
+
 def test_example_workflow_and_coincident_atoms():
     """examples/au_np_pdf.py (the reference's Au_NP_PDF.py flow through the
     `pyiid` import paths) runs; coincident atoms contribute 0 instead of NaN."""
