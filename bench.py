@@ -441,8 +441,11 @@ def main():
     # ---- end to end through the public host-buffer API ------------------------
     # with several ranks the reduced gradient is delivered to rank 0's host
     # array (root_only), as the reference's one-process multi-GPU path does
-    for _ in range(2):
-        be.grad_fq(pos, with_fq=True, root_only=True)
+    # warm-up with the reference pattern of the timed loop: the previous result
+    # is still alive while the next one is produced, so the pinned-output pool
+    # reaches its steady state (two buffers) before the clock starts
+    for _ in range(3):
+        g_host, f_host2 = be.grad_fq(pos, with_fq=True, root_only=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):

@@ -62,9 +62,30 @@ int iid_destroy(iid_handle *h);
 int iid_get_stream(iid_handle *h, void **stream);
 int iid_synchronize(iid_handle *h);
 
-/* Which slice of the pair-tile work list this handle computes: items
- * rank, rank+world, ... (one process per GPU; the caller all-reduces the
- * partial outputs).  Default (0, 1).  Replaces gpu_wrap.gpu_multithreading. */
+/* One handle over several GPUs of the box, in ONE process: what
+ * set_processor('Multi-GPU') gives in the reference (the thread-per-GPU farm
+ * gpu_wrappers/gpu_wrap.py:119-156, 287-314 driven by gpu_multithreading).
+ * n_devices <= 0 = every visible device.  The handle owns one sub-handle per
+ * device; device d computes shard (d, active) of every pass, `active` =
+ * min(n_devices, atoms / 1500) per structure.  The F(Q) pair sums and the
+ * force array are summed on the host in device order; gradient rows are
+ * disjoint per device and are written straight into the caller's array.
+ * Every host-buffer entry point accepts such a handle (the small float64
+ * stages, springs and the device-resident sampler run on device 0; the
+ * sampler states need a structure small enough for one device); the
+ * device-pointer (enqueue-only) pair-sum calls and iid_set_shard return
+ * IID_E_BADARG. */
+int iid_create_multi(int n_devices, int precision, iid_handle **out);
+/* devices behind a handle (1 for iid_create) and how many the current
+ * structure uses */
+int iid_handle_devices(iid_handle *h, int *n_devices, int *active);
+
+/* Which slice of the work this handle computes (one process per GPU; the
+ * caller sums the partial F(Q) / force outputs): work items rank, rank+world,
+ * ... of the pair-triangle list (F(Q), force), and the gradient ROWS of the
+ * i-tiles rank, rank+world, ... (full gradient: every row is computed by one
+ * rank only, so there is no gradient collective).  Default (0, 1).  Replaces
+ * gpu_wrap.gpu_multithreading for the one-process-per-GPU launch. */
 int iid_set_shard(iid_handle *h, int rank, int world);
 
 /* Structure = what stays fixed while positions move: per-atom element index
@@ -95,6 +116,19 @@ int iid_plan_shard(int64_t n, const int32_t *type_index, int64_t n_types,
                    int64_t *n_items_total, int64_t *n_items_mine,
                    int64_t *pair_slots_mine, int64_t *padded_atoms);
 
+/* Host-only: the row jobs of the full-gradient pass that rank `rank` of
+ * `world` runs (iid_set_structure + iid_set_shard build the same): 4 int32 per
+ * job (itile, seg_begin, seg_end, dest: -1 = stores its rows into G, >= 0 =
+ * piece slot of a split row), per segment (jbegin, jend, info, 0) with info =
+ * element type | 1<<16 diagonal tile | 1<<17 gradient only | 1<<18 flush, per
+ * split row (itile, first slot, one past the last slot, 0).  Output arrays may
+ * be NULL (counts only); piece_div <= 0 = default. */
+int iid_plan_rows(int64_t n, const int32_t *type_index, int64_t n_types,
+                  int sm_count, int rank, int world, int piece_div,
+                  int64_t *n_jobs, int64_t *n_segs, int64_t *n_fixes,
+                  int32_t *jobs, int64_t jobs_cap, int32_t *segs,
+                  int64_t segs_cap, int32_t *fixes, int64_t fixes_cap);
+
 /* sizes ------------------------------------------------------------------- */
 int iid_get_sizes(iid_handle *h, int64_t *n, int64_t *nq, int64_t *nr,
                   int64_t *n_items_fq, int64_t *n_items_grad);
@@ -113,15 +147,19 @@ int iid_fq_partial(iid_handle *h, const double *pos_dev, double *S_dev,
 int iid_fq_finish(iid_handle *h, const double *S_dev, double *F_dev,
                   void *stream);
 
-/* iid_grad_fq_partial: this shard's rows/terms of the NORMALISED gradient in
- * the reference's convention (SURVEY.md section 8a note 1)
+/* iid_grad_fq_partial: this shard's ROWS of the NORMALISED gradient in the
+ * reference's convention (SURVEY.md section 8a note 1)
  *   G[i,w,m] = (1/na[m]) sum_j f_i f_j a_ij(m) (q_j - q_i)_w,
  *   a = (Q cos(Q r) - sin(Q r)/r) / r^2
- * accumulated into G_dev[n][3][nq] (float32 for IID_FP32, float64 for
- * IID_FP64; the call zeroes it first), plus the same S[m] partial as
- * iid_fq_partial in S_dev (may be NULL).  Replaces atomic_grad_fq
- * (cpu_atomics.py:81-102, gpu_atomics.py:192-280) + the /na of
- * flat_multi_cpu_wrap.py:93-102. */
+ * into G_dev[n][3][nq] (float32 for IID_FP32, float64 for IID_FP64).  Row
+ * ownership: a block walks one i-tile against ALL j and stores each row once
+ * (plain coalesced stores: no zero-fill, no atomics, bit-reproducible); rows
+ * of atoms owned by other shards are NOT touched.  G_dev may be device memory
+ * or the device alias of pinned, mapped host memory (iid_host_alloc /
+ * iid_host_register + iid_host_device_pointer).  S_dev (may be NULL) receives
+ * this shard's F(Q) pair sums as iid_fq_partial does (summed over the row jobs
+ * in a fixed order).  Replaces atomic_grad_fq (cpu_atomics.py:81-102,
+ * gpu_atomics.py:192-280) + the /na of flat_multi_cpu_wrap.py:93-102. */
 int iid_grad_fq_partial(iid_handle *h, const double *pos_dev, void *G_dev,
                         double *S_dev, void *stream);
 
@@ -156,8 +194,20 @@ int iid_grad_pdf(iid_handle *h, const void *grad_fq_dev, int64_t rows,
  * float64 by precision), pdf_host[nr], forces_host[n*3] are float64 unless
  * noted. */
 int iid_fq_host(iid_handle *h, const double *pos_host, double *F_host);
+/* G_host in pinned, mapped memory (iid_host_alloc, iid_host_register) is
+ * written by the kernel directly (no device copy, no download); any other
+ * host pointer is filled through pipelined pinned staging. */
 int iid_grad_fq_host(iid_handle *h, const double *pos_host, void *G_host,
                      double *F_host);
+/* Pinned, mapped, portable host memory for output arrays; registration of an
+ * existing host mapping (e.g. POSIX shared memory that the ranks of a
+ * one-process-per-GPU job all write their gradient rows into -- the one host
+ * array gpu_wrap.py:159-194 assembles); the device alias to pass as G_dev. */
+int iid_host_alloc(int64_t bytes, void **ptr);
+int iid_host_free(void *ptr);
+int iid_host_register(void *ptr, int64_t bytes);
+int iid_host_unregister(void *ptr);
+int iid_host_device_pointer(void *host, void **dev);
 int iid_pdf_host(iid_handle *h, const double *pos_host, double *pdf_host,
                  double *F_host);
 /* One call per HMC leapfrog: energy = potential(G(r), target)*conv and
@@ -256,7 +306,10 @@ int iid_download_host(iid_handle *h, const void *dev, void *host, int64_t bytes)
  * "nw_max" (warps per block), "grad_nw_max" (warps per full-gradient block),
  * "grad_split" (0/1: F(Q) summed below the diagonal only, gradient-only bin
  * loop above it), "prod_unroll" (0/1: two pair set-ups per producer
- * iteration).  Defaults can also be set with IID_* environment variables
+ * iteration), "piece_div" (smallest piece of a split gradient row = row /
+ * piece_div), "zero_copy" (0/1: gradient rows straight into mapped host
+ * arrays), "acc_j" (FP32 full gradient: j atoms per float32 partial sum before
+ * it is parked and re-started, 0 = one accumulator over the whole row).  Defaults can also be set with IID_* environment variables
  * before iid_create. */
 int iid_set_option(iid_handle *h, const char *key, int64_t value);
 
@@ -267,6 +320,10 @@ int iid_launch_count(iid_handle *h, int64_t *count);
  * kernel launched by this handle, and its algorithmic pair*Q count */
 int iid_last_kernel_ms(iid_handle *h, float *ms, double *pairq);
 int iid_set_timing(iid_handle *h, int enabled);
+/* Measured issue rates (micro-benchmarks, ~30 ms) of the pipes that bound the
+ * pair sums, in lane-FMAs per second: out[0] scalar FFMA, out[1] packed FFMA2,
+ * out[2] DFMA -- the denominators of the per-mode roofline fractions. */
+int iid_measure_peaks(iid_handle *h, double *out);
 
 #ifdef __cplusplus
 }

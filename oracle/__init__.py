@@ -66,6 +66,9 @@ def lib():
             g = getattr(_lib, 'oracle_grad_pairsum_' + suf)
             g.restype = _c_int
             g.argtypes = f.argtypes
+            gw = getattr(_lib, 'oracle_grad_pairsum_ws_' + suf)
+            gw.restype = _c_int
+            gw.argtypes = f.argtypes + [ctypes.c_void_p]
             h = getattr(_lib, 'oracle_pair_internals_' + suf)
             h.restype = _c_int
             h.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _c_i64, _c_i64, cr,
@@ -125,16 +128,23 @@ def fq_pairsum(positions, scatter, qbin, precision='fp32', k_range=None,
 
 
 def grad_pairsum(positions, scatter, qbin, precision='fp32', k_range=None,
-                 chunk=0, nthreads=1):
+                 chunk=0, nthreads=1, out=None, workspace=None):
     """rtn[N,3,Q] scatter-summed pair gradients before normalisation
-    (cpu_atomics.py:81-102)."""
+    (cpu_atomics.py:81-102).  ``out`` / ``workspace`` ([nthreads, N, 3, Q]):
+    preallocated result and per-thread accumulators for repeated timed calls."""
     q, scat, dt, suf = _prep(positions, scatter, precision)
     n, nq = scat.shape
     k0, k1 = (0, n * (n - 1) // 2) if k_range is None else k_range
-    out = np.zeros((n, 3, nq), dt)
-    rc = getattr(lib(), 'oracle_grad_pairsum_' + suf)(
+    if out is None:
+        out = np.zeros((n, 3, nq), dt)
+    assert out.dtype == dt and out.shape == (n, 3, nq) and out.flags.c_contiguous
+    wptr = None
+    if workspace is not None:
+        assert workspace.dtype == dt and workspace.size >= max(1, nthreads) * n * 3 * nq
+        wptr = workspace.ctypes.data
+    rc = getattr(lib(), 'oracle_grad_pairsum_ws_' + suf)(
         q.ctypes.data, scat.ctypes.data, n, nq, dt(qbin), int(k0), int(k1),
-        int(chunk), int(nthreads), out.ctypes.data)
+        int(chunk), int(nthreads), out.ctypes.data, wptr)
     if rc:
         raise MemoryError('oracle grad')
     return out

@@ -235,10 +235,10 @@ int oracle_fq_pairsum_##SUF(const real *q, const real *scat, int64_t n,        \
  * pair order into ONE accumulator array, which is bit-identical to the        \
  * single-chunk flat-serial path.  nthreads > 1: one accumulator per thread,   \
  * summed at the end (the Pool variant, np.sum(ans, axis=0)). */               \
-int oracle_grad_pairsum_##SUF(const real *q, const real *scat, int64_t n,      \
+int oracle_grad_pairsum_ws_##SUF(const real *q, const real *scat, int64_t n,   \
                               int64_t Q, real qbin, int64_t k_begin,           \
                               int64_t k_end, int64_t chunk, int nthreads,      \
-                              real *rtn)                                       \
+                              real *rtn, real *ws)                             \
 {                                                                              \
     if (chunk <= 0) chunk = 1 << 12;                                           \
     int64_t nchunk = (k_end - k_begin + chunk - 1) / chunk;                    \
@@ -254,7 +254,9 @@ int oracle_grad_pairsum_##SUF(const real *q, const real *scat, int64_t n,      \
         return 0;                                                              \
     }                                                                          \
     int err = 0;                                                               \
-    real *part = (real *)calloc(sz * (size_t)nthreads, sizeof(real));          \
+    real *part = ws;                                                           \
+    if (part) memset(part, 0, sizeof(real) * sz * (size_t)nthreads);           \
+    else part = (real *)calloc(sz * (size_t)nthreads, sizeof(real));           \
     if (!part) return -1;                                                      \
     _Pragma("omp parallel num_threads(nthreads)")                              \
     {                                                                          \
@@ -271,8 +273,19 @@ int oracle_grad_pairsum_##SUF(const real *q, const real *scat, int64_t n,      \
     }                                                                          \
     for (int t = 0; t < nthreads; ++t)                                         \
         for (size_t e = 0; e < sz; ++e) rtn[e] += part[(size_t)t * sz + e];    \
-    free(part);                                                                \
+    if (!ws) free(part);                                                       \
     return err;                                                                \
+}                                                                              \
+/* `ws` (may be NULL) of the _ws variant: caller-provided nthreads * n*3*Q      \
+ * accumulators, so that repeated timed calls (bench.py --impl reference) do   \
+ * not re-allocate and page-fault 150 MB per thread on every call. */          \
+int oracle_grad_pairsum_##SUF(const real *q, const real *scat, int64_t n,      \
+                              int64_t Q, real qbin, int64_t k_begin,           \
+                              int64_t k_end, int64_t chunk, int nthreads,      \
+                              real *rtn)                                       \
+{                                                                              \
+    return oracle_grad_pairsum_ws_##SUF(q, scat, n, Q, qbin, k_begin, k_end,   \
+                                        chunk, nthreads, rtn, NULL);           \
 }                                                                              \
 /* Expose the per-pair intermediates for the kernel-internals tests            \
  * (reference tests/test_scatter_internals.py:39-94). */                       \

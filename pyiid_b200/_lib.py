@@ -29,6 +29,8 @@ SIGNATURES = {
     'iid_device_count': [_pint],
     'iid_device_info': [_int, _pint, _pint, _pint],
     'iid_create': [_int, _int, ctypes.POINTER(_vp)],
+    'iid_create_multi': [_int, _int, ctypes.POINTER(_vp)],
+    'iid_handle_devices': [_vp, _pint, _pint],
     'iid_destroy': [_vp],
     'iid_get_stream': [_vp, ctypes.POINTER(_vp)],
     'iid_synchronize': [_vp],
@@ -37,6 +39,8 @@ SIGNATURES = {
     'iid_set_transform': [_vp, _i64, _i64, _vp],
     'iid_plan_shard': [_i64, _vp, _i64, _int, _int, _int, _int, _pi64, _pi64,
                        _pi64, _pi64],
+    'iid_plan_rows': [_i64, _vp, _i64, _int, _int, _int, _int, _pi64, _pi64, _pi64,
+                      _vp, _i64, _vp, _i64, _vp, _i64],
     'iid_get_sizes': [_vp, _pi64, _pi64, _pi64, _pi64, _pi64],
     'iid_fq_partial': [_vp, _vp, _vp, _vp],
     'iid_fq_finish': [_vp, _vp, _vp, _vp],
@@ -53,6 +57,11 @@ SIGNATURES = {
     'iid_contract_host': [_vp, _vp, _int, _i64, _i64, _vp, _vp],
     'iid_fq_to_gr_host': [_vp, _vp, _vp],
     'iid_download_host': [_vp, _vp, _vp, _i64],
+    'iid_host_alloc': [_i64, ctypes.POINTER(_vp)],
+    'iid_host_free': [_vp],
+    'iid_host_register': [_vp, _i64],
+    'iid_host_unregister': [_vp],
+    'iid_host_device_pointer': [_vp, ctypes.POINTER(_vp)],
     'iid_spring_partial': [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp],
     'iid_spring_host': [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _vp, _vp, _vp],
     'iid_spring_voxel_host': [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _dbl, _i64, _i64, _i64, _vp],
@@ -67,6 +76,7 @@ SIGNATURES = {
     'iid_last_kernel_ms': [_vp, ctypes.POINTER(ctypes.c_float),
                            ctypes.POINTER(_dbl)],
     'iid_set_timing': [_vp, _int],
+    'iid_measure_peaks': [_vp, _vp],
 }
 
 _lib = None

@@ -20,6 +20,7 @@ import os
 import numpy as np
 
 from . import _lib
+from . import hostmem
 from ._lib import IID_FP32, IID_FP64, IID_POT_RW, IID_POT_CHI_SQ, check
 
 POTENTIALS = {'rw': IID_POT_RW, 'chi_sq': IID_POT_CHI_SQ}
@@ -97,8 +98,21 @@ def element_table(scatter_array, numbers=None):
             np.ascontiguousarray(inv.reshape(-1), dtype=np.int32))
 
 
+def visible_devices():
+    """Number of CUDA devices the library sees (0 without a GPU)."""
+    cnt = ctypes.c_int(0)
+    try:
+        if _lib.load().iid_device_count(ctypes.byref(cnt)) != 0:
+            return 0
+    except _lib.IIDError:
+        return 0
+    return cnt.value
+
+
 class Backend(object):
-    """One native handle on one GPU for one precision."""
+    """One native handle for one precision: on one GPU, or -- ``device='multi'``
+    -- over every GPU of the box from this one process (``iid_create_multi``,
+    the reference's ``gpu_wrap.py`` thread-per-GPU farm)."""
     _instances = {}
 
     @classmethod
@@ -115,6 +129,8 @@ class Backend(object):
 
     @classmethod
     def get(cls, precision='fp32', device=None, slot='fq'):
+        if device == 'multi' and _dist_state()[1] > 1:
+            device = None  # one process per GPU already: this rank's device
         if device is None:
             device = int(os.environ.get('LOCAL_RANK', '0'))
             try:
@@ -126,10 +142,11 @@ class Backend(object):
                 raise
         # one handle per Q grid in use ('fq' / 'pdf'), so that alternating
         # get_fq / get_pdf calls do not re-upload the structure
-        key = (precision, int(device), slot)
+        device = device if device == 'multi' else int(device)
+        key = (precision, device, slot)
         inst = cls._instances.get(key)
         if inst is None:
-            inst = cls(precision, int(device))
+            inst = cls(precision, device)
             cls._instances[key] = inst
         return inst
 
@@ -138,10 +155,14 @@ class Backend(object):
             raise ValueError("precision must be 'fp32' or 'fp64'")
         self.lib = _lib.load()
         self.precision = precision
-        self.device = device
+        self.multi = device == 'multi'
+        self.device = 0 if self.multi else device
         self.h = ctypes.c_void_p()
-        check(self.lib.iid_create(device, IID_FP32 if precision == 'fp32'
-                                  else IID_FP64, ctypes.byref(self.h)))
+        prec = IID_FP32 if precision == 'fp32' else IID_FP64
+        if self.multi:
+            check(self.lib.iid_create_multi(0, prec, ctypes.byref(self.h)))
+        else:
+            check(self.lib.iid_create(device, prec, ctypes.byref(self.h)))
         self.gdtype = np.float32 if precision == 'fp32' else np.float64
         self._skey = None
         self._tkey = None
@@ -155,11 +176,20 @@ class Backend(object):
         self.n = self.nq = self.nr = 0
         self.rank, self.world = 0, 1
         self._tensors = {}
+        self._shared = {}
         self._ext = None
         self.sync_shard()
 
     # -- sharding -----------------------------------------------------------
+    def devices(self):
+        """(devices behind the handle, devices the current structure uses)."""
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        check(self.lib.iid_handle_devices(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def sync_shard(self):
+        if self.multi:
+            return  # shards over its own devices
         rank, world = _dist_state()
         if (rank, world) != (self.rank, self.world):
             check(self.lib.iid_set_shard(self.h, rank, world))
@@ -266,42 +296,68 @@ class Backend(object):
 
     def grad_fq(self, positions, with_fq=False, root_only=False):
         """grad F(Q) [N,3,nq] in the kernel precision
-        (flat_multi_cpu_wrap.wrap_fq_grad :63-102).  Sharded over ranks the
-        partial gradients are all-reduced and every rank returns the full
-        array; ``root_only`` reduces to rank 0 instead (the other ranks return
-        None for the gradient), as the reference's single-process multi-GPU
-        path delivers one host array (gpu_wrap.py:287-314)."""
+        (flat_multi_cpu_wrap.wrap_fq_grad :63-102).
+
+        One process: the array is pinned, mapped host memory from a pool and
+        the kernel stores its rows straight into it (``hostmem.pinned_empty``;
+        pageable memory + staged download when the pool is exhausted).
+
+        One process per GPU (torch.distributed): every rank computes the rows
+        of its i-tiles.  Default: each rank returns its own full copy
+        (all-reduce of the disjoint rows + one download per rank).
+        ``root_only``: all ranks write their rows into ONE shared host array
+        (``hostmem.SharedOutput``) -- the single array the reference's
+        one-process multi-GPU path assembles (gpu_wrap.py:159-194, 287-314) --
+        without any gradient collective; every rank gets a view of it, valid
+        until the call after the next."""
         pos = self._pos(positions)
         self.sync_shard()
-        want_g = self.world == 1 or not root_only or self.rank == 0
-        g = np.empty((self.n, 3, self.nq), self.gdtype) if want_g else None
         f = np.empty(self.nq, np.float64)
         if self.world == 1:
+            g = hostmem.pinned_empty((self.n, 3, self.nq), self.gdtype)
+            if g is None:
+                g = np.empty((self.n, 3, self.nq), self.gdtype)
             check(self.lib.iid_grad_fq_host(self.h, pos.ctypes.data, g.ctypes.data,
                                             f.ctypes.data))
             return (g, f) if with_fq else g
         import torch
         import torch.distributed as dist
         tdt = torch.float32 if self.precision == 'fp32' else torch.float64
+        shared = self._shared_out() if root_only else None
         with torch.cuda.device(self.device), self._on_stream():
             p = self._upload(pos)
-            gt = self._t('G', (self.n, 3, self.nq), tdt)
             s = self._t('S', (self.nq,), torch.float64)
             ft = self._t('F', (self.nq,), torch.float64)
             st = self._stream()
-            check(self.lib.iid_grad_fq_partial(self.h, p.data_ptr(), gt.data_ptr(),
-                                               s.data_ptr(), st))
-            dist.all_reduce(s)
-            if root_only:
-                dist.reduce(gt, dst=0)
+            if shared is not None:
+                g, gptr = shared.next()
             else:
-                dist.all_reduce(gt)
+                gt = self._t('G', (self.n, 3, self.nq), tdt)
+                gt.zero_()  # rows of the other ranks' atoms are not written here
+                gptr = gt.data_ptr()
+            check(self.lib.iid_grad_fq_partial(self.h, p.data_ptr(), gptr, s.data_ptr(), st))
+            dist.all_reduce(s)
             check(self.lib.iid_fq_finish(self.h, s.data_ptr(), ft.data_ptr(), st))
-            if want_g:
+            if shared is None:
+                dist.all_reduce(gt)
+                g = np.empty((self.n, 3, self.nq), self.gdtype)
                 check(self.lib.iid_download_host(self.h, gt.data_ptr(), g.ctypes.data,
                                                  g.nbytes))
-            f = ft.cpu().numpy()
+            f = ft.cpu().numpy()  # synchronises this rank's stream: its rows are written
+            if shared is not None:
+                dist.barrier()    # ... and so are everybody else's
         return (g, f) if with_fq else g
+
+    def _shared_out(self):
+        """The shared output arrays of this structure (collective on first
+        use); None when they cannot be set up on every rank."""
+        import torch.distributed as dist
+        key = (self.n, self.nq)
+        so = self._shared.get(key)
+        if so is None:
+            so = hostmem.SharedOutput((self.n, 3, self.nq), self.gdtype, dist, self.device)
+            self._shared[key] = so
+        return so if so.ok else None
 
     def pdf(self, positions, with_fq=False):
         """G(r) [nr] float64 = get_pdf_at_qmin(F(Q)) (master_kernel.py:39-104)."""
@@ -577,6 +633,12 @@ class Backend(object):
         pq = ctypes.c_double(0)
         check(self.lib.iid_last_kernel_ms(self.h, ctypes.byref(ms), ctypes.byref(pq)))
         return ms.value, pq.value
+
+    def measure_peaks(self):
+        """Measured lane-FMA/s of the scalar FFMA, packed FFMA2 and DFMA pipes."""
+        out = np.zeros(3, np.float64)
+        check(self.lib.iid_measure_peaks(self.h, out.ctypes.data))
+        return {'ffma': out[0], 'ffma2': out[1], 'dfma': out[2]}
 
     def sizes(self):
         v = [ctypes.c_int64(0) for _ in range(5)]

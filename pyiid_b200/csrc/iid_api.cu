@@ -21,6 +21,7 @@
 #include "iid_sampler.cuh"
 #include "iid_small.cuh"
 #include "iid_spring.cuh"
+#include "iid_ubench.cuh"
 
 using namespace iid;
 
@@ -44,6 +45,9 @@ static int fail(int code, const std::string &msg)
 #define NEED(h)                                                               \
     do {                                                                      \
         if (!(h)) return fail(IID_E_BADARG, "null handle");                   \
+        if (!(h)->subs.empty())                                               \
+            return fail(IID_E_BADARG, std::string(__func__) +                 \
+                        ": not available on a multi-device handle");          \
         CU(cudaSetDevice((h)->device));                                       \
     } while (0)
 
@@ -79,6 +83,12 @@ struct iid_handle {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     int rank = 0, world = 1;
+    // multi-device handle (iid_create_multi): one complete sub-handle per GPU,
+    // sub d computing shard (d, active); this handle only coordinates
+    std::vector<iid_handle *> subs;
+    int active = 1;                    // sub-handles used for the current structure
+    std::vector<double> inv_na_host;   // [nq] 1/na for the host-side F = 2 S / na
+    std::vector<double> T_host;        // multi: the transform, for devices activated later
     // structure
     int64_t n = 0, np = 0, nq = 0, qp = 0, ntypes = 0;
     double qbin = 0.0;
@@ -87,8 +97,26 @@ struct iid_handle {
     int *orig = nullptr, *tile_type = nullptr;
     void *ftab = nullptr, *inv_na = nullptr;
     double *inv_na_d = nullptr;
-    WorkItem *items_tri = nullptr, *items_sq = nullptr;
-    int64_t n_items_tri = 0, n_items_sq = 0;
+    WorkItem *items_tri = nullptr;
+    int64_t n_items_tri = 0;
+    // full-gradient pass: row jobs of THIS shard (iid_debye.cuh), rebuilt when
+    // the structure or the shard changes
+    std::vector<int> run_begin, run_end, run_type_v;
+    RowJob *jobs = nullptr;
+    RowSeg *segs = nullptr;
+    RowFix *fixes = nullptr;
+    int64_t n_jobs = 0, n_segs = 0, n_fixes = 0, n_pieces = 0, n_jobs_total = 0;
+    double *Spart = nullptr;     // [n_jobs][qp]
+    size_t Spart_count = 0;
+    void *Gside = nullptr;       // [n_pieces][32][3][nq]
+    size_t Gside_bytes = 0;
+    int piece_div = 128;         // smallest piece of a split row = a slot's share / piece_div
+    bool zero_copy = true;       // gradient rows straight into pinned, mapped host arrays
+    int acc_j = 4096;            // FP32 row jobs park their partial sums every acc_j j atoms
+    float *Gscr = nullptr;       // [n_slots][3 * 32][block threads] parked partial sums
+    size_t Gscr_count = 0;
+    int *slot_busy = nullptr;
+    int n_slots = 0;
     // transform
     int64_t nr = 0;
     double *T = nullptr;
@@ -150,8 +178,21 @@ struct iid_handle {
     double last_pairq = 0.0;
 };
 
+static int upload_row_jobs(iid_handle *h);
+static int multi_destroy(iid_handle *h);
+static int multi_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
+                               int64_t n_types, const double *ftable, int64_t nq, double qbin);
+static int multi_set_transform(iid_handle *h, int64_t nr, int64_t nq, const double *T);
+static int multi_fq_host(iid_handle *h, const double *pos_host, double *F_host, double *pdf_host);
+static int multi_grad_fq_host(iid_handle *h, const double *pos_host, void *G_host,
+                              double *F_host);
+static int multi_energy_forces_host(iid_handle *h, const double *pos_host,
+                                    const double *target_host, int potential, double conv,
+                                    double *out_host, double *forces_host, double *pdf_host);
+#define MULTI(h) ((h) && !(h)->subs.empty())
+
 // ---------------------------------------------------------------------------
-extern "C" int iid_version(void) { return 100; }
+extern "C" int iid_version(void) { return 200; }
 extern "C" const char *iid_last_error(void) { return g_err.c_str(); }
 
 extern "C" int iid_device_count(int *count)
@@ -211,17 +252,22 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_GRAD_NW")) h->grad_nw_max = std::max(1, std::min(12, atoi(s)));
     if (const char *s = getenv("IID_QSPACE_WQ")) h->qspace_wq = atoi(s) != 0;
     if (const char *s = getenv("IID_SLAB")) h->slab_override = std::max(0, atoi(s));
+    if (const char *s = getenv("IID_PIECE_DIV")) h->piece_div = std::max(1, atoi(s));
+    if (const char *s = getenv("IID_ZERO_COPY")) h->zero_copy = atoi(s) != 0;
+    if (const char *s = getenv("IID_ACC_J")) h->acc_j = std::max(0, atoi(s));
     *out = h;
     return 0;
 }
 
 extern "C" int iid_destroy(iid_handle *h)
 {
+    if (MULTI(h)) return multi_destroy(h);
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
-                    h->inv_na, h->inv_na_d, h->items_tri, h->items_sq, h->T,
+                    h->inv_na, h->inv_na_d, h->items_tri, h->jobs, h->segs, h->fixes, h->Spart,
+                    h->Gside, h->Gscr, h->slot_busy, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
                     h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf,
                     h->lf_slab, h->lf_mass, h->lf_ctl, h->lf_mirror};
@@ -241,6 +287,7 @@ extern "C" int iid_destroy(iid_handle *h)
 
 extern "C" int iid_get_stream(iid_handle *h, void **stream)
 {
+    if (MULTI(h)) return iid_get_stream(h->subs[0], stream);
     if (!h || !stream) return fail(IID_E_BADARG, "null argument");
     *stream = (void *)h->stream;
     return 0;
@@ -248,6 +295,13 @@ extern "C" int iid_get_stream(iid_handle *h, void **stream)
 
 extern "C" int iid_synchronize(iid_handle *h)
 {
+    if (MULTI(h)) {
+        for (iid_handle *sh : h->subs) {
+            int rc = iid_synchronize(sh);
+            if (rc) return rc;
+        }
+        return 0;
+    }
     NEED(h);
     CU(cudaStreamSynchronize(h->stream));
     return 0;
@@ -261,12 +315,19 @@ static void drop_graph(iid_handle *h)
 
 extern "C" int iid_set_shard(iid_handle *h, int rank, int world)
 {
+    if (MULTI(h)) return fail(IID_E_BADARG, "a multi-device handle shards over its own devices");
     if (!h) return fail(IID_E_BADARG, "null handle");
     if (world < 1 || rank < 0 || rank >= world)
         return fail(IID_E_BADARG, "need 0 <= rank < world");
-    if (rank != h->rank || world != h->world) drop_graph(h);
+    const bool changed = rank != h->rank || world != h->world;
+    if (changed) drop_graph(h);
     h->rank = rank;
     h->world = world;
+    if (changed && h->np > 0) {
+        CU(cudaSetDevice(h->device));
+        CU(cudaStreamSynchronize(h->stream));
+        return upload_row_jobs(h);
+    }
     return 0;
 }
 
@@ -357,13 +418,178 @@ static int pick_small_slab(const std::vector<int> &run_begin, const std::vector<
     return best;
 }
 
+// ---------------------------------------------------------------------------
+// Row jobs of the full-gradient pass (iid_debye.cuh).  Rank `rank` of `world`
+// owns the i-tiles t with t % world == rank: every gradient row is computed by
+// exactly one rank, so there is no gradient collective and every rank writes
+// (or downloads) only its own rows.  A row = the i-tile against ALL j: per
+// element run the range below the tile (F(Q) + gradient), the tile itself
+// (F(Q) weight 1/2) and the range above it (gradient only).  Most rows are one
+// job each (plain stores into G); the rows kept back for load balance are cut
+// into pieces of decreasing size (guided self-scheduling: piece = remaining
+// tail work / slots, not below row / piece_div) that are dispatched after the
+// whole rows and meet in rows_fixup_kernel.
+struct RowPlan {
+    std::vector<RowJob> jobs;
+    std::vector<RowSeg> segs;
+    std::vector<RowFix> fixes;
+    int64_t n_pieces = 0, pair_slots = 0, n_jobs_total = 0;
+};
+
+static double seg_cost(const RowSeg &g)
+{
+    // packed instructions per bin step: 8.25 with F(Q), 6.7 gradient only; one
+    // 16-j tile of pipeline restart per segment
+    return (double)(g.jend - g.jbegin + 16) * ((g.info & ITEM_NOF) ? 6.7 : 8.25);
+}
+
+static void row_segments(const std::vector<int> &run_begin, const std::vector<int> &run_end,
+                         const std::vector<int> &run_type, int it, std::vector<RowSeg> &out)
+{
+    const int lo = it * TILE_I, hi = lo + TILE_I;
+    out.clear();
+    for (size_t b = 0; b < run_begin.size(); ++b) {
+        const int rb = run_begin[b], re = run_end[b], ty = run_type[b];
+        const size_t first = out.size();
+        if (re <= lo) out.push_back({rb, re, ty, 0});
+        else if (rb >= hi) out.push_back({rb, re, ty | ITEM_NOF, 0});
+        else {
+            if (lo > rb) out.push_back({rb, lo, ty, 0});
+            out.push_back({lo, hi, ty | ITEM_DIAG, 0});
+            if (re > hi) out.push_back({hi, re, ty | ITEM_NOF, 0});
+        }
+        if (out.size() > first) out.back().info |= SEG_FLUSH;
+    }
+}
+
+static void build_row_jobs(const std::vector<int> &run_begin, const std::vector<int> &run_end,
+                           const std::vector<int> &run_type, int np, int rank, int world,
+                           int slots, int piece_div, RowPlan &P)
+{
+    P = RowPlan();
+    const int ntile = np / TILE_I;
+    slots = std::max(1, slots);
+    piece_div = std::max(1, piece_div);
+    struct Row { int it; double cost; std::vector<RowSeg> segs; };
+    std::vector<Row> rows;
+    for (int it = rank; it < ntile; it += world) {
+        Row r;
+        r.it = it;
+        row_segments(run_begin, run_end, run_type, it, r.segs);
+        r.cost = 0.0;
+        for (const RowSeg &g : r.segs) r.cost += seg_cost(g);
+        rows.push_back(std::move(r));
+    }
+    std::stable_sort(rows.begin(), rows.end(),
+                     [](const Row &a, const Row &b) { return a.cost > b.cost; });
+    const size_t nrows = rows.size();
+    // whole rows: all but the last 0.5 .. 1.5 rows per slot
+    size_t nwhole = 0;
+    if (nrows >= (size_t)slots) {
+        const double waves = (double)nrows / slots;
+        nwhole = (size_t)std::max(0.0, std::floor(waves - 0.5)) * slots;
+    }
+    auto emit = [&](int it, const std::vector<RowSeg> &sg, int dest) {
+        RowJob j;
+        j.itile = it;
+        j.seg_begin = (int)P.segs.size();
+        for (const RowSeg &g : sg) {
+            P.segs.push_back(g);
+            P.pair_slots += (int64_t)(g.jend - g.jbegin) * TILE_I;
+        }
+        j.seg_end = (int)P.segs.size();
+        j.dest = dest;
+        P.jobs.push_back(j);
+    };
+    for (size_t k = 0; k < nwhole; ++k) emit(rows[k].it, rows[k].segs, -1);
+    double remaining = 0.0, total = 0.0;
+    for (size_t k = 0; k < nrows; ++k) total += rows[k].cost;
+    for (size_t k = nwhole; k < nrows; ++k) remaining += rows[k].cost;
+    // smallest piece: the schedule ends within about one piece of the ideal, so
+    // 1/piece_div of a slot's share (not below 64 j)
+    const double min_piece = std::max(64 * 8.25, total / slots / piece_div);
+    for (size_t k = nwhole; k < nrows; ++k) {
+        const Row &r = rows[k];
+        // cut the row's segment list into pieces
+        std::vector<std::vector<RowSeg>> pieces;
+        std::vector<RowSeg> cur;
+        double cur_cost = 0.0, row_left = r.cost;  // row_left: not yet in a closed piece
+        double target = std::max(min_piece, remaining / slots);
+        auto close_piece = [&]() {
+            pieces.push_back(cur);
+            row_left -= cur_cost;
+            remaining = std::max(0.0, remaining - cur_cost);
+            cur.clear();
+            cur_cost = 0.0;
+            target = std::max(min_piece, remaining / slots);
+        };
+        for (size_t si = 0; si < r.segs.size(); ++si) {
+            RowSeg g = r.segs[si];
+            for (;;) {
+                const double c = seg_cost(g);
+                if (row_left <= 1.25 * target || cur_cost + c <= 1.1 * target) {
+                    cur.push_back(g);  // the rest of the row is the last piece / the segment fits
+                    cur_cost += c;
+                    break;
+                }
+                if (cur_cost >= 0.9 * target) {
+                    close_piece();
+                    continue;
+                }
+                // cut inside the segment at a multiple of 32 j
+                const double per_j = (g.info & ITEM_NOF) ? 6.7 : 8.25;
+                int take = (int)((target - cur_cost) / per_j) / TILE_I * TILE_I;
+                take = std::max(TILE_I, take);
+                if (take >= g.jend - g.jbegin) {
+                    cur.push_back(g);
+                    cur_cost += c;
+                    break;
+                }
+                RowSeg head = g;
+                head.jend = g.jbegin + take;
+                head.info &= ~SEG_FLUSH;
+                cur.push_back(head);
+                cur_cost += seg_cost(head);
+                g.jbegin = head.jend;
+                close_piece();
+            }
+        }
+        if (!cur.empty()) close_piece();
+        if (pieces.size() == 1) {
+            emit(r.it, pieces[0], -1);
+        } else {
+            RowFix f;
+            f.itile = r.it;
+            f.d0 = (int)P.n_pieces;
+            for (auto &pc : pieces) emit(r.it, pc, (int)P.n_pieces++);
+            f.d1 = (int)P.n_pieces;
+            f.pad = 0;
+            P.fixes.push_back(f);
+        }
+    }
+    // longest first: the block scheduler hands out the jobs in this order
+    auto job_cost = [&](const RowJob &j) {
+        double c = 0.0;
+        for (int k = j.seg_begin; k < j.seg_end; ++k) c += seg_cost(P.segs[k]);
+        return c;
+    };
+    std::vector<std::pair<double, RowJob>> order;
+    for (const RowJob &j : P.jobs) order.push_back({job_cost(j), j});
+    std::stable_sort(order.begin(), order.end(),
+                     [](const std::pair<double, RowJob> &a, const std::pair<double, RowJob> &b) {
+                         return a.first > b.first;
+                     });
+    for (size_t k = 0; k < order.size(); ++k) P.jobs[k] = order[k].second;
+    P.n_jobs_total = (int64_t)P.jobs.size();
+}
+
 // Host-side plan of one structure: element-sorted, per-element padded atom
 // order and the two work-item lists.  No device needed.
 struct Layout {
     int64_t np = 0;
     std::vector<int64_t> count;
-    std::vector<int> run_type, orig, tile_type;
-    std::vector<WorkItem> tri, sq;
+    std::vector<int> run_type, run_begin, run_end, orig, tile_type;
+    std::vector<WorkItem> tri;
 };
 
 static int build_layout(int64_t n, const int32_t *type_index, int64_t n_types, int sm_count,
@@ -378,7 +604,9 @@ static int build_layout(int64_t n, const int32_t *type_index, int64_t n_types, i
             return fail(IID_E_BADARG, "type_index out of range");
         ++L.count[type_index[i]];
     }
-    std::vector<int> run_begin, run_end;
+    std::vector<int> &run_begin = L.run_begin, &run_end = L.run_end;
+    run_begin.clear();
+    run_end.clear();
     int64_t np = 0;
     std::vector<int64_t> start(n_types, 0);
     L.run_type.clear();
@@ -411,7 +639,6 @@ static int build_layout(int64_t n, const int32_t *type_index, int64_t n_types, i
         if (slab_override > 0) s = (slab_override + TILE_I - 1) / TILE_I * TILE_I;
         return (int)s;
     };
-    build_items(run_begin, run_end, (int)np, pick(ntile * np), false, L.sq);
     if (ntile <= 64 && slab_override <= 0) {
         const int cap = pick_small_slab(run_begin, run_end, (int)np, std::max(1, sm_count));
         build_items(run_begin, run_end, (int)np, cap, true, L.tri, 8);
@@ -419,11 +646,10 @@ static int build_layout(int64_t n, const int32_t *type_index, int64_t n_types, i
         build_items(run_begin, run_end, (int)np, pick(ntile * np / 2), true, L.tri);
     }
     // the item info field stores the run's ELEMENT type
-    for (auto *v : {&L.tri, &L.sq})
-        for (auto &w : *v) {
-            const int b = w.info & 0xffff;
-            w.info = (w.info & (ITEM_DIAG | ITEM_NOF)) | L.run_type[b];
-        }
+    for (auto &w : L.tri) {
+        const int b = w.info & 0xffff;
+        w.info = (w.info & (ITEM_DIAG | ITEM_NOF)) | L.run_type[b];
+    }
     return 0;
 }
 
@@ -438,16 +664,79 @@ extern "C" int iid_plan_shard(int64_t n, const int32_t *type_index, int64_t n_ty
     Layout L;
     int rc = build_layout(n, type_index, n_types, sm_count, 0, L);
     if (rc) return rc;
-    const std::vector<WorkItem> &items = triangle ? L.tri : L.sq;
-    int64_t mine = 0, slots = 0;
-    for (size_t k = (size_t)rank; k < items.size(); k += (size_t)world) {
-        ++mine;
-        slots += (int64_t)(items[k].jend - items[k].jbegin) * TILE_I;
+    int64_t mine = 0, slots = 0, total = 0;
+    if (triangle) {
+        const std::vector<WorkItem> &items = L.tri;
+        for (size_t k = (size_t)rank; k < items.size(); k += (size_t)world) {
+            ++mine;
+            slots += (int64_t)(items[k].jend - items[k].jbegin) * TILE_I;
+        }
+        total = (int64_t)items.size();
+    } else {
+        // full gradient: row jobs, i-tiles dealt cyclically to the ranks
+        RowPlan P;
+        for (int r = 0; r < world; ++r) {
+            build_row_jobs(L.run_begin, L.run_end, L.run_type, (int)L.np, r, world, sm_count, 128, P);
+            total += (int64_t)P.jobs.size();
+            if (r == rank) {
+                mine = (int64_t)P.jobs.size();
+                slots = P.pair_slots;
+            }
+        }
     }
-    if (n_items_total) *n_items_total = (int64_t)items.size();
+    if (n_items_total) *n_items_total = total;
     if (n_items_mine) *n_items_mine = mine;
     if (pair_slots_mine) *pair_slots_mine = slots;
     if (padded_atoms) *padded_atoms = L.np;
+    return 0;
+}
+
+// Host-only: the row jobs rank `rank` of `world` would run (4 int32 per job:
+// itile, seg_begin, seg_end, dest; per segment: jbegin, jend, info, 0; per
+// split row: itile, first slot, one past the last slot, 0).  Arrays may be
+// NULL to query the counts only.
+extern "C" int iid_plan_rows(int64_t n, const int32_t *type_index, int64_t n_types, int sm_count,
+                             int rank, int world, int piece_div, int64_t *n_jobs,
+                             int64_t *n_segs, int64_t *n_fixes, int32_t *jobs, int64_t jobs_cap,
+                             int32_t *segs, int64_t segs_cap, int32_t *fixes, int64_t fixes_cap)
+{
+    if (world < 1 || rank < 0 || rank >= world) return fail(IID_E_BADARG, "need 0 <= rank < world");
+    Layout L;
+    int rc = build_layout(n, type_index, n_types, sm_count, 0, L);
+    if (rc) return rc;
+    RowPlan P;
+    build_row_jobs(L.run_begin, L.run_end, L.run_type, (int)L.np, rank, world, sm_count,
+                   piece_div > 0 ? piece_div : 128, P);
+    if (n_jobs) *n_jobs = (int64_t)P.jobs.size();
+    if (n_segs) *n_segs = (int64_t)P.segs.size();
+    if (n_fixes) *n_fixes = (int64_t)P.fixes.size();
+    static_assert(sizeof(RowJob) == 16 && sizeof(RowSeg) == 16 && sizeof(RowFix) == 16, "layout");
+    if (jobs) memcpy(jobs, P.jobs.data(), std::min<size_t>(jobs_cap, P.jobs.size()) * 16);
+    if (segs) memcpy(segs, P.segs.data(), std::min<size_t>(segs_cap, P.segs.size()) * 16);
+    if (fixes) memcpy(fixes, P.fixes.data(), std::min<size_t>(fixes_cap, P.fixes.size()) * 16);
+    return 0;
+}
+
+// (Re)build this shard's row jobs of the full-gradient pass and upload them.
+static int upload_row_jobs(iid_handle *h)
+{
+    if (h->np == 0) return 0;
+    RowPlan P;
+    build_row_jobs(h->run_begin, h->run_end, h->run_type_v, (int)h->np, h->rank, h->world,
+                   h->sm_count, h->piece_div, P);
+    int rc;
+    if ((rc = dev_alloc(&h->jobs, P.jobs.size())) || (rc = dev_alloc(&h->segs, P.segs.size())) ||
+        (rc = dev_alloc(&h->fixes, P.fixes.size())))
+        return rc;
+    CU(cudaMemcpy(h->jobs, P.jobs.data(), P.jobs.size() * sizeof(RowJob), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->segs, P.segs.data(), P.segs.size() * sizeof(RowSeg), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->fixes, P.fixes.data(), P.fixes.size() * sizeof(RowFix),
+                  cudaMemcpyHostToDevice));
+    h->n_jobs = (int64_t)P.jobs.size();
+    h->n_segs = (int64_t)P.segs.size();
+    h->n_fixes = (int64_t)P.fixes.size();
+    h->n_pieces = P.n_pieces;
+    CU(cudaStreamSynchronize(0));
     return 0;
 }
 
@@ -455,6 +744,7 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
                                  int64_t n_types, const double *ftable, int64_t nq,
                                  double qbin)
 {
+    if (MULTI(h)) return multi_set_structure(h, n, type_index, n_types, ftable, nq, qbin);
     NEED(h);
     if (n < 1 || n_types < 1 || nq < 1 || !type_index || !ftable)
         return fail(IID_E_BADARG, "bad structure arguments");
@@ -469,7 +759,7 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
     const int64_t np = L.np;
     const std::vector<int64_t> &count = L.count;
     const std::vector<int> &orig = L.orig, &tile_type = L.tile_type;
-    const std::vector<WorkItem> &tri = L.tri, &sq = L.sq;
+    const std::vector<WorkItem> &tri = L.tri;
     const int64_t qp = (nq + 31) / 32 * 32;
     // normaliser, closed form of N * mean_pairs(f_i f_j):
     //   na = ((sum_i f_i)^2 - sum_i f_i^2) / (N - 1)
@@ -486,23 +776,26 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
     }
     if (nq != h->nq) h->nr = 0;  // a transform built for another Q grid is void
     h->n = n; h->np = np; h->nq = nq; h->qp = qp; h->ntypes = n_types; h->qbin = qbin;
+    h->inv_na_host.assign(inv_na.begin(), inv_na.begin() + nq);
     int rc;
     if ((rc = dev_alloc(&h->x, np)) || (rc = dev_alloc(&h->y, np)) ||
         (rc = dev_alloc(&h->z, np)) || (rc = dev_alloc(&h->valid, np)) ||
         (rc = dev_alloc(&h->orig, np)) || (rc = dev_alloc(&h->tile_type, np / TILE_I)) ||
         (rc = dev_alloc(&h->inv_na_d, qp)) || (rc = dev_alloc(&h->items_tri, tri.size())) ||
-        (rc = dev_alloc(&h->items_sq, sq.size())) || (rc = dev_alloc(&h->pos, 3 * n)) ||
+        (rc = dev_alloc(&h->pos, 3 * n)) ||
         (rc = dev_alloc(&h->S, qp)) || (rc = dev_alloc(&h->F, qp)) ||
         (rc = dev_alloc(&h->wq, qp)) || (rc = dev_alloc(&h->force, 3 * n)))
         return rc;
     h->n_items_tri = (int64_t)tri.size();
-    h->n_items_sq = (int64_t)sq.size();
+    h->run_begin = L.run_begin;
+    h->run_end = L.run_end;
+    h->run_type_v = L.run_type;
     CU(cudaMemcpy(h->orig, orig.data(), np * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->tile_type, tile_type.data(), tile_type.size() * sizeof(int),
                   cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->inv_na_d, inv_na.data(), qp * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->items_tri, tri.data(), tri.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->items_sq, sq.data(), sq.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    if ((rc = upload_row_jobs(h))) return rc;
     CU(cudaMemset(h->S, 0, qp * sizeof(double)));
     CU(cudaMemset(h->F, 0, qp * sizeof(double)));
     CU(cudaMemset(h->wq, 0, qp * sizeof(double)));
@@ -539,6 +832,7 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
 
 extern "C" int iid_set_transform(iid_handle *h, int64_t nr, int64_t nq, const double *T)
 {
+    if (MULTI(h)) return multi_set_transform(h, nr, nq, T);
     NEED(h);
     if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
     if (nq != h->nq) return fail(IID_E_BADARG, "transform nq differs from structure nq");
@@ -580,12 +874,23 @@ extern "C" int iid_set_transform(iid_handle *h, int64_t nr, int64_t nq, const do
 extern "C" int iid_get_sizes(iid_handle *h, int64_t *n, int64_t *nq, int64_t *nr,
                              int64_t *n_items_fq, int64_t *n_items_grad)
 {
+    if (MULTI(h)) {
+        int64_t fq = 0, gr = 0, a = 0, b = 0;
+        for (int d = 0; d < h->active; ++d) {
+            iid_get_sizes(h->subs[d], n, nq, nr, &a, &b);
+            fq = a;  // the triangle list is shared, the row jobs are per device
+            gr += b;
+        }
+        if (n_items_fq) *n_items_fq = fq;
+        if (n_items_grad) *n_items_grad = gr;
+        return 0;
+    }
     if (!h) return fail(IID_E_BADARG, "null handle");
     if (n) *n = h->n;
     if (nq) *nq = h->nq;
     if (nr) *nr = h->nr;
     if (n_items_fq) *n_items_fq = h->n_items_tri;
-    if (n_items_grad) *n_items_grad = h->n_items_sq;
+    if (n_items_grad) *n_items_grad = h->n_jobs;
     return 0;
 }
 
@@ -698,9 +1003,8 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     DebyeParams p;
     p.x = h->x; p.y = h->y; p.z = h->z; p.valid = h->valid; p.orig = h->orig;
     p.tile_type = h->tile_type;
-    const bool square = mode == MODE_GRAD;
-    p.items = square ? h->items_sq : h->items_tri;
-    const int64_t nitems = square ? h->n_items_sq : h->n_items_tri;
+    const bool rows = mode == MODE_GRAD;
+    p.items = h->items_tri;
     p.item_begin = h->rank;
     p.item_stride = h->world;
     p.ftab = h->ftab; p.inv_na = h->inv_na; p.wq = wq;
@@ -709,22 +1013,92 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     p.qbin_turns = h->qbin / 6.283185307179586476925286766559;
     p.G = G; p.S = S; p.force = force;
     p.grad_split = h->grad_split ? 1 : 0;
-    const int64_t mine = nitems > h->rank ? (nitems - h->rank + h->world - 1) / h->world : 0;
+    p.jobs = h->jobs; p.segs = h->segs; p.Gside = nullptr;
+    int64_t mine;
+    if (rows) {
+        // row jobs of this shard; S = per-job partial sums; the pieces of the
+        // split rows go through the side buffer
+        mine = h->n_jobs;
+        const size_t esz = h->precision == IID_FP32 ? sizeof(float) : sizeof(double);
+        const size_t side = (size_t)h->n_pieces * 32 * 3 * (size_t)h->nq * esz;
+        if (side > h->Gside_bytes) {
+            if (h->Gside) cudaFree(h->Gside);
+            h->Gside = nullptr;
+            h->Gside_bytes = 0;
+            CU(cudaMalloc(&h->Gside, side));
+            h->Gside_bytes = side;
+        }
+        p.Gside = h->Gside;
+        p.Gscr = nullptr; p.slot_busy = nullptr; p.n_slots = 0; p.acc_j = 0;
+        if (h->precision == IID_FP32 && h->acc_j > 0 && h->np > h->acc_j) {
+            // scratch slots for the parked float32 partial sums (iid_debye2.cuh)
+            const int nchunk = (int)((h->nq + C32 - 1) / C32);
+            const int nwmax = std::min(h->nw_max, h->grad_nw_max);
+            const int gy = (nchunk + nwmax - 1) / nwmax;
+            const int nw = (nchunk + gy - 1) / gy;
+            const int n_slots = h->sm_count * 4;
+            const size_t cnt = (size_t)n_slots * 3 * C32 * 32 * nw;
+            if (cnt > h->Gscr_count || n_slots != h->n_slots) {
+                int rc = dev_alloc(&h->Gscr, cnt);
+                if (!rc) rc = dev_alloc(&h->slot_busy, n_slots);
+                h->Gscr_count = rc ? 0 : cnt;
+                h->n_slots = rc ? 0 : n_slots;
+                if (rc) return rc;
+                CU(cudaMemsetAsync(h->slot_busy, 0, n_slots * sizeof(int), st));
+            }
+            p.Gscr = h->Gscr; p.slot_busy = h->slot_busy; p.n_slots = h->n_slots;
+            p.acc_j = h->acc_j;
+        }
+        if (S) {
+            const size_t cnt = (size_t)std::max<int64_t>(1, h->n_jobs) * h->qp;
+            if (cnt > h->Spart_count) {
+                int rc = dev_alloc(&h->Spart, cnt);
+                h->Spart_count = rc ? 0 : cnt;
+                if (rc) return rc;
+            }
+            p.S = h->Spart;
+        }
+    } else {
+        const int64_t nitems = h->n_items_tri;
+        mine = nitems > h->rank ? (nitems - h->rank + h->world - 1) / h->world : 0;
+    }
     h->last_pairq = 0.5 * (double)h->n * (double)(h->n - 1) * (double)h->nq / h->world;
-    if (mine == 0) return 0;
-    if (h->precision == IID_FP32 && h->cheb) {
-        if (mode == MODE_FQ) return launch_debye2_t<C32, MODE_FQ, true>(h, p, mine, st);
-        if (mode == MODE_GRAD) return launch_debye2_t<C32, MODE_GRAD, true>(h, p, mine, st);
-        return launch_debye2_t<C32, MODE_FORCE, true>(h, p, mine, st);
+    int rc = 0;
+    if (mine > 0) {
+        if (h->precision == IID_FP32 && h->cheb) {
+            if (mode == MODE_FQ) rc = launch_debye2_t<C32, MODE_FQ, true>(h, p, mine, st);
+            else if (mode == MODE_GRAD) rc = launch_debye2_t<C32, MODE_GRAD, true>(h, p, mine, st);
+            else rc = launch_debye2_t<C32, MODE_FORCE, true>(h, p, mine, st);
+        } else if (h->precision == IID_FP32) {  // IID_CHEB=0: rotation recurrence everywhere
+            if (mode == MODE_FQ) rc = launch_debye2_t<C32, MODE_FQ, false>(h, p, mine, st);
+            else if (mode == MODE_GRAD) rc = launch_debye2_t<C32, MODE_GRAD, false>(h, p, mine, st);
+            else rc = launch_debye2_t<C32, MODE_FORCE, false>(h, p, mine, st);
+        } else {
+            if (mode == MODE_FQ) rc = launch_debye64_t<C64, MODE_FQ>(h, p, mine, st);
+            else if (mode == MODE_GRAD) rc = launch_debye64_t<C64, MODE_GRAD>(h, p, mine, st);
+            else rc = launch_debye64_t<C64, MODE_FORCE>(h, p, mine, st);
+        }
+        if (rc) return rc;
     }
-    if (h->precision == IID_FP32) {  // IID_CHEB=0: rotation recurrence everywhere
-        if (mode == MODE_FQ) return launch_debye2_t<C32, MODE_FQ, false>(h, p, mine, st);
-        if (mode == MODE_GRAD) return launch_debye2_t<C32, MODE_GRAD, false>(h, p, mine, st);
-        return launch_debye2_t<C32, MODE_FORCE, false>(h, p, mine, st);
+    if (rows) {
+        if (h->n_fixes > 0) {
+            if (h->precision == IID_FP32)
+                rows_fixup_kernel<float><<<(unsigned)h->n_fixes, 256, 0, st>>>(
+                    h->fixes, h->orig, (const float *)h->Gside, (int)h->nq, (float *)G);
+            else
+                rows_fixup_kernel<double><<<(unsigned)h->n_fixes, 256, 0, st>>>(
+                    h->fixes, h->orig, (const double *)h->Gside, (int)h->nq, (double *)G);
+            ++h->launches;
+            CU(cudaGetLastError());
+        }
+        if (S) {
+            reduce_spart_kernel<<<(unsigned)((h->nq + 31) / 32), 1024, 0, st>>>(
+                h->Spart, (int)h->n_jobs, (int)h->nq, (int)h->qp, S);
+            ++h->launches;
+            CU(cudaGetLastError());
+        }
     }
-    if (mode == MODE_FQ) return launch_debye64_t<C64, MODE_FQ>(h, p, mine, st);
-    if (mode == MODE_GRAD) return launch_debye64_t<C64, MODE_GRAD>(h, p, mine, st);
-    return launch_debye64_t<C64, MODE_FORCE>(h, p, mine, st);
+    return 0;
 }
 
 // Force pass.  FP32 mode with a handful of element types: sum over the Q bins
@@ -807,9 +1181,8 @@ extern "C" int iid_grad_fq_partial(iid_handle *h, const double *pos_dev, void *G
     cudaStream_t st = pick(h, stream);
     int rc = stage_positions(h, pos_dev, st);
     if (rc) return rc;
-    const size_t esz = h->precision == IID_FP32 ? sizeof(float) : sizeof(double);
-    CU(cudaMemsetAsync(G_dev, 0, (size_t)h->n * 3 * h->nq * esz, st));
-    if (S_dev) CU(cudaMemsetAsync(S_dev, 0, h->nq * sizeof(double), st));
+    // every row of this shard's i-tiles is written exactly once (plain stores):
+    // no zero-fill; rows of other shards are not touched
     return launch_debye(h, MODE_GRAD, G_dev, S_dev, nullptr, nullptr, st);
 }
 
@@ -867,6 +1240,7 @@ extern "C" int iid_potential(iid_handle *h, const double *G_dev, const double *t
 extern "C" int iid_grad_pdf(iid_handle *h, const void *grad_fq_dev, int64_t rows,
                             double *grad_pdf_dev, void *stream)
 {
+    if (MULTI(h)) return iid_grad_pdf(h->subs[0], grad_fq_dev, rows, grad_pdf_dev, stream);
     NEED(h);
     if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
     if (!grad_fq_dev || !grad_pdf_dev || rows < 0) return fail(IID_E_BADARG, "bad argument");
@@ -949,6 +1323,7 @@ static int download_pipelined(iid_handle *h, const void *dev, void *host, size_t
 // handle's stream).
 extern "C" int iid_download_host(iid_handle *h, const void *dev, void *host, int64_t bytes)
 {
+    if (MULTI(h)) return iid_download_host(h->subs[0], dev, host, bytes);
     NEED(h);
     if (!dev || !host || bytes < 0) return fail(IID_E_BADARG, "bad argument");
     if (bytes == 0) return 0;
@@ -968,6 +1343,7 @@ static int upload_positions(iid_handle *h, const double *pos_host)
 
 extern "C" int iid_fq_host(iid_handle *h, const double *pos_host, double *F_host)
 {
+    if (MULTI(h)) return multi_fq_host(h, pos_host, F_host, nullptr);
     NEED(h);
     if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
     if (!pos_host || !F_host) return fail(IID_E_BADARG, "null pointer");
@@ -982,15 +1358,34 @@ extern "C" int iid_fq_host(iid_handle *h, const double *pos_host, double *F_host
     return 0;
 }
 
+// Device alias of a host pointer the GPU can write directly (pinned + mapped:
+// iid_host_alloc / iid_host_register), else nullptr.
+static void *mapped_alias(const void *host)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 extern "C" int iid_grad_fq_host(iid_handle *h, const double *pos_host, void *G_host,
                                 double *F_host)
 {
+    if (MULTI(h)) return multi_grad_fq_host(h, pos_host, G_host, F_host);
     NEED(h);
     if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
     if (!pos_host || !G_host) return fail(IID_E_BADARG, "null pointer");
     const size_t esz = h->precision == IID_FP32 ? sizeof(float) : sizeof(double);
     const size_t bytes = (size_t)h->n * 3 * h->nq * esz;
-    if (bytes > h->Gfull_bytes) {
+    // Pinned, mapped host memory: the kernel stores every gradient row once,
+    // in coalesced 128-byte pieces, straight into the caller's array (0.8 GB/s
+    // of posted PCIe writes spread over the whole pass) -- no device copy of
+    // the gradient, no download.  Pageable memory: device array + pipelined
+    // download through pinned staging.
+    void *alias = h->zero_copy ? mapped_alias(G_host) : nullptr;
+    if (!alias && bytes > h->Gfull_bytes) {
         if (h->Gfull) cudaFree(h->Gfull);
         h->Gfull = nullptr;
         h->Gfull_bytes = 0;
@@ -999,19 +1394,62 @@ extern "C" int iid_grad_fq_host(iid_handle *h, const double *pos_host, void *G_h
     }
     int rc;
     if ((rc = upload_positions(h, pos_host))) return rc;
-    if ((rc = iid_grad_fq_partial(h, h->pos, h->Gfull, h->S, nullptr))) return rc;
+    if ((rc = iid_grad_fq_partial(h, h->pos, alias ? alias : h->Gfull, h->S, nullptr))) return rc;
     if ((rc = iid_fq_finish(h, h->S, h->F, nullptr))) return rc;
     double *pf = h->pin + 6 * h->n;
     CU(cudaMemcpyAsync(pf, h->F, h->nq * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if ((rc = download_pipelined(h, h->Gfull, G_host, bytes))) return rc;
+    if (!alias && (rc = download_pipelined(h, h->Gfull, G_host, bytes))) return rc;
     CU(cudaStreamSynchronize(h->stream));
     if (F_host) memcpy(F_host, pf, h->nq * sizeof(double));
+    return 0;
+}
+
+// Pinned, mapped, portable host memory: an output array allocated here (or a
+// host mapping registered here, e.g. POSIX shared memory that several ranks
+// write their rows into) is written directly by the gradient kernel.
+extern "C" int iid_host_alloc(int64_t bytes, void **ptr)
+{
+    if (!ptr || bytes < 1) return fail(IID_E_BADARG, "bad argument");
+    *ptr = nullptr;
+    CU(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    return 0;
+}
+
+extern "C" int iid_host_free(void *ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return 0;
+}
+
+extern "C" int iid_host_register(void *ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 1) return fail(IID_E_BADARG, "bad argument");
+    CU(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return 0;
+}
+
+extern "C" int iid_host_unregister(void *ptr)
+{
+    if (ptr) CU(cudaHostUnregister(ptr));
+    return 0;
+}
+
+// device pointer under which the current device writes to a mapped host array
+extern "C" int iid_host_device_pointer(void *host, void **dev)
+{
+    if (!host || !dev) return fail(IID_E_BADARG, "null pointer");
+    *dev = mapped_alias(host);
+    if (!*dev) return fail(IID_E_BADARG, "not pinned, mapped host memory");
     return 0;
 }
 
 extern "C" int iid_pdf_host(iid_handle *h, const double *pos_host, double *pdf_host,
                             double *F_host)
 {
+    if (MULTI(h)) {
+        if (!pdf_host) return fail(IID_E_BADARG, "null pointer");
+        return multi_fq_host(h, pos_host, F_host, pdf_host);
+    }
     NEED(h);
     if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
     if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
@@ -1105,6 +1543,18 @@ extern "C" int iid_spring_host(iid_handle *h, const double *pos_host, int64_t n,
                                double k, double rt, const double *com, double *energy_host,
                                double *forces_host, double *atomwise_host)
 {
+    if (MULTI(h)) {
+        // O(N^2) with a tiny constant: one device, all rows
+        iid_handle *s0 = h->subs[0];
+        const int r = s0->rank, w = s0->world;
+        s0->rank = 0;
+        s0->world = 1;
+        const int rc = iid_spring_host(s0, pos_host, n, sp_type, k, rt, com, energy_host,
+                                       forces_host, atomwise_host);
+        s0->rank = r;
+        s0->world = w;
+        return rc;
+    }
     NEED(h);
     int rc;
     if ((rc = check_spring(sp_type, n))) return rc;
@@ -1141,6 +1591,9 @@ extern "C" int iid_spring_voxel_host(iid_handle *h, const double *pos_host, int6
                                      double k, double rt, const double *com, double resolution,
                                      int64_t nx, int64_t ny, int64_t nz, double *voxels_host)
 {
+    if (MULTI(h))
+        return iid_spring_voxel_host(h->subs[0], pos_host, n, sp_type, k, rt, com, resolution, nx,
+                                     ny, nz, voxels_host);
     NEED(h);
     int rc;
     if ((rc = check_spring(sp_type, n))) return rc;
@@ -1177,6 +1630,14 @@ extern "C" int iid_spring_voxel_host(iid_handle *h, const double *pos_host, int6
 extern "C" int iid_set_restraints(iid_handle *h, int count, const int *sp_type, const double *k,
                                   const double *rt)
 {
+    if (MULTI(h)) {
+        for (iid_handle *sh : h->subs) {
+            int rc = iid_set_restraints(sh, count, sp_type, k, rt);
+            if (rc) return rc;
+        }
+        h->n_restraints = count;
+        return 0;
+    }
     if (!h) return fail(IID_E_BADARG, "null handle");
     if (count < 0 || count > IID_MAX_RESTRAINTS)
         return fail(IID_E_BADARG, "at most IID_MAX_RESTRAINTS restraints");
@@ -1200,6 +1661,11 @@ extern "C" int iid_set_restraints(iid_handle *h, int count, const int *sp_type, 
 
 extern "C" int iid_get_restraint_energy(iid_handle *h, double *energy)
 {
+    if (MULTI(h)) {
+        if (!energy) return fail(IID_E_BADARG, "null argument");
+        *energy = h->n_restraints ? h->rs_k[0] : 0.0;  // summed over the devices by the last call
+        return 0;
+    }
     if (!h || !energy) return fail(IID_E_BADARG, "null argument");
     *energy = h->n_restraints && h->pin ? h->pin[6 * h->n + h->qp + 4] : 0.0;
     return 0;
@@ -1209,14 +1675,18 @@ extern "C" int iid_get_restraint_energy(iid_handle *h, double *energy)
 // F(Q) pass -> F -> G(r) -> Rw / chi^2 (h->out4) -> chain-rule weights -> force
 // pass (h->force) -> fused restraints.  Enqueued on the handle's stream; shared
 // by iid_energy_forces_host and iid_leapfrog_host (both replay it from a graph).
+// phase: EVAL_ALL, or the two halves around the host-side sum of the F(Q)
+// partials of a multi-device handle (EVAL_FQ: staging + F(Q) pass; EVAL_REST:
+// everything after it, h->S already holding the summed pair sums).
+enum { EVAL_ALL = 0, EVAL_FQ = 1, EVAL_REST = 2 };
 static int enqueue_eval_device(iid_handle *h, int potential, double conv, bool want_forces,
-                               bool staged = false)
+                               bool staged = false, int phase = EVAL_ALL)
 {
     int rc2;
     cudaStream_t st = h->stream;
     // staging also clears S and the force accumulator (no memset nodes); a
     // caller that staged the positions itself (leapfrog) has done both
-    if (!staged) {
+    if (!staged && phase != EVAL_REST) {
         const int np = (int)h->np;
         prep_kernel<<<(np + 255) / 256, 256, 0, st>>>(h->pos, h->orig, np,
                                                       h->precision == IID_FP32, h->x, h->y, h->z,
@@ -1225,7 +1695,10 @@ static int enqueue_eval_device(iid_handle *h, int potential, double conv, bool w
         ++h->launches;
         CU(cudaGetLastError());
     }
-    if ((rc2 = launch_debye(h, MODE_FQ, nullptr, h->S, nullptr, nullptr, st))) return rc2;
+    if (phase != EVAL_REST &&
+        (rc2 = launch_debye(h, MODE_FQ, nullptr, h->S, nullptr, nullptr, st)))
+        return rc2;
+    if (phase == EVAL_FQ) return 0;
     // F = 2 S / na and G = T F in one launch
     {
         const int64_t threads = h->nr * 32;
@@ -1347,6 +1820,9 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
                                       const double *target_host, int potential, double conv,
                                       double *out_host, double *forces_host, double *pdf_host)
 {
+    if (MULTI(h))
+        return multi_energy_forces_host(h, pos_host, target_host, potential, conv, out_host,
+                                        forces_host, pdf_host);
     NEED(h);
     if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
     if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
@@ -1397,6 +1873,11 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
 extern "C" int iid_sampler_setup(iid_handle *h, int64_t n_slots, const double *masses_host,
                                  const double *cell_centre)
 {
+    if (MULTI(h)) {
+        if (h->active != 1)
+            return fail(IID_E_BADARG, "device-resident sampler states need a one-device structure");
+        return iid_sampler_setup(h->subs[0], n_slots, masses_host, cell_centre);
+    }
     NEED(h);
     if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
     if (n_slots < 2 || n_slots > 4096 || !masses_host || !cell_centre)
@@ -1438,6 +1919,7 @@ static int check_slot(iid_handle *h, int slot)
 extern "C" int iid_state_upload(iid_handle *h, int slot, const double *q_host,
                                 const double *p_host, const double *f_host)
 {
+    if (MULTI(h)) return iid_state_upload(h->subs[0], slot, q_host, p_host, f_host);
     NEED(h);
     int rc = check_slot(h, slot);
     if (rc) return rc;
@@ -1456,6 +1938,7 @@ extern "C" int iid_state_upload(iid_handle *h, int slot, const double *q_host,
 extern "C" int iid_state_download(iid_handle *h, int slot, double *q_host, double *p_host,
                                   double *f_host)
 {
+    if (MULTI(h)) return iid_state_download(h->subs[0], slot, q_host, p_host, f_host);
     NEED(h);
     int rc = check_slot(h, slot);
     if (rc) return rc;
@@ -1472,6 +1955,12 @@ extern "C" int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, i
                                  const double *target_host, int potential, double conv,
                                  double *out_host, double *q_host, double *p_host)
 {
+    if (MULTI(h)) {
+        if (h->active != 1)
+            return fail(IID_E_BADARG, "device-resident sampler states need a one-device structure");
+        return iid_leapfrog_host(h->subs[0], src, dst, step, centre, target_host, potential, conv,
+                                 out_host, q_host, p_host);
+    }
     NEED(h);
     if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
     if (h->world != 1)
@@ -1525,6 +2014,8 @@ extern "C" int iid_rw_host(iid_handle *h, const double *gcalc_host, const double
                            int64_t len, int potential, double conv, double *out_host,
                            double *c_host)
 {
+    if (MULTI(h))
+        return iid_rw_host(h->subs[0], gcalc_host, gobs_host, len, potential, conv, out_host, c_host);
     NEED(h);
     if (!gcalc_host || !gobs_host || !out_host || len < 1)
         return fail(IID_E_BADARG, "bad argument");
@@ -1564,6 +2055,8 @@ extern "C" int iid_contract_host(iid_handle *h, const void *A_host, int a_is_f32
                                  int64_t rows, int64_t len, const double *c_host,
                                  double *out_host)
 {
+    if (MULTI(h))
+        return iid_contract_host(h->subs[0], A_host, a_is_f32, rows, len, c_host, out_host);
     NEED(h);
     if (!A_host || !c_host || !out_host || rows < 0 || len < 1)
         return fail(IID_E_BADARG, "bad argument");
@@ -1607,6 +2100,7 @@ extern "C" int iid_contract_host(iid_handle *h, const void *A_host, int a_is_f32
 // elasticscatter/__init__.py:371-390)
 extern "C" int iid_fq_to_gr_host(iid_handle *h, const double *F_host, double *pdf_host)
 {
+    if (MULTI(h)) return iid_fq_to_gr_host(h->subs[0], F_host, pdf_host);
     NEED(h);
     if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
     if (!F_host || !pdf_host) return fail(IID_E_BADARG, "null pointer");
@@ -1625,6 +2119,13 @@ extern "C" int iid_fq_to_gr_host(iid_handle *h, const double *F_host, double *pd
 // Tunables (also read from IID_* environment variables at iid_create).
 extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
 {
+    if (MULTI(h)) {
+        for (iid_handle *sh : h->subs) {
+            int rc = iid_set_option(sh, key, value);
+            if (rc) return rc;
+        }
+        return 0;
+    }
     if (!h || !key) return fail(IID_E_BADARG, "null argument");
     const std::string k(key);
     if (k == "force_table") h->use_force_table = value != 0;
@@ -1636,6 +2137,17 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "grad_nw_max") h->grad_nw_max = (int)std::max<int64_t>(1, std::min<int64_t>(12, value));
     else if (k == "qspace_wq") h->qspace_wq = value != 0;
     else if (k == "nw_max") h->nw_max = (int)std::max<int64_t>(1, std::min<int64_t>(12, value));
+    else if (k == "zero_copy") h->zero_copy = value != 0;
+    else if (k == "acc_j") h->acc_j = (int)std::max<int64_t>(0, value);
+    else if (k == "piece_div") {
+        h->piece_div = (int)std::max<int64_t>(1, std::min<int64_t>(1024, value));
+        if (h->np > 0) {
+            CU(cudaSetDevice(h->device));
+            CU(cudaStreamSynchronize(h->stream));
+            int rc = upload_row_jobs(h);
+            if (rc) return rc;
+        }
+    }
     else return fail(IID_E_BADARG, "unknown option: " + k);
     drop_graph(h);
     return 0;
@@ -1644,6 +2156,12 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
 // --- instrumentation -----------------------------------------------------------
 extern "C" int iid_launch_count(iid_handle *h, int64_t *count)
 {
+    if (MULTI(h)) {
+        if (!count) return fail(IID_E_BADARG, "null argument");
+        *count = 0;
+        for (iid_handle *sh : h->subs) *count += sh->launches;
+        return 0;
+    }
     if (!h || !count) return fail(IID_E_BADARG, "null argument");
     *count = h->launches;
     return 0;
@@ -1651,6 +2169,10 @@ extern "C" int iid_launch_count(iid_handle *h, int64_t *count)
 
 extern "C" int iid_set_timing(iid_handle *h, int enabled)
 {
+    if (MULTI(h)) {
+        for (iid_handle *sh : h->subs) sh->timing = enabled != 0;
+        return 0;
+    }
     if (!h) return fail(IID_E_BADARG, "null handle");
     h->timing = enabled != 0;
     return 0;
@@ -1658,6 +2180,21 @@ extern "C" int iid_set_timing(iid_handle *h, int enabled)
 
 extern "C" int iid_last_kernel_ms(iid_handle *h, float *ms, double *pairq)
 {
+    if (MULTI(h)) {
+        if (!ms) return fail(IID_E_BADARG, "null argument");
+        *ms = 0.f;
+        double pq = 0.0;
+        for (int d = 0; d < h->active; ++d) {  // the slowest device, all devices' pair*Q
+            float m = 0.f;
+            double q = 0.0;
+            int rc = iid_last_kernel_ms(h->subs[d], &m, &q);
+            if (rc) return rc;
+            *ms = std::max(*ms, m);
+            pq += q;
+        }
+        if (pairq) *pairq = pq;
+        return 0;
+    }
     NEED(h);
     if (!ms) return fail(IID_E_BADARG, "null argument");
     *ms = 0.f;
@@ -1666,5 +2203,326 @@ extern "C" int iid_last_kernel_ms(iid_handle *h, float *ms, double *pairq)
         CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
     }
     if (pairq) *pairq = h->last_pairq;
+    return 0;
+}
+
+// Measured issue rates of the pipes that bound the pair sums, in lane-FMAs per
+// second: out[0] scalar FFMA, out[1] packed FFMA2 (two lanes per thread
+// instruction), out[2] DFMA.  Best of three timed launches each, CUDA events on
+// the handle's stream; ~30 ms in all.
+extern "C" int iid_measure_peaks(iid_handle *h, double *out)
+{
+    if (MULTI(h)) return iid_measure_peaks(h->subs[0], out);
+    NEED(h);
+    if (!out) return fail(IID_E_BADARG, "null pointer");
+    float *buf = nullptr;
+    CU(cudaMalloc((void **)&buf, 1024 * sizeof(float)));
+    std::vector<float> init(64);
+    for (int i = 0; i < 32; ++i) {
+        init[i] = 0.999f + 1e-5f * i;   // |a| < 1: the chains stay finite
+        init[32 + i] = 1e-3f * (i + 1);
+    }
+    CU(cudaMemcpy(buf, init.data(), 64 * sizeof(float), cudaMemcpyHostToDevice));
+    const int blocks = h->sm_count * 4, threads = 256;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    for (int kind = 0; kind < 3; ++kind) {
+        const int trips = kind == UB_DFMA ? 512 : 2048;
+        double best = 0.0;
+        for (int rep = 0; rep < 4; ++rep) {
+            CU(cudaEventRecord(e0, h->stream));
+            if (kind == UB_FFMA)
+                pipe_peak_kernel<UB_FFMA><<<blocks, threads, 0, h->stream>>>(buf, trips, buf + 64);
+            else if (kind == UB_FFMA2)
+                pipe_peak_kernel<UB_FFMA2><<<blocks, threads, 0, h->stream>>>(buf, trips, buf + 64);
+            else
+                pipe_peak_kernel<UB_DFMA><<<blocks, threads, 0, h->stream>>>(buf, trips, buf + 64);
+            CU(cudaEventRecord(e1, h->stream));
+            CU(cudaEventSynchronize(e1));
+            ++h->launches;
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            const double fmas = (double)blocks * threads * trips * UB_UNROLL * UB_CHAINS *
+                                (kind == UB_FFMA2 ? 2.0 : 1.0);
+            if (rep > 0 && ms > 0.f) best = std::max(best, fmas / (ms * 1e-3));
+        }
+        out[kind] = best;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    return 0;
+}
+
+// --- multi-device handle ---------------------------------------------------------
+// One process, every GPU of the box (reference: the thread-per-GPU task farm of
+// gpu_wrappers/gpu_wrap.py:119-156, 287-314).  The handle owns one complete
+// sub-handle per device; sub d computes shard (d, active) of each pass.  The
+// only cross-device data are the F(Q) pair sums (nq doubles), the force array
+// (3n doubles) and four scalars; they are summed on the host in device order
+// (deterministic), so no collective library is involved.  The gradient rows
+// are disjoint per device and go straight into the caller's array.
+extern "C" int iid_create_multi(int n_devices, int precision, iid_handle **out)
+{
+    if (!out) return fail(IID_E_BADARG, "null out");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(IID_E_NODEVICE, "no CUDA device: this library has no CPU fallback");
+    if (n_devices <= 0) n_devices = count;
+    if (n_devices > count) return fail(IID_E_BADARG, "more devices requested than present");
+    iid_handle *h = new iid_handle();
+    h->precision = precision;
+    for (int d = 0; d < n_devices; ++d) {
+        iid_handle *sh = nullptr;
+        int rc = iid_create(d, precision, &sh);
+        if (rc) {
+            for (iid_handle *x : h->subs) iid_destroy(x);
+            delete h;
+            return rc;
+        }
+        h->subs.push_back(sh);
+    }
+    h->device = 0;
+    h->sm_count = h->subs[0]->sm_count;
+    *out = h;
+    return 0;
+}
+
+extern "C" int iid_handle_devices(iid_handle *h, int *n_devices, int *active)
+{
+    if (!h) return fail(IID_E_BADARG, "null handle");
+    if (n_devices) *n_devices = h->subs.empty() ? 1 : (int)h->subs.size();
+    if (active) *active = h->subs.empty() ? 1 : h->active;
+    return 0;
+}
+
+static int multi_destroy(iid_handle *h)
+{
+    for (iid_handle *sh : h->subs) iid_destroy(sh);
+    if (h->pinG) {
+        cudaSetDevice(0);
+        cudaFreeHost(h->pinG);
+    }
+    delete h;
+    return 0;
+}
+
+static int multi_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
+                               int64_t n_types, const double *ftable, int64_t nq, double qbin)
+{
+    // small structures do not amortise the per-device launches and the host
+    // hops: about 1500 atoms per device at least
+    int active = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->subs.size(), n / 1500));
+    if (const char *s = getenv("IID_MULTI_ACTIVE"))
+        active = std::max(1, std::min((int)h->subs.size(), atoi(s)));
+    h->active = active;
+    for (int d = 0; d < active; ++d) {
+        iid_handle *sh = h->subs[d];
+        sh->rank = d;  // before the structure: the row jobs are built once
+        sh->world = active;
+        int rc = iid_set_structure(sh, n, type_index, n_types, ftable, nq, qbin);
+        if (rc) return rc;
+    }
+    if (nq != h->nq) h->nr = 0;
+    // a device that joins with this structure gets the transform the others hold
+    for (int d = 0; d < active && h->nr > 0; ++d)
+        if (h->subs[d]->nr != h->nr) {
+            int rc = iid_set_transform(h->subs[d], h->nr, nq, h->T_host.data());
+            if (rc) return rc;
+        }
+    h->n = n;
+    h->nq = nq;
+    h->qp = h->subs[0]->qp;
+    h->np = h->subs[0]->np;
+    h->inv_na_host = h->subs[0]->inv_na_host;
+    return 0;
+}
+
+static int multi_set_transform(iid_handle *h, int64_t nr, int64_t nq, const double *T)
+{
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (nr < 1 || !T || nq != h->nq) return fail(IID_E_BADARG, "bad transform arguments");
+    for (int d = 0; d < h->active; ++d) {
+        int rc = iid_set_transform(h->subs[d], nr, nq, T);
+        if (rc) return rc;
+    }
+    for (size_t d = (size_t)h->active; d < h->subs.size(); ++d) h->subs[d]->nr = 0;
+    h->T_host.assign(T, T + (size_t)nr * nq);
+    h->nr = nr;
+    return 0;
+}
+
+// F(Q) pair sums of every active device -> their sum in `S` (host, device order)
+static int multi_fq_pass(iid_handle *h, const double *pos_host, std::vector<double> &S)
+{
+    int rc;
+    for (int d = 0; d < h->active; ++d) {
+        iid_handle *sh = h->subs[d];
+        CU(cudaSetDevice(sh->device));
+        if ((rc = upload_positions(sh, pos_host))) return rc;
+        if ((rc = iid_fq_partial(sh, sh->pos, sh->S, nullptr))) return rc;
+        CU(cudaMemcpyAsync(sh->pin + 6 * sh->n, sh->S, sh->nq * sizeof(double),
+                           cudaMemcpyDeviceToHost, sh->stream));
+    }
+    S.assign((size_t)h->nq, 0.0);
+    for (int d = 0; d < h->active; ++d) {
+        iid_handle *sh = h->subs[d];
+        CU(cudaSetDevice(sh->device));
+        CU(cudaStreamSynchronize(sh->stream));
+        const double *ps = sh->pin + 6 * sh->n;
+        for (int64_t m = 0; m < h->nq; ++m) S[m] += ps[m];
+    }
+    return 0;
+}
+
+static int multi_fq_host(iid_handle *h, const double *pos_host, double *F_host, double *pdf_host)
+{
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (pdf_host && h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
+    if (!pos_host || (!F_host && !pdf_host)) return fail(IID_E_BADARG, "null pointer");
+    std::vector<double> S;
+    int rc = multi_fq_pass(h, pos_host, S);
+    if (rc) return rc;
+    std::vector<double> F((size_t)h->nq);
+    for (int64_t m = 0; m < h->nq; ++m) F[m] = 2.0 * S[m] * h->inv_na_host[m];
+    if (F_host) memcpy(F_host, F.data(), h->nq * sizeof(double));
+    if (pdf_host) return iid_fq_to_gr_host(h->subs[0], F.data(), pdf_host);
+    return 0;
+}
+
+static int multi_grad_fq_host(iid_handle *h, const double *pos_host, void *G_host, double *F_host)
+{
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (!pos_host || !G_host) return fail(IID_E_BADARG, "null pointer");
+    const size_t esz = h->precision == IID_FP32 ? sizeof(float) : sizeof(double);
+    const size_t bytes = (size_t)h->n * 3 * h->nq * esz;
+    CU(cudaSetDevice(h->subs[0]->device));
+    void *alias = mapped_alias(G_host);
+    unsigned char *stage = nullptr;
+    if (!alias) {
+        // pageable destination: all devices write their rows into one pinned,
+        // mapped staging array, copied on by a few host threads afterwards
+        if (bytes > h->pinG_bytes) {
+            if (h->pinG) cudaFreeHost(h->pinG);
+            h->pinG = nullptr;
+            h->pinG_bytes = 0;
+            CU(cudaHostAlloc((void **)&h->pinG, bytes,
+                             cudaHostAllocPortable | cudaHostAllocMapped));
+            h->pinG_bytes = bytes;
+        }
+        stage = h->pinG;
+    }
+    int rc;
+    for (int d = 0; d < h->active; ++d) {
+        iid_handle *sh = h->subs[d];
+        CU(cudaSetDevice(sh->device));
+        void *dst = mapped_alias(stage ? (void *)stage : G_host);
+        if (!dst) return fail(IID_E_BADARG, "output array is not mapped on every device");
+        if ((rc = upload_positions(sh, pos_host))) return rc;
+        if ((rc = iid_grad_fq_partial(sh, sh->pos, dst, sh->S, nullptr))) return rc;
+        CU(cudaMemcpyAsync(sh->pin + 6 * sh->n, sh->S, sh->nq * sizeof(double),
+                           cudaMemcpyDeviceToHost, sh->stream));
+    }
+    std::vector<double> S((size_t)h->nq, 0.0);
+    for (int d = 0; d < h->active; ++d) {
+        iid_handle *sh = h->subs[d];
+        CU(cudaSetDevice(sh->device));
+        CU(cudaStreamSynchronize(sh->stream));
+        const double *ps = sh->pin + 6 * sh->n;
+        for (int64_t m = 0; m < h->nq; ++m) S[m] += ps[m];
+    }
+    if (F_host)
+        for (int64_t m = 0; m < h->nq; ++m) F_host[m] = 2.0 * S[m] * h->inv_na_host[m];
+    if (stage) {
+        const int nthreads = 8;
+        std::vector<std::thread> workers;
+        const size_t part = (bytes + nthreads - 1) / nthreads;
+        for (int t = 0; t < nthreads; ++t) {
+            const size_t o = (size_t)t * part;
+            if (o >= bytes) break;
+            const size_t l = std::min(part, bytes - o);
+            workers.emplace_back([=]() { memcpy((unsigned char *)G_host + o, stage + o, l); });
+        }
+        for (auto &w : workers) w.join();
+    }
+    return 0;
+}
+
+static int multi_energy_forces_host(iid_handle *h, const double *pos_host,
+                                    const double *target_host, int potential, double conv,
+                                    double *out_host, double *forces_host, double *pdf_host)
+{
+    if (h->n == 0) return fail(IID_E_NOSTRUCT, "call iid_set_structure first");
+    if (h->active == 1) {  // small structure: the one-device graph replay
+        int rc = iid_energy_forces_host(h->subs[0], pos_host, target_host, potential, conv,
+                                        out_host, forces_host, pdf_host);
+        if (rc == 0 && h->n_restraints) iid_get_restraint_energy(h->subs[0], &h->rs_k[0]);
+        return rc;
+    }
+    if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
+    if (!pos_host || !out_host) return fail(IID_E_BADARG, "null pointer");
+    if (potential != IID_POT_RW && potential != IID_POT_CHI_SQ)
+        return fail(IID_E_BADARG, "unknown potential");
+    int rc;
+    const bool want_forces = forces_host != nullptr;
+    // phase 1 on every device: staging + its share of the F(Q) pass
+    for (int d = 0; d < h->active; ++d) {
+        iid_handle *sh = h->subs[d];
+        CU(cudaSetDevice(sh->device));
+        double *pt = sh->pin + 6 * sh->n + sh->qp + 8 + sh->nr;
+        if ((rc = refresh_target(sh, target_host, pt))) return rc;
+        if ((rc = upload_positions(sh, pos_host))) return rc;
+        if ((rc = enqueue_eval_device(sh, potential, conv, want_forces, false, EVAL_FQ))) return rc;
+        CU(cudaMemcpyAsync(sh->pin + 6 * sh->n, sh->S, sh->nq * sizeof(double),
+                           cudaMemcpyDeviceToHost, sh->stream));
+    }
+    std::vector<double> S((size_t)h->qp, 0.0);
+    for (int d = 0; d < h->active; ++d) {
+        iid_handle *sh = h->subs[d];
+        CU(cudaSetDevice(sh->device));
+        CU(cudaStreamSynchronize(sh->stream));
+        const double *ps = sh->pin + 6 * sh->n;
+        for (int64_t m = 0; m < h->nq; ++m) S[m] += ps[m];
+    }
+    // phase 2 on every device: summed pair sums -> G(r), Rw, weights (redundant,
+    // 11 MB of T) -> its share of the force pass and of the restraints
+    for (int d = 0; d < h->active; ++d) {
+        iid_handle *sh = h->subs[d];
+        CU(cudaSetDevice(sh->device));
+        double *pf = sh->pin + 6 * sh->n;
+        memcpy(pf, S.data(), h->qp * sizeof(double));
+        CU(cudaMemcpyAsync(sh->S, pf, sh->qp * sizeof(double), cudaMemcpyHostToDevice,
+                           sh->stream));
+        if ((rc = enqueue_eval_device(sh, potential, conv, want_forces, false, EVAL_REST)))
+            return rc;
+        if (want_forces)
+            CU(cudaMemcpyAsync(sh->pin + 3 * sh->n, sh->force, (size_t)3 * sh->n * sizeof(double),
+                               cudaMemcpyDeviceToHost, sh->stream));
+        CU(cudaMemcpyAsync(pf + sh->qp, sh->out4, 5 * sizeof(double), cudaMemcpyDeviceToHost,
+                           sh->stream));
+        if (pdf_host && d == 0)
+            CU(cudaMemcpyAsync(pf + sh->qp + 8, sh->Gr, sh->nr * sizeof(double),
+                               cudaMemcpyDeviceToHost, sh->stream));
+    }
+    if (want_forces) memset(forces_host, 0, (size_t)3 * h->n * sizeof(double));
+    double e_rest = 0.0;
+    for (int d = 0; d < h->active; ++d) {
+        iid_handle *sh = h->subs[d];
+        CU(cudaSetDevice(sh->device));
+        CU(cudaStreamSynchronize(sh->stream));
+        const double *po = sh->pin + 6 * sh->n + sh->qp;
+        if (d == 0) {
+            memcpy(out_host, po, 4 * sizeof(double));
+            if (pdf_host) memcpy(pdf_host, po + 8, h->nr * sizeof(double));
+        }
+        e_rest += po[4];
+        if (want_forces) {
+            const double *pfor = sh->pin + 3 * sh->n;
+            for (int64_t k = 0; k < 3 * h->n; ++k) forces_host[k] += pfor[k];
+        }
+    }
+    h->rs_k[0] = e_rest;  // read back by iid_get_restraint_energy
     return 0;
 }

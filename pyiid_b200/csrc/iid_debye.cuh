@@ -41,7 +41,31 @@ struct WorkItem {
     int info;    // bits 0..15 element type of the j-slab, bit 16 diagonal item
 };
 constexpr int ITEM_DIAG = 1 << 16;
-constexpr int ITEM_NOF = 1 << 17;  // square list: item above the diagonal, gradient only
+constexpr int ITEM_NOF = 1 << 17;  // j range above the diagonal: gradient only
+constexpr int SEG_FLUSH = 1 << 18; // row jobs: last segment of an element run -> flush
+
+// Full-gradient pass (MODE_GRAD): ROW OWNERSHIP.  A block owns one row job =
+// (i-tile, consecutive j segments); it keeps the 32 x 3 x Q accumulators of
+// its atoms in registers over all segments and writes each gradient row
+// exactly once with plain coalesced stores -- no zero-fill of the output, no
+// atomics, bit-reproducible.  A job whose segments cover the whole j range
+// (dest < 0) stores into the caller's G rows; the rows kept back for load
+// balance are cut into pieces (dest >= 0) that store into a side buffer and
+// are summed in a fixed order by rows_fixup_kernel.
+struct RowSeg {
+    int jbegin, jend;  // sorted/padded j range, one element run, multiples of 32
+    int info;          // element type | ITEM_DIAG | ITEM_NOF | SEG_FLUSH
+    int pad;
+};
+struct RowJob {
+    int itile;               // atoms [32*itile, 32*itile + 32)
+    int seg_begin, seg_end;  // segments [seg_begin, seg_end) of the segment array
+    int dest;                // < 0: rows of G; >= 0: slot of the side buffer
+};
+// a split row for rows_fixup_kernel: G rows of tile itile = sum of side slots [d0, d1)
+struct RowFix {
+    int itile, d0, d1, pad;
+};
 
 enum Mode { MODE_FQ = 0, MODE_GRAD = 1, MODE_FORCE = 2 };
 
@@ -57,10 +81,20 @@ struct DebyeParams {
     const double *wq;    // [qp] chain-rule weights (MODE_FORCE)
     int nq, qp;
     double qbin, qbin_turns;  // qbin and qbin/(2 pi)
-    void *G;        // [n][3][nq] kernel precision (MODE_GRAD)
-    double *S;      // [qp] (MODE_FQ, MODE_GRAD; may be null in MODE_GRAD)
+    void *G;        // [n][3][nq] kernel precision (MODE_GRAD); device or mapped host memory
+    double *S;      // [qp] (MODE_FQ); MODE_GRAD: [n_jobs][qp] per-job partial sums (may be null)
     double *force;  // [n][3] (MODE_FORCE)
-    int grad_split;  // MODE_GRAD: 1 = F(Q) from the lower triangle only (ITEM_NOF items skip it)
+    int grad_split;  // MODE_GRAD: 1 = F(Q) from the lower triangle only (ITEM_NOF segments skip it)
+    // MODE_GRAD row jobs
+    const RowJob *jobs;
+    const RowSeg *segs;
+    void *Gside;    // [n_pieces][32][3][nq] kernel precision
+    // FP32 accuracy: a row job parks its float32 partial sums every acc_j j
+    // atoms in a thread-private scratch slot (L2 resident) instead of letting
+    // one float32 accumulator run over the whole row (0 = never)
+    float *Gscr;    // [n_slots][3 C][block threads]
+    int *slot_busy; // [n_slots] 0 = free
+    int n_slots, acc_j;
 };
 
 // sin(2 pi f), cos(2 pi f) for |f| <= 1/8 turn: float32 minimax polynomials on

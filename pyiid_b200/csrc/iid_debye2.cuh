@@ -82,22 +82,38 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
     const int m0 = (chunk0 + warp) * C;
     const bool active = m0 < p.nq;
 
-    const WorkItem it = p.items[p.item_begin + (int64_t)blockIdx.x * p.item_stride];
-    const bool diag = (it.info & ITEM_DIAG) != 0;
-    // full-gradient (square) list: F(Q) comes from the items below the diagonal
-    // (weight 1) and the diagonal tile (both orders present, weight 1/2); items
-    // above it -- or every item when no F(Q) is wanted -- are gradient only
-    const bool nof = MODE == MODE_GRAD && p.grad_split &&
-                     ((it.info & ITEM_NOF) != 0 || p.S == nullptr);
-    const int btype = it.info & 0xffff;
-    const int atype = p.tile_type[it.itile];
-    const int gi = it.itile * TILE_I + lane;
+    // MODE_GRAD: a row job (i-tile, consecutive j segments); the other modes: one
+    // work item = one segment
+    int itile, seg = 0, seg_end = 1, dest = -1;
+    RowSeg sg;
+    if constexpr (MODE == MODE_GRAD) {
+        const RowJob job = p.jobs[blockIdx.x];
+        itile = job.itile;
+        seg = job.seg_begin;
+        seg_end = job.seg_end;
+        dest = job.dest;
+        sg = p.segs[seg];
+    } else {
+        const WorkItem it = p.items[p.item_begin + (int64_t)blockIdx.x * p.item_stride];
+        itile = it.itile;
+        sg.jbegin = it.jbegin;
+        sg.jend = it.jend;
+        sg.info = it.info;
+    }
+    // per segment: diagonal tile (both orders present: F(Q) weight 1/2, applied
+    // by the producer to the r^2 of the record), gradient-only range (above the
+    // diagonal, or every segment when no F(Q) is wanted), element type of the j run
+    bool diag = (sg.info & ITEM_DIAG) != 0;
+    bool nof = MODE == MODE_GRAD && p.grad_split && ((sg.info & ITEM_NOF) != 0 || p.S == nullptr);
+    float fw = (MODE == MODE_GRAD && (diag || !p.grad_split)) ? 0.5f : 1.f;
+    const int atype = p.tile_type[itile];
+    const int gi = itile * TILE_I + lane;
     const double xi = p.x[gi], yi = p.y[gi], zi = p.z[gi];
     const bool vi = p.valid[gi] != 0.f;
 
     const float *ftab = reinterpret_cast<const float *>(p.ftab);
     const float *fa = ftab + (size_t)atype * p.qp;
-    const float *fb = ftab + (size_t)btype * p.qp;
+    const float *fb = ftab + (size_t)(sg.info & 0xffff) * p.qp;
     const float *inv_na = reinterpret_cast<const float *>(p.inv_na);
 
     constexpr int NPAIR = TJ2 * 32;
@@ -181,7 +197,7 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
                 s[u] *= b3;
                 c[u] *= b3;
                 if (live[u]) {
-                    RA[pr[u]] = make_float4(cth, sth, (float)(p.qbin * r), r2f);
+                    RA[pr[u]] = make_float4(cth, sth, (float)(p.qbin * r), r2f * fw);
                     RA[NPAIR + pr[u]] = make_float4((float)dxd, (float)dyd, (float)dzd, cQ);
                     T[8 * NPAIR + pr[u]] = sQ;
                 }
@@ -401,88 +417,307 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
         }
     };
 
-    const int ntile = (it.jend - it.jbegin) / TJ2;  // slabs are multiples of 32
-    // warps w and w+4 share a scheduler: one produces the next tile before its
-    // consume phase, the other after it, so one of them always feeds the FP32 pipe
-    // (measured: pairing by warp & 1, or no stagger at all, costs 6 %)
-    const bool early = ((warp >> 2) & 1) == 0;
-    produce(it.jbegin, 0);
-    __syncthreads();
-    for (int t = 0; t < ntile; ++t) {
-        const int b = t & 1;
-        const bool has_next = t + 1 < ntile;
-        const int jnext = it.jbegin + (t + 1) * TJ2;
-        if (has_next && early) produce(jnext, b ^ 1);
-        if (active) {
-            if constexpr (MODE == MODE_GRAD && CHEB) {
-                if (nof) consume(std::true_type{}, b);
-                else consume(std::false_type{}, b);
-            } else {
-                consume(std::false_type{}, b);
-            }
-        }
-        if (has_next && !early) produce(jnext, b ^ 1);
-        __syncthreads();
-        if constexpr (MODE == MODE_FORCE) {
-            if (!diag) {
-                reduce_j(b, it.jbegin + t * TJ2);
-                __syncthreads();  // records of buffer b are rewritten next iteration
-            }
-        }
-    }
-
-    if (!active) return;
+    // ---- MODE_GRAD flush: the block owns its rows -> plain stores ---------------
+    // Transpose the warp's (bin x atom) accumulators through its own slice of
+    // the idle pair-record buffers so that lane L holds bin m0 + L of atom a:
+    // every store instruction then writes one contiguous 128-byte piece of ONE
+    // row (coalesced for HBM and for mapped host memory alike).  The first flush
+    // of a job stores, later ones (further element runs) add to what the same
+    // thread stored before.
+    static_assert(C <= 32, "one lane per bin of the chunk");
     const int oi = p.orig[gi];
-    if constexpr (MODE == MODE_FORCE) {
-        if (oi >= 0) {
-            atomicAdd(&p.force[(size_t)oi * 3 + 0], (double)fix);
-            atomicAdd(&p.force[(size_t)oi * 3 + 1], (double)fiy);
-            atomicAdd(&p.force[(size_t)oi * 3 + 2], (double)fiz);
+    double srun = 0.0;  // MODE_GRAD: this job's F(Q) pair sum of bin m0 + lane
+    // Float32 accuracy over long rows.  One float32 accumulator per (atom, bin)
+    // running over all j of a 50 000-atom row loses a digit against the
+    // float64 mode (measured 1.3e-5 instead of 1.7e-6 on grad F, 1.1e-6 instead
+    // of 8e-8 on F(Q)).  Every acc_j j atoms the block therefore parks its
+    // gradient partial sums in a scratch slot (thread-private layout: each
+    // thread reads back only what it wrote; [value][thread] so the accesses
+    // coalesce; the slots in use fit the L2) and folds the F(Q) partial sums
+    // into the float64 `srun`; the row flush adds the parked sums back.  The
+    // order of all these additions is fixed: results stay bit-reproducible.
+    int slot = -1;           // scratch slot of this block (acquired on first use)
+    bool parked = false;     // the slot holds partial sums of the current run
+    int jacc = 0;            // j atoms accumulated since the last park
+    __shared__ int slot_sh;
+    [[maybe_unused]] auto park = [&](int b) {
+      if constexpr (MODE == MODE_GRAD) {
+        if (slot < 0) {
+            if (threadIdx.x == 0) {
+                int s0 = (int)((blockIdx.x * 7u + blockIdx.y) % (unsigned)p.n_slots), got = -1;
+                while (got < 0)
+                    for (int k = 0; k < p.n_slots && got < 0; ++k) {
+                        const int t = (s0 + k) % p.n_slots;
+                        if (atomicCAS(&p.slot_busy[t], 0, 1) == 0) got = t;
+                    }
+                slot_sh = got;
+            }
+            __syncthreads();
+            slot = slot_sh;
         }
-    } else {
-        const double fweight = ((MODE == MODE_GRAD && !p.grad_split) || diag) ? 0.5 : 1.0;
-        float *G = reinterpret_cast<float *>(p.G);
-        if constexpr (MODE == MODE_GRAD) {
+        if (active) {
+            float2 *scr = reinterpret_cast<float2 *>(p.Gscr) +
+                          (size_t)slot * (3 * H) * blockDim.x + threadIdx.x;
+            // first park of a run: plain stores; later ones: fire-and-forget
+            // vector RED (no read-back stall).  Every address belongs to one
+            // thread and its operations arrive in program order, so the sums
+            // are the same on every run.
+            auto put = [&](float2(&acc)[MODE == MODE_GRAD ? H : 1], int comp) {
 #pragma unroll
-            for (int m = 0; m < C; ++m) {
-                const int bin = m0 + m;
-                if (bin < p.nq && oi >= 0) {  // bin < nq is warp-uniform
-                    const int k = m % H;
-                    const bool hi = m >= H;
-                    const float sc = fa[bin] * fb[bin] * inv_na[bin];
-                    float *row = G + (size_t)oi * 3 * p.nq + bin;
-                    atomicAdd(row, (hi ? accX[k].y : accX[k].x) * sc);
-                    atomicAdd(row + p.nq, (hi ? accY[k].y : accY[k].x) * sc);
-                    atomicAdd(row + 2 * (size_t)p.nq, (hi ? accZ[k].y : accZ[k].x) * sc);
+                for (int k = 0; k < H; ++k) {
+                    float2 *q = scr + (size_t)(comp * H + k) * blockDim.x;
+                    if (parked) atomicAdd(q, acc[k]);
+                    else *q = acc[k];
+                    acc[k] = make_float2(0.f, 0.f);
+                }
+            };
+            put(accX, 0);
+            put(accY, 1);
+            put(accZ, 2);
+            if (p.S != nullptr && !nof) {
+                // F(Q): transpose through the record buffer just consumed
+                float *tr = tab(b) + warp * (C * 33);
+#pragma unroll
+                for (int m = 0; m < C; ++m) {
+                    tr[m * 33 + lane] = m >= H ? accF[m % H].y : accF[m % H].x;
+                }
+                __syncwarp();
+                const int bin = m0 + lane;
+                if (lane < C && bin < p.nq) {
+                    double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                    for (int a = 0; a < 32; a += 2) {
+                        v0 += (double)tr[lane * 33 + a];
+                        v1 += (double)tr[lane * 33 + a + 1];
+                    }
+                    srun += (v0 + v1) * (double)(fa[bin] * fb[bin]);
+                }
+#pragma unroll
+                for (int k = 0; k < H; ++k) accF[k] = make_float2(0.f, 0.f);
+            }
+        }
+        parked = true;
+        jacc = 0;
+        __syncthreads();  // buffer b is produced into at the start of the next tile
+      }
+    };
+    [[maybe_unused]] auto flush_rows = [&](bool add) {
+      if constexpr (MODE == MODE_GRAD) {
+        if (parked) {  // add the parked partial sums of this run back
+            __threadfence();  // this thread's REDs have been performed (L2); loads bypass L1
+            const float2 *scr = reinterpret_cast<const float2 *>(p.Gscr) +
+                                (size_t)slot * (3 * H) * blockDim.x + threadIdx.x;
+            auto back = [&](float2(&acc)[MODE == MODE_GRAD ? H : 1], int comp) {
+                float2 t[H];  // all loads of a component in flight together
+#pragma unroll
+                for (int k = 0; k < H; ++k) t[k] = __ldcg(scr + (size_t)(comp * H + k) * blockDim.x);
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    acc[k].x += t[k].x;
+                    acc[k].y += t[k].y;
+                }
+            };
+            back(accX, 0);
+            back(accY, 1);
+            back(accZ, 2);
+        }
+        float *tr = reinterpret_cast<float *>(smem_raw) + warp * (C * 33);
+        const int bin = m0 + lane;
+        const bool binok = lane < C && bin < p.nq;
+        const float sc = binok ? fa[bin] * fb[bin] * inv_na[bin] : 0.f;
+        float *Gp = dest < 0 ? reinterpret_cast<float *>(p.G)
+                             : reinterpret_cast<float *>(p.Gside) + (size_t)dest * (32 * 3) * p.nq;
+        auto put = [&](const float2(&acc)[MODE == MODE_GRAD ? H : 1], int comp) {
+#pragma unroll
+            for (int m = 0; m < C; ++m) tr[m * 33 + lane] = m >= H ? acc[m % H].y : acc[m % H].x;
+            __syncwarp();
+#pragma unroll 4
+            for (int a = 0; a < 32; ++a) {
+                const int oa = dest < 0 ? __shfl_sync(0xffffffffu, oi, a) : a;
+                if (binok && oa >= 0) {
+                    float *q = Gp + ((size_t)oa * 3 + comp) * p.nq + bin;
+                    float v = tr[lane * 33 + a] * sc;
+                    if (add) v += *q;
+                    *q = v;
                 }
             }
-        }
-        if (p.S != nullptr && !nof) {
-            // S[bin] += sum over the 32 atoms i of this warp.  Transpose the
-            // warp's (bin x atom) accumulators through its own slice of the
-            // (now idle) pair-record buffers, so that lane L sums bin m0 + L
-            // in float64 and the warp issues ONE 32-wide atomic instead of 32
-            // butterfly reductions (the flush was 1/3 of the instructions of a
-            // 32 x 32-atom item).
-            static_assert(C <= 32, "one lane per bin of the chunk");
-            float *tr = reinterpret_cast<float *>(smem_raw) + warp * (C * 33);
-#pragma unroll
-            for (int m = 0; m < C; ++m) {
-                const int k = m % H;
-                tr[m * 33 + lane] = m >= H ? accF[k].y : accF[k].x;
-            }
             __syncwarp();
-            const int bin = m0 + lane;
-            if (lane < C && bin < p.nq) {
+        };
+        put(accX, 0);
+        put(accY, 1);
+        put(accZ, 2);
+        if (p.S != nullptr) {
+#pragma unroll
+            for (int m = 0; m < C; ++m) tr[m * 33 + lane] = m >= H ? accF[m % H].y : accF[m % H].x;
+            __syncwarp();
+            if (binok) {
                 double v0 = 0.0, v1 = 0.0;
 #pragma unroll
                 for (int a = 0; a < 32; a += 2) {
                     v0 += (double)tr[lane * 33 + a];
                     v1 += (double)tr[lane * 33 + a + 1];
                 }
-                atomicAdd(&p.S[bin], fweight * (v0 + v1) * (double)(fa[bin] * fb[bin]));
+                srun += (v0 + v1) * (double)(fa[bin] * fb[bin]);
+            }
+            __syncwarp();
+        }
+      }
+    };
+
+    // warps w and w+4 share a scheduler: one produces the next tile before its
+    // consume phase, the other after it, so one of them always feeds the FP32 pipe
+    // (measured: pairing by warp & 1, or no stagger at all, costs 6 %)
+    const bool early = ((warp >> 2) & 1) == 0;
+    bool first = true;
+    for (;;) {
+        const int ntile = (sg.jend - sg.jbegin) / TJ2;  // segments are multiples of 32
+        produce(sg.jbegin, 0);
+        __syncthreads();
+        for (int t = 0; t < ntile; ++t) {
+            const int b = t & 1;
+            const bool has_next = t + 1 < ntile;
+            const int jnext = sg.jbegin + (t + 1) * TJ2;
+            if (has_next && early) produce(jnext, b ^ 1);
+            if (active) {
+                if constexpr (MODE == MODE_GRAD && CHEB) {
+                    if (nof) consume(std::true_type{}, b);
+                    else consume(std::false_type{}, b);
+                } else {
+                    consume(std::false_type{}, b);
+                }
+            }
+            if (has_next && !early) produce(jnext, b ^ 1);
+            __syncthreads();
+            if constexpr (MODE == MODE_FORCE) {
+                if (!diag) {
+                    reduce_j(b, sg.jbegin + t * TJ2);
+                    __syncthreads();  // records of buffer b are rewritten next iteration
+                }
+            }
+            if constexpr (MODE == MODE_GRAD) {
+                jacc += TJ2;
+                if (p.acc_j > 0 && jacc >= p.acc_j && has_next) park(b);
             }
         }
+        if constexpr (MODE != MODE_GRAD) {
+            break;
+        } else {
+            ++seg;
+            const bool last = seg >= seg_end;
+            if ((sg.info & SEG_FLUSH) || last) {
+                if (active) {
+                    flush_rows(!first);
+#pragma unroll
+                    for (int k = 0; k < H; ++k) {
+                        accF[k] = make_float2(0.f, 0.f);
+                        accX[k] = make_float2(0.f, 0.f);
+                        accY[k] = make_float2(0.f, 0.f);
+                        accZ[k] = make_float2(0.f, 0.f);
+                    }
+                }
+                first = false;
+                parked = false;
+                jacc = 0;
+                if (!last) __syncthreads();  // the scratch is the next segment's record buffer
+            }
+            if (last) break;
+            sg = p.segs[seg];
+            diag = (sg.info & ITEM_DIAG) != 0;
+            nof = p.grad_split && ((sg.info & ITEM_NOF) != 0 || p.S == nullptr);
+            fw = (diag || !p.grad_split) ? 0.5f : 1.f;
+            fb = ftab + (size_t)(sg.info & 0xffff) * p.qp;
+        }
+    }
+
+    if constexpr (MODE == MODE_GRAD) {
+        if (slot >= 0) {  // every thread has read its parked sums back: free the slot
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicExch(&p.slot_busy[slot], 0);
+            }
+        }
+    }
+    if (!active) return;
+    if constexpr (MODE == MODE_GRAD) {
+        // per-job partial of the F(Q) pair sum; reduce_spart_kernel adds the jobs
+        // in a fixed order
+        const int bin = m0 + lane;
+        if (p.S != nullptr && lane < C && bin < p.nq) p.S[(size_t)blockIdx.x * p.qp + bin] = srun;
+    } else if constexpr (MODE == MODE_FORCE) {
+        if (oi >= 0) {
+            atomicAdd(&p.force[(size_t)oi * 3 + 0], (double)fix);
+            atomicAdd(&p.force[(size_t)oi * 3 + 1], (double)fiy);
+            atomicAdd(&p.force[(size_t)oi * 3 + 2], (double)fiz);
+        }
+    } else {
+        const double fweight = diag ? 0.5 : 1.0;
+        // S[bin] += sum over the 32 atoms i of this warp.  Transpose the
+        // warp's (bin x atom) accumulators through its own slice of the
+        // (now idle) pair-record buffers, so that lane L sums bin m0 + L
+        // in float64 and the warp issues ONE 32-wide atomic instead of 32
+        // butterfly reductions (the flush was 1/3 of the instructions of a
+        // 32 x 32-atom item).
+        float *tr = reinterpret_cast<float *>(smem_raw) + warp * (C * 33);
+#pragma unroll
+        for (int m = 0; m < C; ++m) {
+            const int k = m % H;
+            tr[m * 33 + lane] = m >= H ? accF[k].y : accF[k].x;
+        }
+        __syncwarp();
+        const int bin = m0 + lane;
+        if (lane < C && bin < p.nq) {
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int a = 0; a < 32; a += 2) {
+                v0 += (double)tr[lane * 33 + a];
+                v1 += (double)tr[lane * 33 + a + 1];
+            }
+            atomicAdd(&p.S[bin], fweight * (v0 + v1) * (double)(fa[bin] * fb[bin]));
+        }
+    }
+}
+
+// G rows of the split i-tiles = sum of their pieces in the side buffer, in a
+// fixed order.  One block per split row (32 atoms x 3 x nq values).
+template <typename TG>
+__global__ void __launch_bounds__(256) rows_fixup_kernel(const RowFix *__restrict__ fix,
+                                                         const int *__restrict__ orig,
+                                                         const TG *__restrict__ side, int nq,
+                                                         TG *__restrict__ G)
+{
+    const RowFix f = fix[blockIdx.x];
+    const int per_atom = 3 * nq;
+    for (int e = threadIdx.x; e < 32 * per_atom; e += blockDim.x) {
+        const int a = e / per_atom, rem = e - a * per_atom;
+        const int oa = orig[f.itile * TILE_I + a];
+        if (oa < 0) continue;
+        TG v = side[((size_t)f.d0 * 32 + a) * per_atom + rem];
+        for (int d = f.d0 + 1; d < f.d1; ++d) v += side[((size_t)d * 32 + a) * per_atom + rem];
+        G[(size_t)oa * per_atom + rem] = v;
+    }
+}
+
+// S[m] = sum over the row jobs of their partial sums, fixed order: thread
+// (tx, ty) adds jobs ty, ty + 32, ... of bin 32 blockIdx.x + tx, then the 32
+// slices are added in order.
+__global__ void __launch_bounds__(1024) reduce_spart_kernel(const double *__restrict__ part,
+                                                            int njobs, int nq, int qp,
+                                                            double *__restrict__ S)
+{
+    __shared__ double sl[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int m = blockIdx.x * 32 + tx;
+    double acc = 0.0;
+    if (m < nq)
+        for (int j = ty; j < njobs; j += 32) acc += part[(size_t)j * qp + m];
+    sl[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && m < nq) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += sl[k][tx];
+        S[m] = t;
     }
 }
 

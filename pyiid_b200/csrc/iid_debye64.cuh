@@ -40,21 +40,35 @@ __global__ void __launch_bounds__(MAXT, 1) debye64_kernel(const DebyeParams p)
     const int m0 = (chunk0 + warp) * C;
     const bool active = m0 < p.nq;
 
-    const WorkItem it = p.items[p.item_begin + (int64_t)blockIdx.x * p.item_stride];
-    const bool diag = (it.info & ITEM_DIAG) != 0;
-    // square list: items above the diagonal (or all, when no F(Q) is wanted)
-    // are gradient only, see iid_debye2.cuh
-    const bool nof = MODE == MODE_GRAD && p.grad_split &&
-                     ((it.info & ITEM_NOF) != 0 || p.S == nullptr);
-    const int btype = it.info & 0xffff;
-    const int atype = p.tile_type[it.itile];
-    const int gi = it.itile * TILE_I + lane;
+    // MODE_GRAD: a row job (i-tile, consecutive j segments), see iid_debye.cuh;
+    // the other modes: one work item = one segment
+    int itile, seg = 0, seg_end = 1, dest = -1;
+    RowSeg sg;
+    if constexpr (MODE == MODE_GRAD) {
+        const RowJob job = p.jobs[blockIdx.x];
+        itile = job.itile;
+        seg = job.seg_begin;
+        seg_end = job.seg_end;
+        dest = job.dest;
+        sg = p.segs[seg];
+    } else {
+        const WorkItem it = p.items[p.item_begin + (int64_t)blockIdx.x * p.item_stride];
+        itile = it.itile;
+        sg.jbegin = it.jbegin;
+        sg.jend = it.jend;
+        sg.info = it.info;
+    }
+    bool diag = (sg.info & ITEM_DIAG) != 0;
+    bool nof = MODE == MODE_GRAD && p.grad_split && ((sg.info & ITEM_NOF) != 0 || p.S == nullptr);
+    double fw = (MODE == MODE_GRAD && (diag || !p.grad_split)) ? 0.5 : 1.0;
+    const int atype = p.tile_type[itile];
+    const int gi = itile * TILE_I + lane;
     const double xi = p.x[gi], yi = p.y[gi], zi = p.z[gi];
     const bool vi = p.valid[gi] != 0.f;
 
     const double *ftab = reinterpret_cast<const double *>(p.ftab);
     const double *fa = ftab + (size_t)atype * p.qp;
-    const double *fb = ftab + (size_t)btype * p.qp;
+    const double *fb = ftab + (size_t)(sg.info & 0xffff) * p.qp;
     const double *inv_na = reinterpret_cast<const double *>(p.inv_na);
 
     constexpr int NPAIR = TJ * 32;
@@ -124,7 +138,7 @@ __global__ void __launch_bounds__(MAXT, 1) debye64_kernel(const DebyeParams p)
             s *= b3;
             c *= b3;
             T[pr] = make_double2(cth, sth);
-            T[NPAIR + pr] = make_double2(p.qbin * r, r2);
+            T[NPAIR + pr] = make_double2(p.qbin * r, r2 * fw);
             T[2 * NPAIR + pr] = make_double2(dx, dy);
             T[3 * NPAIR + pr] = make_double2(dz, 0.0);
             for (int w = 0; w < nwarp; ++w) {
@@ -252,75 +266,139 @@ __global__ void __launch_bounds__(MAXT, 1) debye64_kernel(const DebyeParams p)
         }
     };
 
-    const int ntile = (it.jend - it.jbegin) / TJ;  // slabs are multiples of 32
-    const bool early = ((warp >> 2) & 1) == 0;
-    produce(it.jbegin, 0);
-    __syncthreads();
-    for (int t = 0; t < ntile; ++t) {
-        const int b = t & 1;
-        const bool has_next = t + 1 < ntile;
-        const int jnext = it.jbegin + (t + 1) * TJ;
-        if (has_next && early) produce(jnext, b ^ 1);
-        if (active) {
-            if constexpr (MODE == MODE_GRAD) {
-                if (nof) consume(std::true_type{}, b);
-                else consume(std::false_type{}, b);
-            } else {
-                consume(std::false_type{}, b);
-            }
-        }
-        if (has_next && !early) produce(jnext, b ^ 1);
-        __syncthreads();
-        if constexpr (MODE == MODE_FORCE) {
-            if (!diag) {
-                reduce_j(b, it.jbegin + t * TJ);
-                __syncthreads();
-            }
-        }
-    }
-
-    if (!active) return;
+    // ---- MODE_GRAD flush: plain coalesced stores of the rows this block owns
+    // (see iid_debye2.cuh)
+    static_assert(C <= 32, "one lane per bin of the chunk");
     const int oi = p.orig[gi];
-    if constexpr (MODE == MODE_FORCE) {
-        if (oi >= 0) {
-            atomicAdd(&p.force[(size_t)oi * 3 + 0], fix);
-            atomicAdd(&p.force[(size_t)oi * 3 + 1], fiy);
-            atomicAdd(&p.force[(size_t)oi * 3 + 2], fiz);
-        }
-    } else {
-        const double fweight = ((MODE == MODE_GRAD && !p.grad_split) || diag) ? 0.5 : 1.0;
-        double *G = reinterpret_cast<double *>(p.G);
-        if constexpr (MODE == MODE_GRAD) {
+    double srun = 0.0;
+    [[maybe_unused]] auto flush_rows = [&](bool add) {
+      if constexpr (MODE == MODE_GRAD) {
+        double *tr = reinterpret_cast<double *>(smem_raw64) + warp * (C * 33);
+        const int bin = m0 + lane;
+        const bool binok = lane < C && bin < p.nq;
+        const double sc = binok ? fa[bin] * fb[bin] * inv_na[bin] : 0.0;
+        double *Gp = dest < 0 ? reinterpret_cast<double *>(p.G)
+                              : reinterpret_cast<double *>(p.Gside) + (size_t)dest * (32 * 3) * p.nq;
+        auto put = [&](const double(&acc)[C], int comp) {
 #pragma unroll
-            for (int k = 0; k < C; ++k) {
-                const int bin = m0 + k;
-                if (bin < p.nq && oi >= 0) {  // bin < nq is warp-uniform
-                    const double sc = fa[bin] * fb[bin] * inv_na[bin];
-                    double *row = G + (size_t)oi * 3 * p.nq + bin;
-                    atomicAdd(row, accX[k] * sc);
-                    atomicAdd(row + p.nq, accY[k] * sc);
-                    atomicAdd(row + 2 * (size_t)p.nq, accZ[k] * sc);
+            for (int k = 0; k < C; ++k) tr[k * 33 + lane] = acc[k];
+            __syncwarp();
+#pragma unroll 4
+            for (int a = 0; a < 32; ++a) {
+                const int oa = dest < 0 ? __shfl_sync(0xffffffffu, oi, a) : a;
+                if (binok && oa >= 0) {
+                    double *q = Gp + ((size_t)oa * 3 + comp) * p.nq + bin;
+                    double v = tr[lane * 33 + a] * sc;
+                    if (add) v += *q;
+                    *q = v;
                 }
             }
-        }
-        if (p.S != nullptr && !nof) {
-            // transpose the warp's (bin x atom) accumulators through its slice of
-            // the idle record buffers: lane L sums bin m0 + L, one atomic per bin
-            static_assert(C <= 32, "one lane per bin of the chunk");
-            double *tr = reinterpret_cast<double *>(smem_raw64) + warp * (C * 33);
+            __syncwarp();
+        };
+        put(accX, 0);
+        put(accY, 1);
+        put(accZ, 2);
+        if (p.S != nullptr) {
 #pragma unroll
             for (int k = 0; k < C; ++k) tr[k * 33 + lane] = accF[k];
             __syncwarp();
-            const int bin = m0 + lane;
-            if (lane < C && bin < p.nq) {
+            if (binok) {
                 double v0 = 0.0, v1 = 0.0;
 #pragma unroll
                 for (int a = 0; a < 32; a += 2) {
                     v0 += tr[lane * 33 + a];
                     v1 += tr[lane * 33 + a + 1];
                 }
-                atomicAdd(&p.S[bin], fweight * (v0 + v1) * (fa[bin] * fb[bin]));
+                srun += (v0 + v1) * (fa[bin] * fb[bin]);
             }
+            __syncwarp();
+        }
+      }
+    };
+
+    const bool early = ((warp >> 2) & 1) == 0;
+    bool first = true;
+    for (;;) {
+        const int ntile = (sg.jend - sg.jbegin) / TJ;  // segments are multiples of 32
+        produce(sg.jbegin, 0);
+        __syncthreads();
+        for (int t = 0; t < ntile; ++t) {
+            const int b = t & 1;
+            const bool has_next = t + 1 < ntile;
+            const int jnext = sg.jbegin + (t + 1) * TJ;
+            if (has_next && early) produce(jnext, b ^ 1);
+            if (active) {
+                if constexpr (MODE == MODE_GRAD) {
+                    if (nof) consume(std::true_type{}, b);
+                    else consume(std::false_type{}, b);
+                } else {
+                    consume(std::false_type{}, b);
+                }
+            }
+            if (has_next && !early) produce(jnext, b ^ 1);
+            __syncthreads();
+            if constexpr (MODE == MODE_FORCE) {
+                if (!diag) {
+                    reduce_j(b, sg.jbegin + t * TJ);
+                    __syncthreads();
+                }
+            }
+        }
+        if constexpr (MODE != MODE_GRAD) {
+            break;
+        } else {
+            ++seg;
+            const bool last = seg >= seg_end;
+            if ((sg.info & SEG_FLUSH) || last) {
+                if (active) {
+                    flush_rows(!first);
+#pragma unroll
+                    for (int k = 0; k < C; ++k) {
+                        accF[k] = 0.0;
+                        accX[k] = 0.0;
+                        accY[k] = 0.0;
+                        accZ[k] = 0.0;
+                    }
+                }
+                first = false;
+                if (!last) __syncthreads();
+            }
+            if (last) break;
+            sg = p.segs[seg];
+            diag = (sg.info & ITEM_DIAG) != 0;
+            nof = p.grad_split && ((sg.info & ITEM_NOF) != 0 || p.S == nullptr);
+            fw = (diag || !p.grad_split) ? 0.5 : 1.0;
+            fb = ftab + (size_t)(sg.info & 0xffff) * p.qp;
+        }
+    }
+
+    if (!active) return;
+    if constexpr (MODE == MODE_GRAD) {
+        const int bin = m0 + lane;
+        if (p.S != nullptr && lane < C && bin < p.nq) p.S[(size_t)blockIdx.x * p.qp + bin] = srun;
+    } else if constexpr (MODE == MODE_FORCE) {
+        if (oi >= 0) {
+            atomicAdd(&p.force[(size_t)oi * 3 + 0], fix);
+            atomicAdd(&p.force[(size_t)oi * 3 + 1], fiy);
+            atomicAdd(&p.force[(size_t)oi * 3 + 2], fiz);
+        }
+    } else {
+        const double fweight = diag ? 0.5 : 1.0;
+        // transpose the warp's (bin x atom) accumulators through its slice of
+        // the idle record buffers: lane L sums bin m0 + L, one atomic per bin
+        double *tr = reinterpret_cast<double *>(smem_raw64) + warp * (C * 33);
+#pragma unroll
+        for (int k = 0; k < C; ++k) tr[k * 33 + lane] = accF[k];
+        __syncwarp();
+        const int bin = m0 + lane;
+        if (lane < C && bin < p.nq) {
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int a = 0; a < 32; a += 2) {
+                v0 += tr[lane * 33 + a];
+                v1 += tr[lane * 33 + a + 1];
+            }
+            atomicAdd(&p.S[bin], fweight * (v0 + v1) * (fa[bin] * fb[bin]));
         }
     }
 }

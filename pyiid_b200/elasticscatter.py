@@ -26,7 +26,7 @@ import math
 import numpy as np
 
 from . import formfactors
-from .backend import Backend
+from .backend import Backend, visible_devices, _dist_state
 
 __all__ = ['ElasticScatter', 'wrap_atoms']
 
@@ -66,6 +66,7 @@ class ElasticScatter(object):
         self.pdf_qbin = None
         self.precision = precision
         self.device = device
+        self._device_sel = device
         self._backends = {}
         self.update_experiment(exp_dict)
         self.fq = self._wrap_fq
@@ -87,7 +88,7 @@ class ElasticScatter(object):
     def _be(self, slot):
         be = self._backends.get(slot)
         if be is None:
-            be = Backend.get(self.precision, self.device, slot)
+            be = Backend.get(self.precision, self._device_sel, slot)
             self._backends[slot] = be
         return be
 
@@ -102,8 +103,15 @@ class ElasticScatter(object):
 
     def set_processor(self, processor=None, kernel_type='flat'):
         """Bind ``self.fq``, ``self.grad``, ``self.grad_pdf`` (reference
-        ``__init__.py:206-292``).  Every GPU processor name maps onto the
-        B200 path; ``'CPU'`` is refused."""
+        ``__init__.py:206-292``); ``'CPU'`` is refused.
+
+        ``None`` probes like the reference (``:228-233``, best first):
+        ``'Multi-GPU'`` = every GPU of the box from THIS process
+        (``iid_create_multi``; the reference's ``gpu_wrap.py:287-314``) when
+        more than one is visible and no ``device`` was pinned, else one GPU
+        (``'B200'``).  Under ``torchrun`` (one process per GPU,
+        ``torch.distributed`` initialised) every name binds this rank's GPU and
+        the ranks shard the work (``'MPI-GPU'``)."""
         if processor is not None and processor not in self.avail_pro:
             if processor in ('CPU', 'Serial-CPU'):
                 raise NotImplementedError(
@@ -113,7 +121,17 @@ class ElasticScatter(object):
         self.fq = self._wrap_fq
         self.grad = self._wrap_fq_grad
         self.grad_pdf = self._grad_pdf
-        self.processor = 'B200'
+        world = _dist_state()[1]
+        many = self.device is None and visible_devices() > 1
+        if world > 1:
+            self._device_sel, self.processor = self.device, 'MPI-GPU'
+        elif processor == 'B200' or not many:
+            if processor in ('Multi-GPU', 'MPI-GPU') and self.verbose:
+                print('one GPU visible (or a device pinned): %s runs on one device' % processor)
+            self._device_sel, self.processor = self.device, 'B200'
+        else:
+            self._device_sel, self.processor = 'multi', 'Multi-GPU'
+        self._backends = {}
         self.alg = 'flat'
         return True
 
