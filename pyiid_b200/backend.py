@@ -13,6 +13,7 @@ PyTorch is used only when world_size > 1 (device buffers for the collective);
 the single-GPU path talks to the library with numpy host buffers.
 """
 import atexit
+import collections
 import ctypes
 import math
 import os
@@ -115,11 +116,14 @@ class Backend(object):
     the reference's ``gpu_wrap.py`` thread-per-GPU farm)."""
     _instances = {}
 
+    MAX_PER_KEY = 4  # live handles per (precision, device, Q grid)
+
     @classmethod
     def close_all(cls):
         """Destroy every native handle (registered with atexit)."""
-        for inst in list(cls._instances.values()):
-            inst.close()
+        for pool in list(cls._instances.values()):
+            for inst in pool.values():
+                inst.close()
         cls._instances.clear()
 
     def close(self):
@@ -128,7 +132,12 @@ class Backend(object):
             self.h = ctypes.c_void_p()
 
     @classmethod
-    def get(cls, precision='fp32', device=None, slot='fq'):
+    def get(cls, precision='fp32', device=None, slot='fq', owner=None):
+        """The handle of ``owner`` (an ElasticScatter object's id) for this
+        precision, device and Q grid.  Every owner gets its own handle, so two
+        ElasticScatter objects with different structures or experiments do not
+        re-upload on every alternate call; beyond MAX_PER_KEY the least
+        recently used handle is handed on."""
         if device == 'multi' and _dist_state()[1] > 1:
             device = None  # one process per GPU already: this rank's device
         if device is None:
@@ -144,10 +153,14 @@ class Backend(object):
         # get_fq / get_pdf calls do not re-upload the structure
         device = device if device == 'multi' else int(device)
         key = (precision, device, slot)
-        inst = cls._instances.get(key)
+        pool = cls._instances.setdefault(key, collections.OrderedDict())
+        inst = pool.pop(owner, None)
         if inst is None:
-            inst = cls(precision, device)
-            cls._instances[key] = inst
+            if len(pool) < cls.MAX_PER_KEY:
+                inst = cls(precision, device)
+            else:
+                _, inst = pool.popitem(last=False)
+        pool[owner] = inst  # most recently used last
         return inst
 
     def __init__(self, precision='fp32', device=0):
@@ -412,7 +425,7 @@ class Backend(object):
                 self.h, pos.ctypes.data, tptr, pot, float(conv), out.ctypes.data,
                 forces.ctypes.data if want_forces else None,
                 pdf.ctypes.data if want_pdf else None))
-            self._target_key = tkey
+            self._target_done(target, tkey)
             if self._restraints:
                 self._read_restraint_energy()
             return out[0], out[1], forces, pdf
@@ -461,13 +474,22 @@ class Backend(object):
 
     def _target_ptr(self, target):
         """(pointer or None, key): None when this target is already resident on
-        the device."""
-        if target is self._last_target:
-            tkey = self._target_key  # same (read-only) array object as last time
-        else:
-            tkey = target.tobytes()
+        the device.  A READ-ONLY array object seen before is recognised by
+        identity (Calc1D keeps its target that way: the sampler's hot path);
+        a writable one may have been modified in place since, so its content
+        is compared with the private copy of what was uploaded."""
+        if target is self._last_target and not target.flags.writeable:
+            return None, self._target_key
+        if self._target_key is not None and target.shape == self._target_key.shape and \
+                np.array_equal(target, self._target_key):
+            return None, self._target_key
+        return target.ctypes.data, target
+
+    def _target_done(self, target, tkey):
+        """The native call succeeded: remember what is resident."""
+        if tkey is not self._target_key:
+            self._target_key = np.array(tkey, dtype=np.float64)  # private copy
         self._last_target = target
-        return (None if tkey == self._target_key else target.ctypes.data), tkey
 
     # -- device-resident sampler states (pyiid/sim/__init__.py:10-38) ------------
     def sampler_setup(self, n_slots, masses, cell_centre):
@@ -511,7 +533,7 @@ class Backend(object):
         check(self.lib.iid_leapfrog_host(
             self.h, int(src), int(dst), float(step), int(bool(center)), tptr,
             POTENTIALS[potential], float(conv), out.ctypes.data, q.ctypes.data, p.ctypes.data))
-        self._target_key = tkey
+        self._target_done(target, tkey)
         return out[0], out[1], out[4], out[5], q, p
 
     # -- spring restraints (calc/spring_calc.py) -------------------------------

@@ -122,7 +122,11 @@ class Calc1D(Calculator):
             raise NotImplementedError('Need functions which return the '
                                       'simulated data associated with the '
                                       'experiment and its gradient')
-        self.target_data = np.asarray(target_data)
+        # a private read-only copy: the device-resident target is recognised by
+        # object identity on the sampler's hot path, which is only safe if the
+        # array cannot change in place (assign a new array to replace it)
+        self.target_data = np.array(target_data)
+        self.target_data.flags.writeable = False
         self.exp_function = exp_function
         self.exp_grad_function = exp_grad_function
         self.scale = 1

@@ -1083,10 +1083,10 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     if (rows) {
         if (h->n_fixes > 0) {
             if (h->precision == IID_FP32)
-                rows_fixup_kernel<float><<<(unsigned)h->n_fixes, 256, 0, st>>>(
+                rows_fixup_kernel<float><<<dim3((unsigned)h->n_fixes, FIX_SPLIT), 256, 0, st>>>(
                     h->fixes, h->orig, (const float *)h->Gside, (int)h->nq, (float *)G);
             else
-                rows_fixup_kernel<double><<<(unsigned)h->n_fixes, 256, 0, st>>>(
+                rows_fixup_kernel<double><<<dim3((unsigned)h->n_fixes, FIX_SPLIT), 256, 0, st>>>(
                     h->fixes, h->orig, (const double *)h->Gside, (int)h->nq, (double *)G);
             ++h->launches;
             CU(cudaGetLastError());
@@ -1106,8 +1106,9 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
 // (O(N^2)); otherwise the direct O(N^2 Q) kernel.
 static int launch_force(iid_handle *h, const double *wq, double *force, cudaStream_t st)
 {
+    // (phi_table_kernel keeps one weight per Q bin in dynamic shared memory)
     const bool table = h->use_force_table && h->precision == IID_FP32 && h->ntypes <= 4 &&
-                       h->n >= h->force_table_min_n;
+                       h->n >= h->force_table_min_n && h->nq * sizeof(double) <= 48 * 1024;
     if (!table) return launch_debye(h, MODE_FORCE, nullptr, nullptr, wq, force, st);
     const size_t tstride = PHI_KMAX + 2 * PHI_PAD;
     if (!h->phi_tab) {
@@ -1132,7 +1133,8 @@ static int launch_force(iid_handle *h, const double *wq, double *force, cudaStre
             std::max(1, std::min(np / TILE_I, (4 * h->sm_count + mine - 1) / mine));
         force_table_kernel<<<dim3((unsigned)mine, (unsigned)jsplit), FT_BLOCK, 0, st>>>(
             h->x, h->y, h->z, h->valid, h->orig, h->tile_type, np, E, h->phi_info, h->phi_tab,
-            jsplit, h->rank, h->world, force);
+            jsplit, h->rank, h->world, force, wq, (const float *)h->ftab, (const float *)h->inv_na,
+            (int)h->nq, (int)h->qp, h->qbin);
     }
     h->launches += 3;
     CU(cudaGetLastError());

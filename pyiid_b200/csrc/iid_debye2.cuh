@@ -444,7 +444,12 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
       if constexpr (MODE == MODE_GRAD) {
         if (slot < 0) {
             if (threadIdx.x == 0) {
-                int s0 = (int)((blockIdx.x * 7u + blockIdx.y) % (unsigned)p.n_slots), got = -1;
+                // start at this SM's own slots: consecutive blocks of an SM reuse the
+                // same slot, so the scratch in use (one slot per resident block)
+                // stays in the L2 instead of wandering over all the slots
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                int s0 = (int)((smid * 4u) % (unsigned)p.n_slots), got = -1;
                 while (got < 0)
                     for (int k = 0; k < p.n_slots && got < 0; ++k) {
                         const int t = (s0 + k) % p.n_slots;
@@ -680,6 +685,7 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
 
 // G rows of the split i-tiles = sum of their pieces in the side buffer, in a
 // fixed order.  One block per split row (32 atoms x 3 x nq values).
+constexpr int FIX_SPLIT = 8;  // blocks per split row (4 atoms each)
 template <typename TG>
 __global__ void __launch_bounds__(256) rows_fixup_kernel(const RowFix *__restrict__ fix,
                                                          const int *__restrict__ orig,
@@ -688,8 +694,10 @@ __global__ void __launch_bounds__(256) rows_fixup_kernel(const RowFix *__restric
 {
     const RowFix f = fix[blockIdx.x];
     const int per_atom = 3 * nq;
-    for (int e = threadIdx.x; e < 32 * per_atom; e += blockDim.x) {
-        const int a = e / per_atom, rem = e - a * per_atom;
+    constexpr int APB = TILE_I / FIX_SPLIT;
+    const int a0 = blockIdx.y * APB;
+    for (int e = threadIdx.x; e < APB * per_atom; e += blockDim.x) {
+        const int a = a0 + e / per_atom, rem = e % per_atom;
         const int oa = orig[f.itile * TILE_I + a];
         if (oa < 0) continue;
         TG v = side[((size_t)f.d0 * 32 + a) * per_atom + rem];

@@ -58,11 +58,14 @@ __global__ void phi_grid_kernel(const double *__restrict__ x, const double *__re
             d2 += e * e;
         }
         const double rmax = sqrt(d2) * 1.0000001 + 1e-9;  // longest possible pair distance
-        double h = h_target;
-        if (rmax / h > (double)(PHI_KMAX - 4)) h = rmax / (double)(PHI_KMAX - 4);
+        // the grid step is never widened (the interpolation error grows like
+        // (Q_max h)^4): a structure whose bounding-box diagonal exceeds the
+        // table (524 A at Q_max = 25) has its distant pairs summed directly
+        // over the Q bins by force_table_kernel
+        const double h = h_target;
         info[0] = h;
         info[1] = 1.0 / h;
-        info[2] = ceil(rmax / h) + 2.0;
+        info[2] = fmin(ceil(rmax / h) + 2.0, (double)(PHI_KMAX - 4));
     }
 }
 
@@ -128,6 +131,29 @@ __global__ void __launch_bounds__(128) phi_table_kernel(const double *__restrict
     }
 }
 
+// Phi_ab(r) summed directly over the Q bins (float64 rotation recurrence): the
+// pairs beyond the tabulated range.
+__device__ double phi_direct(double r, int a, int b, const double *__restrict__ wq,
+                             const float *__restrict__ ftab, const float *__restrict__ inv_na,
+                             int nq, int qp, double qbin)
+{
+    const double turns = qbin * r * 0.15915494309189533577;
+    double sth, cth;
+    sincospi(2.0 * (turns - rint(turns)), &sth, &cth);
+    double s = 0.0, c = 1.0, mk = 0.0, phi = 0.0;
+    const double kap = qbin * r;
+    for (int m = 0; m < nq; ++m) {
+        const double w = wq[m] * (double)ftab[(size_t)a * qp + m] *
+                         (double)ftab[(size_t)b * qp + m] * (double)inv_na[m];
+        phi = fma(w, fma(mk, c, -s), phi);
+        const double sn = fma(s, cth, c * sth);
+        c = fma(c, cth, -(s * sth));
+        s = sn;
+        mk += kap;
+    }
+    return phi / (r * r * r);
+}
+
 // force[i] = sum_j Phi_{ab}(r_ij) (q_j - q_i): thread = atom i (sorted/padded
 // order), the j range [jbegin, jend) of this block row is staged through shared
 // memory.  Rows are split over blockIdx.y / ranks; partials meet by atomicAdd.
@@ -137,7 +163,8 @@ __global__ void __launch_bounds__(FT_BLOCK) force_table_kernel(
     const float *__restrict__ valid, const int *__restrict__ orig,
     const int *__restrict__ tile_type, int np, int ntypes, const double *__restrict__ info,
     const float *__restrict__ tab, int jsplit, int row_begin, int row_stride,
-    double *__restrict__ force)
+    double *__restrict__ force, const double *__restrict__ wq, const float *__restrict__ ftab,
+    const float *__restrict__ inv_na, int nq, int qp, double qbin)
 {
     __shared__ double sx[FT_BLOCK], sy[FT_BLOCK], sz[FT_BLOCK];
     __shared__ int st[FT_BLOCK];
@@ -147,6 +174,7 @@ __global__ void __launch_bounds__(FT_BLOCK) force_table_kernel(
     const double xi = gi < np ? x[gi] : 0.0, yi = gi < np ? y[gi] : 0.0, zi = gi < np ? z[gi] : 0.0;
     const int ta = gi < np ? tile_type[gi / TILE_I] : 0;
     const double inv_h = info[1];
+    const int klast = (int)info[2] - 2;  // last interval with all four nodes tabulated
     const size_t tstride = PHI_KMAX + 2 * PHI_PAD;
     const float *taba = tab + (size_t)ta * ntypes * tstride + PHI_PAD;
     // this block's share of the j atoms, in units of one 32-atom tile
@@ -175,14 +203,19 @@ __global__ void __launch_bounds__(FT_BLOCK) force_table_kernel(
             yv = yv * fma(-0.5 * r2, yv * yv, 1.5);
             yv = yv * fma(-0.5 * r2, yv * yv, 1.5);  // second Newton step: 1e-15
             const double tpos = r2 * yv * inv_h;
-            const int k = (int)tpos;
-            const double u = tpos - (double)k;
-            const float *tp = taba + (size_t)tb * tstride + k;
-            const double pm = tp[-1], p0 = tp[0], p1 = tp[1], p2 = tp[2];
-            // 4-point Lagrange on the uniform grid
-            const double um = u - 1.0, u2 = u - 2.0, up = u + 1.0;
-            const double phi = -(u * um * u2) * (1.0 / 6.0) * pm + (up * um * u2) * 0.5 * p0 -
-                               (up * u * u2) * 0.5 * p1 + (up * u * um) * (1.0 / 6.0) * p2;
+            double phi;
+            if (tpos < (double)klast) {
+                const int k = (int)tpos;
+                const double u = tpos - (double)k;
+                const float *tp = taba + (size_t)tb * tstride + k;
+                const double pm = tp[-1], p0 = tp[0], p1 = tp[1], p2 = tp[2];
+                // 4-point Lagrange on the uniform grid
+                const double um = u - 1.0, u2 = u - 2.0, up = u + 1.0;
+                phi = -(u * um * u2) * (1.0 / 6.0) * pm + (up * um * u2) * 0.5 * p0 -
+                      (up * u * u2) * 0.5 * p1 + (up * u * um) * (1.0 / 6.0) * p2;
+            } else {
+                phi = phi_direct(r2 * yv, ta, tb, wq, ftab, inv_na, nq, qp, qbin);
+            }
             fx = fma(phi, dx, fx);
             fy = fma(phi, dy, fy);
             fz = fma(phi, dz, fz);

@@ -88,7 +88,7 @@ class ElasticScatter(object):
     def _be(self, slot):
         be = self._backends.get(slot)
         if be is None:
-            be = Backend.get(self.precision, self._device_sel, slot)
+            be = Backend.get(self.precision, self._device_sel, slot, owner=id(self))
             self._backends[slot] = be
         return be
 
@@ -322,6 +322,8 @@ class ElasticScatter(object):
         """Gradient of the PDF, float64 [N, 3, R] (reference
         ``__init__.py:498-524``)."""
         self._ensure_wrapped(atoms)
+        if len(atoms) < 2:  # no pairs: zeros (k_max == 0, flat_multi_cpu_wrap.py:85-86)
+            return np.zeros((len(atoms), 3, len(self.get_r())))
         fq_grad = self.grad(atoms, self.pdf_qbin, 'PDF')
         qmin_bin = int(self.exp['qmin'] / self.pdf_qbin)
         fq_grad[:, :, :qmin_bin] = 0.

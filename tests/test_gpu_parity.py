@@ -254,6 +254,52 @@ def test_known_answers_on_device():
     assert abs(wrap_chi_sq(np.sin(x), np.sin(x))[0]) < 1e-15
 
 
+@pytest.mark.parametrize('potential', ['rw', 'chi_sq'])
+def test_anti_correlated_target_takes_the_scale_le_zero_branch(potential):
+    """master_kernel.py:229-230, 263-264, 338-340, 368-370: a target that is
+    anti-correlated with the model gives scale <= 0; get_rw then returns
+    (1, 1), get_chi_sq resets the scale to 1, and the gradients follow.  Driven
+    on the device through the fused path (potential_kernel + Q-space weights +
+    force pass) and through the generic wrap_* route (iid_rw_host)."""
+    atoms = structures.random_atoms(24, 11)
+    exp = oracle.DEFAULT_EXP
+    scat = ElasticScatter(precision='fp64')
+    gcalc = scat.get_pdf(atoms)
+    rs = np.random.RandomState(3)
+    target = -0.7 * gcalc + 0.05 * np.abs(gcalc).max() * rs.standard_normal(gcalc.shape)
+    assert oracle.get_scale(target, gcalc) < 0
+    pos = atoms.get_positions()
+    sp = atoms.get_array('PDF scatter')
+    oe, of, oscale = oracle.calc1d_energy_forces(pos, sp, exp, target, potential, 3., 'fp64')
+    assert oscale == 1
+    a = atoms.copy()
+    a.set_calculator(Calc1D(target_data=target, exp_function=scat.get_pdf,
+                            exp_grad_function=scat.get_grad_pdf, conv=3.,
+                            potential=potential))
+    e, f = a.get_potential_energy(), a.get_forces()
+    assert a.calc.scale == 1
+    assert abs(e - oe) < 1e-10 * abs(oe)
+    assert nerr(f, of) < 10 * TOL64
+    if potential == 'rw':
+        assert e == 3.0  # Rw = 1 exactly
+    # the generic route: potential and chain-rule contraction on host arrays
+    gp = scat.get_grad_pdf(atoms)
+    wrap, wgrad = (wrap_rw, wrap_grad_rw) if potential == 'rw' else (wrap_chi_sq, wrap_grad_chi_sq)
+    val, sc = wrap(gcalc, target)
+    assert sc == 1 and abs(3. * val - oe) < 1e-10 * abs(oe)
+    assert nerr(3. * wgrad(gp, gcalc, target), of) < 10 * TOL64
+    # FP32 mode, r-space weights (iid_potential + wq_kernel) as well
+    s32 = ElasticScatter(precision='fp32')
+    s32._ensure_wrapped(atoms)
+    be = s32._load(atoms, s32.pdf_qbin, 'PDF')
+    be.set_transform(exp['rstep'], s32.pdf_qbin, s32.get_r(), exp['qmin'])
+    for q in (1, 0):
+        be.set_option('qspace_wq', q)
+        e32, sc32, f32, _ = be.energy_forces(pos, target, potential, 3.)
+        assert sc32 == 1 and abs(e32 - oe) < TOL32 * abs(oe) and nerr(f32, of) < 5 * TOL32
+    be.set_option('qspace_wq', 1)
+
+
 # ---- size-independent properties at full size ---------------------------------------
 @pytest.fixture(scope='module')
 def big():
@@ -574,6 +620,48 @@ def test_fp32_f_of_q_against_oracle_at_2000_atoms():
     assert nerr(fq, oracle.experiment_fq(pos, sf, EXP, 'fp64', nthreads=8)) < TOL32
 
 
+def test_nuts_trajectory_equals_the_reference_samplers():
+    """The samples of the REFERENCE's NUTSCanonicalEnsemble source driving a
+    float64 oracle calculator (tests/golden/nuts_au55.npz, generated in the
+    build container by tests/golden/make_golden_nuts.py from
+    pyiid/sim/nuts_hmc.py:91-244 + pyiid/sim/__init__.py:10-38 as they lie in
+    the mount) against pyiid_b200.sim's NUTS on the B200 Calc1D, FP64 mode, same
+    seeds: Atoms-level path, array-level path and device-resident states."""
+    k = golden('nuts_au55')
+
+    def run(**kw):
+        atoms = structures.icosahedron('Au', 2)
+        atoms.set_positions(k['start_positions'])
+        scat = ElasticScatter(precision='fp64')
+        calc = Calc1D(target_data=k['target'], exp_function=scat.get_pdf,
+                      exp_grad_function=scat.get_grad_pdf, conv=float(k['conv']),
+                      potential='rw')
+        atoms.set_calculator(calc)
+
+        class Ensemble(sim.NUTSCanonicalEnsemble):
+            def _find_step_size(self, input_atoms, thermal_nrg=None, momentum=None):
+                return float(k['step'])  # the override the golden run needed
+
+        np.random.seed(int(k['np_seed']))
+        ens = Ensemble(atoms, temperature=float(k['temperature']),
+                       escape_level=int(k['escape_level']), seed=int(k['seed']), **kw)
+        traj, meta = ens.run(int(k['iterations']))
+        return traj, meta, ens
+
+    assert np.allclose(structures.icosahedron('Au', 2).get_masses(), k['masses'])
+    for kw in (dict(fast=False), dict(fast=True, device_states=False),
+               dict(fast=True, device_states=True)):
+        traj, meta, ens = run(**kw)
+        assert len(traj) == len(k['traj_positions']), kw
+        assert meta['accepted_samples'] == int(k['accepted_samples'])
+        assert meta['samples_total'] == int(k['samples_total'])
+        for a, q, p, e in zip(traj, k['traj_positions'], k['traj_momenta'], k['traj_energy']):
+            assert np.abs(a.get_positions() - q).max() < 1e-6, kw
+            assert np.abs(a.get_momenta() - p).max() < 1e-6 * max(1., np.abs(p).max()), kw
+            assert abs(a.get_potential_energy() - e) < 1e-7 * abs(e), kw
+        assert abs(ens.step_size - float(k['final_step_size'])) < 1e-6 * ens.step_size
+
+
 def test_array_level_nuts_equals_atoms_level_nuts():
     """The fast sampler path (plain arrays, one native call per leapfrog)
     reproduces the Atoms-level path: same random numbers, same trajectory."""
@@ -762,6 +850,43 @@ def test_tabulated_force_pass_equals_direct_force_pass():
     e, scale, f, _ = bp.energy_forces(g['positions'], g['target_pdf_f32'], 'rw', 1.0)
     bp.set_option('force_table_min_n', 600)
     assert nerr(f, g['rw_forces_f32']) < TOL32
+    # an extended structure: two clusters 700 A apart (beyond the 524 A the
+    # table covers at its fixed step): the distant pairs are summed directly
+    # over the Q bins, the grid step is never widened
+    far = structures.alloy_sphere(120, seed=8)
+    pos2 = np.vstack([far.get_positions(), far.get_positions()[::-1] + np.array([700., 0, 0])])
+    two = ase_shim.Atoms(numbers=np.concatenate([far.numbers, far.numbers[::-1]]),
+                         positions=pos2)
+    s2 = ElasticScatter(precision='fp32')
+    s2._ensure_wrapped(two)
+    b2 = s2._load(two, s2.pdf_qbin, 'PDF')
+    b2.set_transform(s2.exp['rstep'], s2.pdf_qbin, s2.get_r(), 0.0)
+    t2 = b2.pdf(pos2 * 1.01)
+    out = {}
+    for table in (1, 0):
+        b2.set_option('force_table', table)
+        b2.set_option('force_table_min_n', 2)
+        out[table] = b2.energy_forces(pos2, t2, 'rw', 100.)
+    b2.set_option('force_table', 1)
+    b2.set_option('force_table_min_n', 600)
+    assert nerr(out[1][2], out[0][2]) < 2e-6
+
+
+def test_two_scatter_objects_keep_their_own_handles():
+    """Two ElasticScatter objects with different structures / experiments do
+    not share (and ping-pong) one native handle."""
+    a1, a2 = structures.random_atoms(30, 1), structures.random_atoms(45, 2)
+    s1, s2 = ElasticScatter(), ElasticScatter({'qmax': 20., 'rmax': 30.})
+    f1, f2 = s1.get_fq(a1), s2.get_fq(a2)
+    assert s1.backend is not s2.backend and s1.pdf_backend is not s2.pdf_backend
+    c0 = s1.backend.launch_count()
+    for _ in range(3):
+        assert np.array_equal(s1.get_fq(a1), f1) and np.array_equal(s2.get_fq(a2), f2)
+    # per call: staging + F(Q) pass + finish, no re-upload in between
+    assert s1.backend.launch_count() - c0 == 9
+    assert s1.backend.sizes()['n'] == 30 and s2.backend.sizes()['n'] == 45
+    g = s1.get_grad_pdf(structures.random_atoms(1, 0))
+    assert g.shape == (1, 3, 4000) and not np.any(g)
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'fp64'])

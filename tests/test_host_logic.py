@@ -78,9 +78,9 @@ def test_carbon_form_factor_golden_vector():
     f = formfactors.form_factor(6, np.arange(250) * .1)
     assert np.allclose(f, k['c60_row'], rtol=1e-6)
     for z in formfactors.WK95:
-        assert abs(formfactors.form_factor(z, np.zeros(1))[0] - z) < 0.04
+        assert abs(formfactors.form_factor(z, np.zeros(1))[0] - z) < 0.045
     with pytest.raises(KeyError):
-        formfactors.form_factor(3, np.zeros(1))
+        formfactors.form_factor(120, np.zeros(1))
 
 
 def test_pdf_matrix_reproduces_the_fft_path():
