@@ -45,6 +45,12 @@ SYMBOL = 'Pt'
 # 2 transcendentals + 20 flop ~ 2 SFU + 12 FP32 instructions, so the bound is
 # min(SFU/2, FP32/12) = 8 pair*Q per clock per SM.
 PAIRQ_PER_CLK_PER_SM = 8.0
+# Sharded run against the single-rank evaluation, normalised max-norm.  The two
+# cut the rows into different pieces, i.e. they add the same float32 terms in
+# different partial sums; each is within 2e-6 of the float64 mode at this size
+# (profiles/r2_fullsize_consistency.txt), so their difference stays below twice
+# that.  F(Q) is summed in float64: 1e-12.
+NERR_SHARDED = 5e-6
 FLOP_PER_PAIRQ = 22.0
 
 
@@ -721,7 +727,7 @@ def main():
     }
     failed = None
     if world > 1:
-        bad = {k: v for k, v in check.items() if k.startswith('nerr_') and not v < 2e-6}
+        bad = {k: v for k, v in check.items() if k.startswith('nerr_') and not v < NERR_SHARDED}
         if bad:
             failed = 'sharded run differs from the single-rank evaluation: %r' % bad
             line['check']['failed'] = failed

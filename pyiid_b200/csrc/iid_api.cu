@@ -18,6 +18,7 @@
 #include "iid_debye2.cuh"
 #include "iid_debye64.cuh"
 #include "iid_force_table.cuh"
+#include "iid_fused.cuh"
 #include "iid_sampler.cuh"
 #include "iid_small.cuh"
 #include "iid_spring.cuh"
@@ -133,6 +134,20 @@ struct iid_handle {
     // M = T^T T, vgo = T^T target, coef from the potential kernel
     double *Mq = nullptr, *vgo = nullptr, *coef = nullptr;
     bool vgo_valid = false;
+    double gogo = 0.0;            // target . target (Q-space potential of the fused kernel)
+    double *MF = nullptr, *wq_blk = nullptr;  // fused kernel: (T^T T) F and per-block weights
+    bool use_fused = true;        // one cooperative launch per evaluation of a small structure
+    // zero-copy I/O of the fused kernel, set by the host entry points around
+    // enqueue_eval_device (pinned staging of the handle; null = copy nodes)
+    const double *zc_pos_in = nullptr;
+    double *zc_force_out = nullptr, *zc_out = nullptr;
+    const double *zc_ctl = nullptr;   // leapfrog: step parameters in pinned memory
+    double *zc_mirror = nullptr;      // leapfrog: (q, p, scalars) of the new state in pinned memory
+    bool zero_copy_small = true;
+    double *zc_lf_mirror = nullptr;   // leapfrog finished inside the fused launch, mirrored here
+    unsigned long long *stamps = nullptr;  // IID_FUSED_STAMPS=1: phase times of the fused kernel
+    double stamp_sum[9] = {0};
+    int64_t stamp_n = 0;
     // spring restraints fused into iid_energy_forces_host (iid_spring.cuh)
     int n_restraints = 0;
     int rs_type[IID_MAX_RESTRAINTS] = {0};
@@ -255,6 +270,8 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_PIECE_DIV")) h->piece_div = std::max(1, atoi(s));
     if (const char *s = getenv("IID_ZERO_COPY")) h->zero_copy = atoi(s) != 0;
     if (const char *s = getenv("IID_ACC_J")) h->acc_j = std::max(0, atoi(s));
+    if (const char *s = getenv("IID_FUSED")) h->use_fused = atoi(s) != 0;
+    if (const char *s = getenv("IID_ZERO_COPY_SMALL")) h->zero_copy_small = atoi(s) != 0;
     *out = h;
     return 0;
 }
@@ -267,13 +284,14 @@ extern "C" int iid_destroy(iid_handle *h)
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
                     h->inv_na, h->inv_na_d, h->items_tri, h->jobs, h->segs, h->fixes, h->Spart,
-                    h->Gside, h->Gscr, h->slot_busy, h->T,
+                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
                     h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf,
                     h->lf_slab, h->lf_mass, h->lf_ctl, h->lf_mirror};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pinG) cudaFreeHost(h->pinG);
+    if (h->stamps) cudaFree(h->stamps);
     for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -970,8 +988,13 @@ static int launch_debye64_t(iid_handle *h, const DebyeParams &p, int64_t nblocks
                             cudaStream_t st)
 {
     constexpr int TJ = 8;
+    // F(Q) only keeps 16 accumulators per thread (116 registers): one 16-warp
+    // block covers the 250-bin grid and the pair records are produced once
+    // (3.27 -> 2.7 ms at Au 10k); gradient and force blocks stay at 8 warps
+    constexpr int MAXW = MODE == MODE_FQ ? 16 : 8;
+    constexpr int MAXT = 32 * MAXW;
     const int nchunk = (int)((h->nq + C - 1) / C);
-    const int nwmax = std::min(h->nw_max, 8);
+    const int nwmax = MODE == MODE_FQ ? MAXW : std::min(h->nw_max, 8);
     const int gy = (nchunk + nwmax - 1) / nwmax;
     const int nw = (nchunk + gy - 1) / gy;
     dim3 grid((unsigned)nblocks, (unsigned)gy, 1), block(32 * nw, 1, 1);
@@ -979,12 +1002,12 @@ static int launch_debye64_t(iid_handle *h, const DebyeParams &p, int64_t nblocks
                         (MODE == MODE_FORCE ? debye64_phi_bytes(nw, TJ) : 0);
     static bool attr_done[64] = {false};
     if (!attr_done[h->device & 63]) {
-        CU(cudaFuncSetAttribute(debye64_kernel<C, MODE, 256, TJ>,
+        CU(cudaFuncSetAttribute(debye64_kernel<C, MODE, MAXT, TJ>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done[h->device & 63] = true;
     }
     if (h->timing) CU(cudaEventRecord(h->ev0, st));
-    debye64_kernel<C, MODE, 256, TJ><<<grid, block, smem, st>>>(p);
+    debye64_kernel<C, MODE, MAXT, TJ><<<grid, block, smem, st>>>(p);
     ++h->launches;
     CU(cudaGetLastError());
     if (h->timing) {
@@ -1681,14 +1704,116 @@ extern "C" int iid_get_restraint_energy(iid_handle *h, double *energy)
 // partials of a multi-device handle (EVAL_FQ: staging + F(Q) pass; EVAL_REST:
 // everything after it, h->S already holding the summed pair sums).
 enum { EVAL_ALL = 0, EVAL_FQ = 1, EVAL_REST = 2 };
+
+// The whole evaluation as ONE cooperative launch (iid_fused.cuh) when the
+// structure is small enough for one work item per SM: FP32 mode, one shard,
+// direct force pass, Q-space weights, the caller wants forces and no G(r).
+static bool fused_applicable(const iid_handle *h, bool want_forces, bool want_pdf)
+{
+    const bool table = h->use_force_table && h->ntypes <= 4 && h->n >= h->force_table_min_n;
+    return h->use_fused && h->precision == IID_FP32 && h->cheb && h->world == 1 &&
+           want_forces && !want_pdf && h->qspace_wq && !table && !h->timing &&
+           h->n_items_tri <= h->sm_count && (h->nq + C32 - 1) / C32 <= 12 &&
+           h->np <= (int64_t)h->sm_count * 384;
+}
+
+static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
+{
+    int rc;
+    if (!h->MF) {
+        if ((rc = dev_alloc(&h->MF, h->qp)) ||
+            (rc = dev_alloc(&h->wq_blk, (size_t)h->sm_count * h->qp)))
+            return rc;
+    }
+    FusedParams q;
+    DebyeParams &p = q.fq;
+    p.x = h->x; p.y = h->y; p.z = h->z; p.valid = h->valid; p.orig = h->orig;
+    p.tile_type = h->tile_type;
+    p.items = h->items_tri;
+    p.item_begin = 0;
+    p.item_stride = 1;
+    p.ftab = h->ftab; p.inv_na = h->inv_na; p.wq = nullptr;
+    p.nq = (int)h->nq; p.qp = (int)h->qp;
+    p.qbin = h->qbin;
+    p.qbin_turns = h->qbin / 6.283185307179586476925286766559;
+    p.G = nullptr; p.S = h->S; p.force = nullptr;
+    p.grad_split = 1;
+    p.jobs = nullptr; p.segs = nullptr; p.Gside = nullptr;
+    p.Gscr = nullptr; p.slot_busy = nullptr; p.n_slots = 0; p.acc_j = 0;
+    q.fo = p;
+    q.fo.S = nullptr;
+    q.fo.force = h->force;
+    q.n_items = (int)h->n_items_tri;
+    q.lf = lf ? 1 : 0;
+    q.ctl = h->zc_ctl ? h->zc_ctl : h->lf_ctl; q.slab = h->lf_slab; q.mass = h->lf_mass;
+    q.pos = h->pos;
+    q.pos_in = lf ? nullptr : h->zc_pos_in;
+    q.force_out = h->n_restraints ? nullptr : h->zc_force_out;
+    q.out_host = h->zc_out;
+    q.lf_mirror = (lf && !h->n_restraints) ? h->zc_lf_mirror : nullptr;
+    q.n = (int)h->n; q.np = (int)h->np; q.round_f32 = 1;
+    q.inv_na_d = h->inv_na_d; q.Mq = h->Mq; q.vgo = h->vgo; q.gogo = h->gogo;
+    q.MF = h->MF; q.wq_blk = h->wq_blk;
+    q.potential = potential; q.conv = conv; q.out4 = h->out4;
+    static const bool want_stamps = getenv("IID_FUSED_STAMPS") != nullptr;
+    if (want_stamps && !h->stamps) CU(cudaMalloc((void **)&h->stamps, 16 * sizeof(unsigned long long)));
+    q.stamps = h->stamps;
+    const int nchunk = (int)((h->nq + C32 - 1) / C32);
+    const size_t smem = 2 * debye2_buf_bytes(nchunk, 8) + debye2_phi_bytes(nchunk, 8);
+    static bool attr_done[64] = {false};
+    if (!attr_done[h->device & 63]) {
+        CU(cudaFuncSetAttribute(fused_eval_kernel<true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done[h->device & 63] = true;
+    }
+    void *args[] = {(void *)&q};
+    CU(cudaLaunchCooperativeKernel((const void *)fused_eval_kernel<true>, dim3(h->sm_count),
+                                   dim3(32 * nchunk), args, smem, h->stream));
+    ++h->launches;
+    if (h->stamps) {  // developer timing (block 0's view): synchronous read-back
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(h->stream, &cs);
+        if (cs == cudaStreamCaptureStatusNone) {
+            unsigned long long t[9];
+            CU(cudaStreamSynchronize(h->stream));
+            CU(cudaMemcpy(t, h->stamps, sizeof(t), cudaMemcpyDeviceToHost));
+            for (int k = 1; k < 9; ++k) h->stamp_sum[k] += (double)(t[k] - t[k - 1]);
+            if (++h->stamp_n % 200 == 0) {
+                fprintf(stderr, "fused phases (us, mean of %lld):", (long long)h->stamp_n);
+                const char *nm[9] = {"", "stage", "sync", "fq", "sync", "MF", "sync", "pot", "force"};
+                for (int k = 1; k < 9; ++k)
+                    fprintf(stderr, " %s %.1f", nm[k], 1e-3 * h->stamp_sum[k] / h->stamp_n);
+                fprintf(stderr, "\n");
+            }
+        }
+    }
+    return 0;
+}
+
+// lf: the positions come out of the leapfrog's half kick + drift (state slab,
+// h->lf_ctl) instead of h->pos.
 static int enqueue_eval_device(iid_handle *h, int potential, double conv, bool want_forces,
-                               bool staged = false, int phase = EVAL_ALL)
+                               bool lf = false, int phase = EVAL_ALL, bool want_pdf = false)
 {
     int rc2;
     cudaStream_t st = h->stream;
-    // staging also clears S and the force accumulator (no memset nodes); a
-    // caller that staged the positions itself (leapfrog) has done both
-    if (!staged && phase != EVAL_REST) {
+    if (phase == EVAL_ALL && fused_applicable(h, want_forces, want_pdf)) {
+        if ((rc2 = launch_fused(h, potential, conv, lf))) return rc2;
+        for (int s = 0; s < h->n_restraints; ++s)
+            if ((rc2 = launch_spring(h, h->pos, h->n, h->rs_type[s], h->rs_k[s], h->rs_rt[s],
+                                     nullptr, h->out4 + 4, h->force, nullptr, h->stream)))
+                return rc2;
+        return 0;
+    }
+    // staging also clears S and the force accumulator (no memset nodes)
+    if (lf) {
+        const int np = (int)h->np;
+        lf_stage_kernel<<<(np + 255) / 256, 256, 0, st>>>(
+            h->lf_ctl, h->lf_slab, h->lf_mass, (int)h->n, h->orig, np, h->precision == IID_FP32,
+            h->pos, h->x, h->y, h->z, h->valid, h->S, (int)h->qp, h->force, 3 * (int)h->n);
+        ++h->launches;
+        CU(cudaGetLastError());
+    } else if (phase != EVAL_REST) {
         const int np = (int)h->np;
         prep_kernel<<<(np + 255) / 256, 256, 0, st>>>(h->pos, h->orig, np,
                                                       h->precision == IID_FP32, h->x, h->y, h->z,
@@ -1761,6 +1886,9 @@ static int refresh_target(iid_handle *h, const double *target_host, double *pinn
         CU(cudaMemcpyAsync(h->target, pinned, h->nr * sizeof(double), cudaMemcpyHostToDevice,
                            h->stream));
         h->vgo_valid = false;
+        double c = 0.0;
+        for (int64_t r = 0; r < h->nr; ++r) c = fma(target_host[r], target_host[r], c);
+        h->gogo = c;
     }
     if (!h->vgo_valid) {
         CU(cudaMemsetAsync(h->vgo, 0, h->qp * sizeof(double), h->stream));
@@ -1843,11 +1971,25 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
     // atoms the evaluation is bound by launch latency, not by arithmetic.
     const bool graphable = h->use_graph && !h->timing && forces_host != nullptr;
     memcpy(h->pin, pos_host, (size_t)3 * h->n * sizeof(double));
+    // small structures: the fused kernel reads the positions from, and writes
+    // forces and scalars to, the pinned staging directly -- no copy nodes
+    const bool zc = h->zero_copy_small && fused_applicable(h, forces_host != nullptr,
+                                                           pdf_host != nullptr) &&
+                    h->n_restraints == 0;
     auto enqueue = [&]() -> int {
         int rc2;
-        CU(cudaMemcpyAsync(h->pos, h->pin, (size_t)3 * h->n * sizeof(double),
-                           cudaMemcpyHostToDevice, h->stream));
-        if ((rc2 = enqueue_eval_device(h, potential, conv, forces_host != nullptr))) return rc2;
+        h->zc_pos_in = zc ? h->pin : nullptr;
+        h->zc_force_out = zc ? pfor : nullptr;
+        h->zc_out = zc ? po : nullptr;
+        if (!zc)
+            CU(cudaMemcpyAsync(h->pos, h->pin, (size_t)3 * h->n * sizeof(double),
+                               cudaMemcpyHostToDevice, h->stream));
+        rc2 = enqueue_eval_device(h, potential, conv, forces_host != nullptr, false, EVAL_ALL,
+                                  pdf_host != nullptr);
+        h->zc_pos_in = nullptr;
+        h->zc_force_out = h->zc_out = nullptr;
+        if (rc2) return rc2;
+        if (zc) return 0;
         if (forces_host) {
             CU(cudaMemcpyAsync(pfor, h->force, (size_t)3 * h->n * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
@@ -1858,6 +2000,8 @@ extern "C" int iid_energy_forces_host(iid_handle *h, const double *pos_host,
                                h->stream));
         return 0;
     };
+    // (a one-node graph still beats a direct cooperative launch: 63 against 73 us
+    // per call at Au561)
     if ((rc = run_graphed(h, h->ef, graphable, potential, conv, pdf_host != nullptr, enqueue)))
         return rc;
     CU(cudaStreamSynchronize(h->stream));
@@ -1980,23 +2124,29 @@ extern "C" int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, i
     ctl[2] = (double)dst;
     ctl[3] = centre ? 1.0 : 0.0;
     const int n = (int)h->n;
+    // small structures: the kernels read the step parameters from, and write the
+    // new state's mirror to, the pinned staging directly -- no copy nodes
+    const bool zc = h->zero_copy_small && fused_applicable(h, true, false);
     auto enqueue = [&]() -> int {
         int rc2;
-        CU(cudaMemcpyAsync(h->lf_ctl, ctl, LF_CTL * sizeof(double), cudaMemcpyHostToDevice,
-                           h->stream));
-        const int np = (int)h->np;
-        lf_stage_kernel<<<(np + 255) / 256, 256, 0, h->stream>>>(
-            h->lf_ctl, h->lf_slab, h->lf_mass, n, h->orig, np, h->precision == IID_FP32, h->pos,
-            h->x, h->y, h->z, h->valid, h->S, (int)h->qp, h->force, 3 * n);
+        if (!zc)
+            CU(cudaMemcpyAsync(h->lf_ctl, ctl, LF_CTL * sizeof(double), cudaMemcpyHostToDevice,
+                               h->stream));
+        h->zc_ctl = zc ? ctl : nullptr;
+        h->zc_lf_mirror = zc ? mir : nullptr;  // no restraints: the step finishes in this launch
+        rc2 = enqueue_eval_device(h, potential, conv, true, true);
+        h->zc_ctl = nullptr;
+        h->zc_lf_mirror = nullptr;
+        if (rc2) return rc2;
+        if (zc && !h->n_restraints) return 0;
+        lf_finish_kernel<<<1, 1024, 0, h->stream>>>(zc ? ctl : h->lf_ctl, h->lf_slab, h->lf_mass, n,
+                                                    h->pos, h->force, zc ? mir : h->lf_mirror,
+                                                    h->out4);
         ++h->launches;
         CU(cudaGetLastError());
-        if ((rc2 = enqueue_eval_device(h, potential, conv, true, true))) return rc2;
-        lf_finish_kernel<<<1, 1024, 0, h->stream>>>(h->lf_ctl, h->lf_slab, h->lf_mass, n, h->pos,
-                                                    h->force, h->lf_mirror, h->out4);
-        ++h->launches;
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(mir, h->lf_mirror, (2 * n3 + 16) * sizeof(double),
-                           cudaMemcpyDeviceToHost, h->stream));
+        if (!zc)
+            CU(cudaMemcpyAsync(mir, h->lf_mirror, (2 * n3 + 16) * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->stream));
         return 0;
     };
     const bool graphable = h->use_graph && !h->timing;
@@ -2140,6 +2290,7 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "qspace_wq") h->qspace_wq = value != 0;
     else if (k == "nw_max") h->nw_max = (int)std::max<int64_t>(1, std::min<int64_t>(12, value));
     else if (k == "zero_copy") h->zero_copy = value != 0;
+    else if (k == "fused") h->use_fused = value != 0;
     else if (k == "acc_j") h->acc_j = (int)std::max<int64_t>(0, value);
     else if (k == "piece_div") {
         h->piece_div = (int)std::max<int64_t>(1, std::min<int64_t>(1024, value));

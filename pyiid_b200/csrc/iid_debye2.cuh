@@ -70,15 +70,17 @@ __device__ __forceinline__ void sincos_turns(double u, float &s, float &c)
 // second one is the half-chunk seed rotated by C/4 bins) and takes its first
 // step with the rotation; over 8 bins the error is 1.3-2.5e-7 rms, the same
 // as the rotation ("recurrences").
-template <int C, int MODE, int MAXT, int MINB, int TJ2, bool CHEB, int PU = 1>
-__global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
+// The kernel body, callable from the stand-alone kernel below and from the
+// fused evaluation kernel (iid_fused.cuh): block (bx, by) of a launch with
+// dynamic shared memory `smem_raw`.
+template <int C, int MODE, int TJ2, bool CHEB, int PU = 1>
+__device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char *smem_raw,
+                                            const int bx, const int by)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarp = blockDim.x >> 5;
-    const int chunk0 = blockIdx.y * nwarp;
+    const int chunk0 = by * nwarp;
     const int m0 = (chunk0 + warp) * C;
     const bool active = m0 < p.nq;
 
@@ -87,14 +89,14 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
     int itile, seg = 0, seg_end = 1, dest = -1;
     RowSeg sg;
     if constexpr (MODE == MODE_GRAD) {
-        const RowJob job = p.jobs[blockIdx.x];
+        const RowJob job = p.jobs[bx];
         itile = job.itile;
         seg = job.seg_begin;
         seg_end = job.seg_end;
         dest = job.dest;
         sg = p.segs[seg];
     } else {
-        const WorkItem it = p.items[p.item_begin + (int64_t)blockIdx.x * p.item_stride];
+        const WorkItem it = p.items[p.item_begin + (int64_t)bx * p.item_stride];
         itile = it.itile;
         sg.jbegin = it.jbegin;
         sg.jend = it.jend;
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
         // per-job partial of the F(Q) pair sum; reduce_spart_kernel adds the jobs
         // in a fixed order
         const int bin = m0 + lane;
-        if (p.S != nullptr && lane < C && bin < p.nq) p.S[(size_t)blockIdx.x * p.qp + bin] = srun;
+        if (p.S != nullptr && lane < C && bin < p.nq) p.S[(size_t)bx * p.qp + bin] = srun;
     } else if constexpr (MODE == MODE_FORCE) {
         if (oi >= 0) {
             atomicAdd(&p.force[(size_t)oi * 3 + 0], (double)fix);
@@ -681,6 +683,13 @@ __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
             atomicAdd(&p.S[bin], fweight * (v0 + v1) * (double)(fa[bin] * fb[bin]));
         }
     }
+}
+
+template <int C, int MODE, int MAXT, int MINB, int TJ2, bool CHEB, int PU = 1>
+__global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    debye2_body<C, MODE, TJ2, CHEB, PU>(p, smem_raw, (int)blockIdx.x, (int)blockIdx.y);
 }
 
 // G rows of the split i-tiles = sum of their pieces in the side buffer, in a

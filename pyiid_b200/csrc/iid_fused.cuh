@@ -1,0 +1,231 @@
+// iid_fused.cuh -- one cooperative kernel for a whole Rw / chi^2 energy + force
+// evaluation of a SMALL structure (the sampler's regime: Au561, one work item
+// per SM), sm_100a.
+//
+// pyiid/sim/__init__.py:10-38 (leapfrog) + calc/calc_1d.py:78-95 cost the
+// reference 1 x grad PDF + 2 x PDF per step.  Round 1 ran the evaluation as a
+// graph of 6-7 small launches (staging, F(Q) pass, G(r), potential, weights,
+// force pass) that at 561 atoms spent more time in launch gaps and in the
+// one-block float64 stages than in the two pair sums.  Here the sequence is ONE
+// launch with grid-wide barriers between its phases:
+//
+//   0  staging: (leapfrog: half kick + drift) element sort, float32 rounding,
+//      clearing of the S and force accumulators
+//   1  F(Q) pass, one work item per block (debye2_body<MODE_FQ>)
+//   2  F = 2 S / na;  (M F)[m] for this block's rows of M = T^T T
+//   3  every block, redundantly: Rw / chi^2, scale and the chain-rule weights
+//      in Q SPACE -- with gc = T F:  gc.go = F.(T^T go),  gc.gc = F.(M F), so
+//      neither G(r) nor the R x Q matrix is touched -- then the force pass of
+//      its work item (debye2_body<MODE_FORCE>)
+//
+// The Q-space scalars: a = F.vgo, b = F.MF, c = go.go (once per target);
+// scale s = a/b (<= 0: the reference's branches, master_kernel.py:229-230,
+// 263-264), |go - s gc|^2 = c - 2 s a + s^2 b, gc.(go - s gc) = a - s b.
+#pragma once
+#include <cooperative_groups.h>
+#include "iid_debye2.cuh"
+#include "iid_sampler.cuh"
+
+namespace iid {
+
+struct FusedParams {
+    DebyeParams fq;  // F(Q) pass (S = the handle's accumulator)
+    DebyeParams fo;  // force pass (wq is set per block)
+    int n_items;
+    // staging
+    int lf;  // 1 = leapfrog staging from the state slab, 0 = positions in `pos`
+    const double *ctl;
+    double *slab;
+    const double *mass;
+    double *pos;  // [n][3] caller order (device)
+    // zero-copy I/O through pinned, mapped host memory (no copy nodes around the
+    // launch: at 561 atoms each small DMA costs as much as a phase of the kernel)
+    const double *pos_in;  // plain staging: positions in host memory (or null: `pos`)
+    double *force_out;     // [n][3] host copy of the forces (or null)
+    double *out_host;      // [5] host copy of out4 (or null)
+    double *lf_mirror;     // leapfrog: finish the step in this launch (half kick, kinetic
+                           // energy, centring) and mirror (q, p, scalars) here (or null)
+    int n, np, round_f32;
+    // Q-space stages
+    const double *inv_na_d, *Mq, *vgo;
+    double gogo;
+    double *MF;      // [qp]
+    double *wq_blk;  // [grid][qp]
+    int potential;
+    double conv;
+    double *out4;
+    unsigned long long *stamps;  // developer timing: globaltimer at the phase boundaries (or null)
+};
+
+__device__ __forceinline__ void fused_stamp(const FusedParams &q, int k)
+{
+    if (q.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        q.stamps[k] = t;
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double *sm)
+{
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < nw; ++k) t += sm[k];  // same order in every block
+    return t;
+}
+
+template <bool CHEB>
+__global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int nq = q.fq.nq, qp = q.fq.qp;
+
+    fused_stamp(q, 0);
+    // ---- phase 0: staging ---------------------------------------------------------
+    {
+        const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+        for (int e = gtid; e < qp; e += gsz) q.fq.S[e] = 0.0;
+        for (int e = gtid; e < 3 * q.n; e += gsz) q.fo.force[e] = 0.0;
+        for (int k = gtid; k < q.np; k += gsz) {
+            const int o = q.fq.orig[k];
+            double c[3] = {0.0, 0.0, 0.0};
+            if (o >= 0) {
+                if (q.lf) {
+                    // p_half = p + (step/2) f; q' = q + step p_half / m (numpy's
+                    // operation order, see lf_stage_kernel)
+                    const double step = q.ctl[0];
+                    const int src = (int)q.ctl[1], dst = (int)q.ctl[2];
+                    const double *qq = lf_slot(q.slab, q.n, src, 0),
+                                 *pp = lf_slot(q.slab, q.n, src, 1),
+                                 *ff = lf_slot(q.slab, q.n, src, 2);
+                    double *pd = lf_slot(q.slab, q.n, dst, 1);
+                    const double half = __dmul_rn(0.5, step), m = q.mass[o];
+#pragma unroll
+                    for (int w = 0; w < 3; ++w) {
+                        const size_t e = 3 * (size_t)o + w;
+                        const double ph = __dadd_rn(pp[e], __dmul_rn(half, ff[e]));
+                        pd[e] = ph;
+                        const double qn = __dadd_rn(qq[e], __dmul_rn(step, __ddiv_rn(ph, m)));
+                        q.pos[e] = qn;
+                        c[w] = qn;
+                    }
+                } else if (q.pos_in) {
+#pragma unroll
+                    for (int w = 0; w < 3; ++w) {
+                        c[w] = q.pos_in[3 * (size_t)o + w];
+                        q.pos[3 * (size_t)o + w] = c[w];  // device copy for the kernels that follow
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 3; ++w) c[w] = q.pos[3 * (size_t)o + w];
+                }
+                if (q.round_f32)
+#pragma unroll
+                    for (int w = 0; w < 3; ++w) c[w] = (double)(float)c[w];
+            }
+            const_cast<double *>(q.fq.x)[k] = c[0];
+            const_cast<double *>(q.fq.y)[k] = c[1];
+            const_cast<double *>(q.fq.z)[k] = c[2];
+            const_cast<float *>(q.fq.valid)[k] = o >= 0 ? 1.f : 0.f;
+        }
+    }
+    fused_stamp(q, 1);
+    grid.sync();
+    fused_stamp(q, 2);
+
+    // ---- phase 1: F(Q) pass -------------------------------------------------------
+    if ((int)blockIdx.x < q.n_items)
+        debye2_body<32, MODE_FQ, 8, CHEB>(q.fq, smem_raw, (int)blockIdx.x, 0);
+    fused_stamp(q, 3);
+    grid.sync();
+    fused_stamp(q, 4);
+
+    // ---- phase 2: F and this block's rows of M F ------------------------------------
+    double *Fs = reinterpret_cast<double *>(smem_raw);  // [qp]
+    double *Ms = Fs + qp;                               // [qp] M F
+    double *red = Ms + qp;                              // [32]
+    for (int m = threadIdx.x; m < qp; m += blockDim.x)
+        Fs[m] = m < nq ? 2.0 * __ldcg(q.fq.S + m) * q.inv_na_d[m] : 0.0;
+    __syncthreads();
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int row = blockIdx.x + warp * gridDim.x; row < nq; row += nw * gridDim.x) {
+            const double *mrow = q.Mq + (size_t)row * qp;
+            double acc = 0.0;
+            for (int m = lane; m < nq; m += 32) acc = fma(mrow[m], Fs[m], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) q.MF[row] = acc;
+        }
+    }
+    fused_stamp(q, 5);
+    grid.sync();
+    fused_stamp(q, 6);
+
+    // ---- phase 3: potential + weights (every block), then the force pass ------------
+    double la = 0.0, lb = 0.0;
+    for (int m = threadIdx.x; m < nq; m += blockDim.x) {
+        const double mf = __ldcg(q.MF + m);
+        Ms[m] = mf;
+        la = fma(Fs[m], q.vgo[m], la);
+        lb = fma(Fs[m], mf, lb);
+    }
+    const double a = block_sum(la, red);
+    const double b = block_sum(lb, red);
+    const double c = q.gogo;
+    const double scale_true = b > 0.0 ? a / b : 0.0;
+    const bool pos = scale_true > 0.0;
+    const double scale = pos ? scale_true : 1.0;
+    double dd = c - 2.0 * scale * a + scale * scale * b;  // |go - scale gc|^2
+    if (dd < 0.0) dd = 0.0;
+    const double gd = a - scale * b;                      // gc . (go - scale gc)
+    double value, pref;
+    if (q.potential == 0) {  // Rw
+        value = pos ? sqrt(dd / c) : 1.0;
+        pref = dd > 0.0 ? -value / dd : 0.0;
+    } else {  // chi^2
+        value = dd;
+        pref = -2.0;
+    }
+    const double gdb = b > 0.0 ? gd / b : 0.0;
+    const double coef0 = pref * (scale + gdb);
+    const double coef1 = pref * (scale * scale + 2.0 * gdb * scale_true);
+    double *wq = q.wq_blk + (size_t)blockIdx.x * qp;
+    for (int m = threadIdx.x; m < qp; m += blockDim.x)
+        wq[m] = m < nq ? q.conv * (coef0 * q.vgo[m] - coef1 * Ms[m]) : 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        q.out4[0] = value * q.conv;
+        q.out4[1] = scale;
+        q.out4[2] = value;
+        q.out4[3] = scale_true;
+        q.out4[4] = 0.0;  // restraint energy, summed by the spring kernels that follow
+    }
+    __syncthreads();  // wq is complete (block scope) and the scratch is free again
+    fused_stamp(q, 7);
+    if ((int)blockIdx.x < q.n_items) {
+        DebyeParams fo = q.fo;
+        fo.wq = wq;
+        debye2_body<32, MODE_FORCE, 8, CHEB>(fo, smem_raw, (int)blockIdx.x, 0);
+    }
+    fused_stamp(q, 8);
+    // ---- phase 4 (optional): results straight into the caller's pinned buffer -------
+    if (q.force_out) {
+        grid.sync();
+        const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+        for (int e = gtid; e < 3 * q.n; e += gsz) q.force_out[e] = __ldcg(q.fo.force + e);
+        if (gtid < 5) q.out_host[gtid] = __ldcg(q.out4 + gtid);
+    }
+    // ---- phase 5 (optional): the leapfrog's second half kick, one block ----------------
+    if (q.lf_mirror) {
+        grid.sync();
+        if (blockIdx.x == 0)
+            lf_finish_body(q.ctl, q.slab, q.mass, q.n, q.pos, q.fo.force, q.lf_mirror, q.out4);
+    }
+}
+
+}  // namespace iid

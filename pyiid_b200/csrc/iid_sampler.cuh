@@ -73,13 +73,13 @@ __global__ void lf_stage_kernel(const double *__restrict__ ctl, double *__restri
 // (min + max)/2) when centring.  One block: the sampler's structures are small
 // and the three reductions need the whole array.  Mirrors q, p and the scalars
 // into one contiguous buffer for the single device-to-host copy of the step.
-__global__ void __launch_bounds__(1024) lf_finish_kernel(const double *__restrict__ ctl,
-                                                         double *__restrict__ slab,
-                                                         const double *__restrict__ mass, int n,
-                                                         const double *__restrict__ pos,
-                                                         const double *__restrict__ force,
-                                                         double *__restrict__ mirror,
-                                                         const double *__restrict__ out4)
+// (Also the last phase of the fused evaluation kernel, where p, pos, force and
+// out4 were written by other blocks of the SAME launch: they are read with
+// ld.cg, never through the non-coherent path.)
+__device__ __forceinline__ void lf_finish_body(const double *ctl, double *slab,
+                                               const double *__restrict__ mass, int n,
+                                               const double *pos, const double *force,
+                                               double *mirror, const double *out4)
 {
     // mirror = q [3n] | p [3n] | energy, scale, value, scale_true, restraint
     // energy, kinetic energy, shift x y z: ONE device-to-host copy per step
@@ -99,13 +99,13 @@ __global__ void __launch_bounds__(1024) lf_finish_kernel(const double *__restric
 #pragma unroll
         for (int w = 0; w < 3; ++w) {
             const int k = 3 * a + w;
-            const double fk = force[k];
-            const double pn = __dadd_rn(p[k], __dmul_rn(half, fk));
+            const double fk = __ldcg(force + k);
+            const double pn = __dadd_rn(__ldcg(p + k), __dmul_rn(half, fk));
             p[k] = pn;
             f[k] = fk;
             mirror[3 * (size_t)n + k] = pn;
             ke = fma(pn, __ddiv_rn(pn, m), ke);
-            const double x = pos[k];
+            const double x = __ldcg(pos + k);
             lo[w] = fmin(lo[w], x);
             hi[w] = fmax(hi[w], x);
         }
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(1024) lf_finish_kernel(const double *__restric
                 r[4 + w] = fmax(r[4 + w], __shfl_xor_sync(0xffffffffu, r[4 + w], o));
             }
         }
-        if (lane < 5) out[lane] = out4[lane];
+        if (lane < 5) out[lane] = __ldcg(out4 + lane);
         if (lane == 0) {
             out[5] = 0.5 * r[0];
 #pragma unroll
@@ -157,10 +157,22 @@ __global__ void __launch_bounds__(1024) lf_finish_kernel(const double *__restric
     }
     __syncthreads();
     for (int k = threadIdx.x; k < 3 * n; k += blockDim.x) {
-        const double x = centre ? __dadd_rn(pos[k], shift[k % 3]) : pos[k];
+        const double x0 = __ldcg(pos + k);
+        const double x = centre ? __dadd_rn(x0, shift[k % 3]) : x0;
         q[k] = x;
         mirror[k] = x;
     }
+}
+
+__global__ void __launch_bounds__(1024) lf_finish_kernel(const double *__restrict__ ctl,
+                                                         double *__restrict__ slab,
+                                                         const double *__restrict__ mass, int n,
+                                                         const double *__restrict__ pos,
+                                                         const double *__restrict__ force,
+                                                         double *__restrict__ mirror,
+                                                         const double *__restrict__ out4)
+{
+    lf_finish_body(ctl, slab, mass, n, pos, force, mirror, out4);
 }
 
 }  // namespace iid
