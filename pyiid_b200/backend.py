@@ -626,6 +626,31 @@ class Backend(object):
             res = out.cpu().numpy()
         return res.reshape(g.shape[:-1] + (self.nr,))
 
+    def grad_pdf_of(self, positions, qmin_bin=0):
+        """grad G(r) [N,3,R] float64 straight from the positions: the full
+        gradient of F(Q) stays on the device between the pair sum and the
+        contraction with T (ElasticScatter.get_grad_pdf :498-524 does
+        grad -> host -> grad_pdf -> device again when the two callables are
+        bound separately).  One GPU, one shard; returns None otherwise."""
+        if self.multi or self.world != 1 or self.nr == 0:
+            return None
+        import torch
+        pos = self._pos(positions)
+        tdt = torch.float32 if self.precision == 'fp32' else torch.float64
+        dev = 'cuda:%d' % self.device
+        with torch.cuda.device(self.device), self._on_stream():
+            p = torch.from_numpy(pos).to(dev)
+            g = torch.empty((self.n, 3, self.nq), dtype=tdt, device=dev)
+            check(self.lib.iid_grad_fq_partial(self.h, p.data_ptr(), g.data_ptr(), None,
+                                               self._stream()))
+            if qmin_bin > 0:
+                g[:, :, :qmin_bin] = 0
+            out = torch.empty((self.n * 3, self.nr), dtype=torch.float64, device=dev)
+            check(self.lib.iid_grad_pdf(self.h, g.data_ptr(), self.n * 3, out.data_ptr(),
+                                        self._stream()))
+            res = out.cpu().numpy()
+        return res.reshape(self.n, 3, self.nr)
+
     def gr_from_fq(self, fq):
         """G(r) = T F for a host F(Q) (get_pdf's noise branch)."""
         if self.nr == 0:

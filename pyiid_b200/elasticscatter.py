@@ -324,8 +324,16 @@ class ElasticScatter(object):
         self._ensure_wrapped(atoms)
         if len(atoms) < 2:  # no pairs: zeros (k_max == 0, flat_multi_cpu_wrap.py:85-86)
             return np.zeros((len(atoms), 3, len(self.get_r())))
-        fq_grad = self.grad(atoms, self.pdf_qbin, 'PDF')
         qmin_bin = int(self.exp['qmin'] / self.pdf_qbin)
+        if getattr(self.grad, '__func__', None) is ElasticScatter._wrap_fq_grad and \
+                getattr(self.grad_pdf, '__func__', None) is ElasticScatter._grad_pdf:
+            # both callables are the B200 ones: keep grad F(Q) on the device
+            be = self._load(atoms, self.pdf_qbin, 'PDF')
+            be.set_transform(self.exp['rstep'], self.pdf_qbin, self.get_r(), self.exp['qmin'])
+            out = be.grad_pdf_of(atoms.get_positions(), qmin_bin)
+            if out is not None:
+                return out
+        fq_grad = self.grad(atoms, self.pdf_qbin, 'PDF')
         fq_grad[:, :, :qmin_bin] = 0.
         return self.grad_pdf(fq_grad, self.exp['rstep'], self.pdf_qbin,
                              self.get_r(), self.exp['qmin'])
