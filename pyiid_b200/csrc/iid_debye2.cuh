@@ -134,6 +134,14 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
         accZ[MODE == MODE_GRAD ? H : 1];
     float2 w0[MODE == MODE_FORCE ? H : 1], w1[MODE == MODE_FORCE ? H : 1];
     float fix = 0.f, fiy = 0.f, fiz = 0.f;
+    // MODE_FORCE weights of this warp's bins: lane L forms the weight of bin
+    // m0 + L once (coalesced loads), the others take it by shuffle (128 broadcast
+    // loads per thread in front of a 40-atom item were a visible share of it)
+    float wlane = 0.f;
+    if constexpr (MODE == MODE_FORCE) {
+        const int bin = m0 + lane;
+        if (lane < C && bin < p.nq) wlane = (float)(p.wq[bin]) * fa[bin] * fb[bin] * inv_na[bin];
+    }
 #pragma unroll
     for (int k = 0; k < H; ++k) {
         if constexpr (MODE != MODE_FORCE) accF[k] = make_float2(0.f, 0.f);
@@ -143,15 +151,10 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
             accZ[k] = make_float2(0.f, 0.f);
         }
         if constexpr (MODE == MODE_FORCE) {
-            float w[2];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int bin = m0 + hh * H + k;
-                w[hh] = 0.f;
-                if (bin < p.nq) w[hh] = (float)(p.wq[bin]) * fa[bin] * fb[bin] * inv_na[bin];
-            }
-            w0[k] = make_float2(w[0], w[1]);
-            w1[k] = make_float2(w[0] * (float)(m0 + k), w[1] * (float)(m0 + H + k));
+            const float wa = __shfl_sync(0xffffffffu, wlane, k);
+            const float wb = __shfl_sync(0xffffffffu, wlane, H + k);
+            w0[k] = make_float2(wa, wb);
+            w1[k] = make_float2(wa * (float)(m0 + k), wb * (float)(m0 + H + k));
         }
     }
 
