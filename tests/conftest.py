@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
+# On a box with several GPUs ElasticScatter() would take all of them (the
+# one-process multi-GPU handle); the device-level checks of this suite address
+# ONE handle on ONE device.  The multi-GPU tests ask for 'Multi-GPU' explicitly.
+os.environ.setdefault('IID_PROCESSOR', 'B200')
+
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a B200 (run with -m gpu)')

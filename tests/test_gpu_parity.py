@@ -382,8 +382,8 @@ def test_one_process_multi_gpu_handle():
     ideal = structures.alloy_sphere(4000, seed=3, sigma=0.0)
     one = ElasticScatter(device=0)
     many = ElasticScatter()
-    assert one.processor == 'B200' and many.processor == 'Multi-GPU'
     assert many.set_processor('Multi-GPU') is True
+    assert one.processor == 'B200' and many.processor == 'Multi-GPU'
     f1, fm = one.get_fq(atoms), many.get_fq(atoms)
     assert many.backend.devices()[1] >= 2
     assert nerr(fm, f1) < 1e-6
