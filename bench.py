@@ -756,7 +756,7 @@ def main():
 
 # dram bytes (read + write) of one MODE_GRAD launch at the bench workload, from
 # the ncu --set full capture summarised in profiles/; None until measured there.
-TRAFFIC_BYTES = 730.3e6  # profiles/r1_ncu_full_grad50k_metrics.csv: 292.4 MB read + 437.9 MB write
+TRAFFIC_BYTES = 157.7e6  # profiles/r2_ncu_full_grad50k_metrics.csv: 5.2 MB read + 152.6 MB written
 
 if __name__ == '__main__':
     main()
