@@ -87,6 +87,9 @@ struct iid_handle {
     // multi-device handle (iid_create_multi): one complete sub-handle per GPU,
     // sub d computing shard (d, active); this handle only coordinates
     std::vector<iid_handle *> subs;
+    int n_devices = 1;                 // devices a multi handle may use (subs are created on demand)
+    std::vector<std::pair<std::string, int64_t>> multi_options;
+    double multi_rs_k[IID_MAX_RESTRAINTS] = {0};
     int active = 1;                    // sub-handles used for the current structure
     std::vector<double> inv_na_host;   // [nq] 1/na for the host-side F = 2 S / na
     std::vector<double> T_host;        // multi: the transform, for devices activated later
@@ -195,6 +198,7 @@ struct iid_handle {
 
 static int upload_row_jobs(iid_handle *h);
 static int multi_destroy(iid_handle *h);
+static int multi_need_subs(iid_handle *h, int count);
 static int multi_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
                                int64_t n_types, const double *ftable, int64_t nq, double qbin);
 static int multi_set_transform(iid_handle *h, int64_t nr, int64_t nq, const double *T);
@@ -1661,6 +1665,11 @@ extern "C" int iid_set_restraints(iid_handle *h, int count, const int *sp_type, 
             if (rc) return rc;
         }
         h->n_restraints = count;
+        for (int s = 0; s < count; ++s) {  // for devices that join later
+            h->rs_type[s] = sp_type[s];
+            h->multi_rs_k[s] = k[s];
+            h->rs_rt[s] = rt[s];
+        }
         return 0;
     }
     if (!h) return fail(IID_E_BADARG, "null handle");
@@ -2272,10 +2281,12 @@ extern "C" int iid_fq_to_gr_host(iid_handle *h, const double *F_host, double *pd
 extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
 {
     if (MULTI(h)) {
+        if (!key) return fail(IID_E_BADARG, "null argument");
         for (iid_handle *sh : h->subs) {
             int rc = iid_set_option(sh, key, value);
             if (rc) return rc;
         }
+        h->multi_options.push_back({std::string(key), value});
         return 0;
     }
     if (!h || !key) return fail(IID_E_BADARG, "null argument");
@@ -2323,6 +2334,7 @@ extern "C" int iid_launch_count(iid_handle *h, int64_t *count)
 extern "C" int iid_set_timing(iid_handle *h, int enabled)
 {
     if (MULTI(h)) {
+        h->timing = enabled != 0;
         for (iid_handle *sh : h->subs) sh->timing = enabled != 0;
         return 0;
     }
@@ -2416,6 +2428,22 @@ extern "C" int iid_measure_peaks(iid_handle *h, double *out)
 // (3n doubles) and four scalars; they are summed on the host in device order
 // (deterministic), so no collective library is involved.  The gradient rows
 // are disjoint per device and go straight into the caller's array.
+static int multi_need_subs(iid_handle *h, int count)
+{
+    while ((int)h->subs.size() < count) {
+        iid_handle *sh = nullptr;
+        int rc = iid_create((int)h->subs.size(), h->precision, &sh);
+        if (rc) return rc;
+        // options set on the multi handle so far apply to late joiners as well
+        for (const auto &kv : h->multi_options) iid_set_option(sh, kv.first.c_str(), kv.second);
+        if (h->n_restraints)
+            iid_set_restraints(sh, h->n_restraints, h->rs_type, h->multi_rs_k, h->rs_rt);
+        sh->timing = h->timing;
+        h->subs.push_back(sh);
+    }
+    return 0;
+}
+
 extern "C" int iid_create_multi(int n_devices, int precision, iid_handle **out)
 {
     if (!out) return fail(IID_E_BADARG, "null out");
@@ -2427,15 +2455,13 @@ extern "C" int iid_create_multi(int n_devices, int precision, iid_handle **out)
     if (n_devices > count) return fail(IID_E_BADARG, "more devices requested than present");
     iid_handle *h = new iid_handle();
     h->precision = precision;
-    for (int d = 0; d < n_devices; ++d) {
-        iid_handle *sh = nullptr;
-        int rc = iid_create(d, precision, &sh);
-        if (rc) {
-            for (iid_handle *x : h->subs) iid_destroy(x);
-            delete h;
-            return rc;
-        }
-        h->subs.push_back(sh);
+    h->n_devices = n_devices;
+    // sub-handles (one CUDA context each) are created when a structure first
+    // needs them: a small structure never touches devices 1 .. n-1
+    int rc = multi_need_subs(h, 1);
+    if (rc) {
+        delete h;
+        return rc;
     }
     h->device = 0;
     h->sm_count = h->subs[0]->sm_count;
@@ -2446,7 +2472,7 @@ extern "C" int iid_create_multi(int n_devices, int precision, iid_handle **out)
 extern "C" int iid_handle_devices(iid_handle *h, int *n_devices, int *active)
 {
     if (!h) return fail(IID_E_BADARG, "null handle");
-    if (n_devices) *n_devices = h->subs.empty() ? 1 : (int)h->subs.size();
+    if (n_devices) *n_devices = h->subs.empty() ? 1 : h->n_devices;
     if (active) *active = h->subs.empty() ? 1 : h->active;
     return 0;
 }
@@ -2467,9 +2493,13 @@ static int multi_set_structure(iid_handle *h, int64_t n, const int32_t *type_ind
 {
     // small structures do not amortise the per-device launches and the host
     // hops: about 1500 atoms per device at least
-    int active = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->subs.size(), n / 1500));
+    int active = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->n_devices, n / 1500));
     if (const char *s = getenv("IID_MULTI_ACTIVE"))
-        active = std::max(1, std::min((int)h->subs.size(), atoi(s)));
+        active = std::max(1, std::min(h->n_devices, atoi(s)));
+    {
+        int rc = multi_need_subs(h, active);
+        if (rc) return rc;
+    }
     h->active = active;
     for (int d = 0; d < active; ++d) {
         iid_handle *sh = h->subs[d];
@@ -2501,7 +2531,7 @@ static int multi_set_transform(iid_handle *h, int64_t nr, int64_t nq, const doub
         int rc = iid_set_transform(h->subs[d], nr, nq, T);
         if (rc) return rc;
     }
-    for (size_t d = (size_t)h->active; d < h->subs.size(); ++d) h->subs[d]->nr = 0;
+    for (size_t d = (size_t)h->active; d < h->subs.size(); ++d) h->subs[d]->nr = 0;  // stale
     h->T_host.assign(T, T + (size_t)nr * nq);
     h->nr = nr;
     return 0;
