@@ -309,7 +309,11 @@ int iid_download_host(iid_handle *h, const void *dev, void *host, int64_t bytes)
  * iteration), "piece_div" (smallest piece of a split gradient row = row /
  * piece_div), "zero_copy" (0/1: gradient rows straight into mapped host
  * arrays), "acc_j" (FP32 full gradient: j atoms per float32 partial sum before
- * it is parked and re-started, 0 = one accumulator over the whole row).  Defaults can also be set with IID_* environment variables
+ * it is parked and re-started, 0 = one accumulator over the whole row),
+ * "fused" (0/1: small structures evaluate in ONE cooperative launch),
+ * "fused_det" (0/1: that launch adds its per-item partial sums in a fixed
+ * order -- bit-reproducible energies, forces and sampler trajectories --
+ * instead of atomics).  Defaults can also be set with IID_* environment variables
  * before iid_create. */
 int iid_set_option(iid_handle *h, const char *key, int64_t value);
 

@@ -140,6 +140,9 @@ struct iid_handle {
     double gogo = 0.0;            // target . target (Q-space potential of the fused kernel)
     double *MF = nullptr, *wq_blk = nullptr;  // fused kernel: (T^T T) F and per-block weights
     bool use_fused = true;        // one cooperative launch per evaluation of a small structure
+    bool fused_det = true;        // ... bit-reproducible: per-item partial sums, fixed order
+    double *Sitem = nullptr, *Fi = nullptr, *Fj = nullptr;
+    int64_t tri_maxlen = 0;       // longest j range of a triangle item
     // zero-copy I/O of the fused kernel, set by the host entry points around
     // enqueue_eval_device (pinned staging of the handle; null = copy nodes)
     const double *zc_pos_in = nullptr;
@@ -275,6 +278,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_ZERO_COPY")) h->zero_copy = atoi(s) != 0;
     if (const char *s = getenv("IID_ACC_J")) h->acc_j = std::max(0, atoi(s));
     if (const char *s = getenv("IID_FUSED")) h->use_fused = atoi(s) != 0;
+    if (const char *s = getenv("IID_FUSED_DET")) h->fused_det = atoi(s) != 0;
     if (const char *s = getenv("IID_ZERO_COPY_SMALL")) h->zero_copy_small = atoi(s) != 0;
     *out = h;
     return 0;
@@ -288,7 +292,7 @@ extern "C" int iid_destroy(iid_handle *h)
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
                     h->inv_na, h->inv_na_d, h->items_tri, h->jobs, h->segs, h->fixes, h->Spart,
-                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->T,
+                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->Sitem, h->Fi, h->Fj, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
                     h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf,
                     h->lf_slab, h->lf_mass, h->lf_ctl, h->lf_mirror};
@@ -809,6 +813,12 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
         (rc = dev_alloc(&h->wq, qp)) || (rc = dev_alloc(&h->force, 3 * n)))
         return rc;
     h->n_items_tri = (int64_t)tri.size();
+    h->tri_maxlen = 0;
+    for (const WorkItem &w : tri) h->tri_maxlen = std::max<int64_t>(h->tri_maxlen, w.jend - w.jbegin);
+    // per-item partial sums of the deterministic fused path are sized per structure
+    if (h->Sitem) { cudaFree(h->Sitem); h->Sitem = nullptr; }
+    if (h->Fi) { cudaFree(h->Fi); h->Fi = nullptr; }
+    if (h->Fj) { cudaFree(h->Fj); h->Fj = nullptr; }
     h->run_begin = L.run_begin;
     h->run_end = L.run_end;
     h->run_type_v = L.run_type;
@@ -1749,9 +1759,20 @@ static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
     p.grad_split = 1;
     p.jobs = nullptr; p.segs = nullptr; p.Gside = nullptr;
     p.Gscr = nullptr; p.slot_busy = nullptr; p.n_slots = 0; p.acc_j = 0;
+    if (h->fused_det && !h->Sitem) {
+        const size_t ni = (size_t)std::max<int64_t>(1, h->n_items_tri);
+        if ((rc = dev_alloc(&h->Sitem, ni * h->qp)) || (rc = dev_alloc(&h->Fi, ni * 32 * 3)) ||
+            (rc = dev_alloc(&h->Fj, ni * (size_t)std::max<int64_t>(1, h->tri_maxlen) * 3)))
+            return rc;
+    }
+    p.Sitem = h->fused_det ? h->Sitem : nullptr;
     q.fo = p;
     q.fo.S = nullptr;
+    q.fo.Sitem = nullptr;
     q.fo.force = h->force;
+    q.fo.Fi = h->fused_det ? h->Fi : nullptr;
+    q.fo.Fj = h->fused_det ? h->Fj : nullptr;
+    q.fo.fj_len = (int)h->tri_maxlen;
     q.n_items = (int)h->n_items_tri;
     q.lf = lf ? 1 : 0;
     q.ctl = h->zc_ctl ? h->zc_ctl : h->lf_ctl; q.slab = h->lf_slab; q.mass = h->lf_mass;
@@ -2302,6 +2323,7 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "nw_max") h->nw_max = (int)std::max<int64_t>(1, std::min<int64_t>(12, value));
     else if (k == "zero_copy") h->zero_copy = value != 0;
     else if (k == "fused") h->use_fused = value != 0;
+    else if (k == "fused_det") h->fused_det = value != 0;
     else if (k == "acc_j") h->acc_j = (int)std::max<int64_t>(0, value);
     else if (k == "piece_div") {
         h->piece_div = (int)std::max<int64_t>(1, std::min<int64_t>(1024, value));

@@ -95,6 +95,13 @@ struct DebyeParams {
     float *Gscr;    // [n_slots][3 C][block threads]
     int *slot_busy; // [n_slots] 0 = free
     int n_slots, acc_j;
+    // Deterministic small-structure path (the fused evaluation kernel): instead
+    // of atomics every work item stores its partial sums, added later in item
+    // order.  Null = atomics.
+    double *Sitem = nullptr;  // MODE_FQ: [n_items][qp]
+    double *Fi = nullptr;     // MODE_FORCE: [n_items][32][3] forces on the item's i atoms
+    double *Fj = nullptr;     // MODE_FORCE: [n_items][fj_len][3] forces on its j atoms
+    int fj_len = 0;
 };
 
 // sin(2 pi f), cos(2 pi f) for |f| <= 1/8 turn: float32 minimax polynomials on

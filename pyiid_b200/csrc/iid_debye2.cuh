@@ -414,7 +414,14 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
             const float jy = warp_sum(-phi * d.y);
             const float jz = warp_sum(-phi * d.z);
             const int oj = p.orig[jt + jj];
-            if (lane == 0 && oj >= 0) {
+            if (p.Fj != nullptr) {  // deterministic: one store per (item, j atom)
+                if (lane == 0) {
+                    double *fj = p.Fj + ((size_t)bx * p.fj_len + (jt + jj - sg.jbegin)) * 3;
+                    fj[0] = (double)jx;
+                    fj[1] = (double)jy;
+                    fj[2] = (double)jz;
+                }
+            } else if (lane == 0 && oj >= 0) {
                 atomicAdd(&p.force[(size_t)oj * 3 + 0], (double)jx);
                 atomicAdd(&p.force[(size_t)oj * 3 + 1], (double)jy);
                 atomicAdd(&p.force[(size_t)oj * 3 + 2], (double)jz);
@@ -648,6 +655,24 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
             }
         }
     }
+    if constexpr (MODE == MODE_FORCE) {
+        if (p.Fi != nullptr) {
+            // deterministic i side: the warps' partial forces meet in shared
+            // memory and are added in warp order, one store per (item, atom)
+            float *fs = reinterpret_cast<float *>(smem_raw);  // [nwarp][3][32]
+            fs[(warp * 3 + 0) * 32 + lane] = active ? fix : 0.f;
+            fs[(warp * 3 + 1) * 32 + lane] = active ? fiy : 0.f;
+            fs[(warp * 3 + 2) * 32 + lane] = active ? fiz : 0.f;
+            __syncthreads();
+            if (threadIdx.x < 96) {
+                const int a = threadIdx.x & 31, w = threadIdx.x >> 5;
+                double t = 0.0;
+                for (int k = 0; k < nwarp; ++k) t += (double)fs[(k * 3 + w) * 32 + a];
+                p.Fi[((size_t)bx * 32 + a) * 3 + w] = t;
+            }
+            return;
+        }
+    }
     if (!active) return;
     if constexpr (MODE == MODE_GRAD) {
         // per-job partial of the F(Q) pair sum; reduce_spart_kernel adds the jobs
@@ -683,7 +708,9 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
                 v0 += (double)tr[lane * 33 + a];
                 v1 += (double)tr[lane * 33 + a + 1];
             }
-            atomicAdd(&p.S[bin], fweight * (v0 + v1) * (double)(fa[bin] * fb[bin]));
+            const double part = fweight * (v0 + v1) * (double)(fa[bin] * fb[bin]);
+            if (p.Sitem != nullptr) p.Sitem[(size_t)bx * p.qp + bin] = part;  // deterministic
+            else atomicAdd(&p.S[bin], part);
         }
     }
 }

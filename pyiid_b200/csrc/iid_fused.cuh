@@ -144,6 +144,18 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
         debye2_body<32, MODE_FQ, 8, CHEB>(q.fq, smem_raw, (int)blockIdx.x, 0);
     fused_stamp(q, 3);
     grid.sync();
+    if (q.fq.Sitem != nullptr) {
+        // deterministic F(Q): the items' partial sums added in item order, one
+        // warp per Q bin (lanes over items, butterfly sum)
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int m = blockIdx.x * nw + warp; m < nq; m += gridDim.x * nw) {
+            double acc = 0.0;
+            for (int it = lane; it < q.n_items; it += 32) acc += __ldcg(q.fq.Sitem + (size_t)it * qp + m);
+            acc = warp_sum(acc);
+            if (lane == 0) q.fq.S[m] = acc;
+        }
+        grid.sync();
+    }
     fused_stamp(q, 4);
 
     // ---- phase 2: F and this block's rows of M F ------------------------------------
@@ -213,8 +225,45 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
         debye2_body<32, MODE_FORCE, 8, CHEB>(fo, smem_raw, (int)blockIdx.x, 0);
     }
     fused_stamp(q, 8);
-    // ---- phase 4 (optional): results straight into the caller's pinned buffer -------
-    if (q.force_out) {
+    // ---- phase 4: (deterministic) the items' partial forces added in item order;
+    // (optional) results straight into the caller's pinned buffer -----------------
+    if (q.fo.Fi != nullptr) {
+        grid.sync();
+        // one warp per atom, lanes over the items (each lane adds its items in item
+        // order, then a butterfly sum: the same order on every run)
+        const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int g = blockIdx.x * nw + warp; g < q.np; g += gridDim.x * nw) {
+            const int o = q.fq.orig[g];
+            if (o < 0) continue;  // warp-uniform
+            const int tile = g / TILE_I, a = g - tile * TILE_I;
+            double fx = 0.0, fy = 0.0, fz = 0.0;
+            for (int it = lane; it < q.n_items; it += 32) {
+                const WorkItem wi = q.fq.items[it];
+                if (wi.itile == tile) {
+                    const double *fi = q.fo.Fi + ((size_t)it * 32 + a) * 3;
+                    fx += __ldcg(fi);
+                    fy += __ldcg(fi + 1);
+                    fz += __ldcg(fi + 2);
+                }
+                if (!(wi.info & ITEM_DIAG) && g >= wi.jbegin && g < wi.jend) {
+                    const double *fj = q.fo.Fj + ((size_t)it * q.fo.fj_len + (g - wi.jbegin)) * 3;
+                    fx += __ldcg(fj);
+                    fy += __ldcg(fj + 1);
+                    fz += __ldcg(fj + 2);
+                }
+            }
+            fx = warp_sum(fx);
+            fy = warp_sum(fy);
+            fz = warp_sum(fz);
+            if (lane < 3) {
+                const double f = lane == 0 ? fx : (lane == 1 ? fy : fz);
+                q.fo.force[(size_t)o * 3 + lane] = f;
+                if (q.force_out) q.force_out[(size_t)o * 3 + lane] = f;
+            }
+        }
+        if (q.force_out && gtid < 5) q.out_host[gtid] = __ldcg(q.out4 + gtid);
+    } else if (q.force_out) {
         grid.sync();
         const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
         for (int e = gtid; e < 3 * q.n; e += gsz) q.force_out[e] = __ldcg(q.fo.force + e);

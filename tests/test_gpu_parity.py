@@ -662,6 +662,58 @@ def test_nuts_trajectory_equals_the_reference_samplers():
         assert abs(ens.step_size - float(k['final_step_size'])) < 1e-6 * ens.step_size
 
 
+def test_seeded_nuts_run_reproduces_bit_for_bit():
+    """pyiid/tests/test_consistancy.py:8-16 holds every result to run-to-run
+    equality; a seeded sampler run on the device must reproduce as well (one
+    fused launch per leapfrog, device-resident states)."""
+    start, scat = make_hmc_atoms(3)
+    target = start.calc.target_data  # one target for both runs
+
+    def run():
+        atoms = start.copy()
+        atoms.set_calculator(Calc1D(target_data=target, exp_function=scat.get_pdf,
+                                    exp_grad_function=scat.get_grad_pdf, conv=100,
+                                    potential='rw'))
+        np.random.seed(4)
+        ens = sim.NUTSCanonicalEnsemble(atoms, temperature=600, escape_level=5, seed=11)
+        traj, meta = ens.run(4)
+        return (np.array([a.get_positions() for a in traj]),
+                np.array([a.get_potential_energy() for a in traj]), meta['samples_total'],
+                ens.step_size)
+
+    (q1, e1, n1, s1), (q2, e2, n2, s2) = run(), run()
+    assert n1 == n2 and s1 == s2 and np.array_equal(q1, q2) and np.array_equal(e1, e2)
+    # the evaluation itself: same bits every time, energy and forces
+    be = scat.pdf_backend
+    pos = start.get_positions()
+    ref = be.energy_forces(pos, target, 'rw', 100.)
+    for _ in range(5):
+        e, sc, f, _ = be.energy_forces(pos, target, 'rw', 100.)
+        assert e == ref[0] and sc == ref[1] and np.array_equal(f, ref[2])
+
+
+def test_pinned_output_pool_limit_falls_back_to_pageable_memory():
+    """When the pinned pool is exhausted the gradient goes through the staged
+    download into pageable memory -- same bits."""
+    from pyiid_b200 import hostmem
+    import gc
+    atoms = structures.alloy_sphere(300, seed=6)
+    scat = ElasticScatter()
+    g1 = scat.get_grad_fq(atoms)
+    assert hostmem.is_pinned(g1)
+    limit = hostmem.POOL_LIMIT_BYTES
+    keep = []
+    try:
+        gc.collect()
+        hostmem._pool.trim()                             # idle buffers of earlier tests
+        hostmem.POOL_LIMIT_BYTES = hostmem._pool.total  # nothing more may be allocated
+        keep = [scat.get_grad_fq(atoms) for _ in range(3)]
+    finally:
+        hostmem.POOL_LIMIT_BYTES = limit
+    assert any(not hostmem.is_pinned(g) for g in keep)
+    assert all(np.array_equal(g, g1) for g in keep)
+
+
 def test_array_level_nuts_equals_atoms_level_nuts():
     """The fast sampler path (plain arrays, one native call per leapfrog)
     reproduces the Atoms-level path: same random numbers, same trajectory."""
