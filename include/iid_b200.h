@@ -313,7 +313,8 @@ int iid_download_host(iid_handle *h, const void *dev, void *host, int64_t bytes)
  * "fused" (0/1: small structures evaluate in ONE cooperative launch),
  * "fused_det" (0/1: that launch adds its per-item partial sums in a fixed
  * order -- bit-reproducible energies, forces and sampler trajectories --
- * instead of atomics).  Defaults can also be set with IID_* environment variables
+ * instead of atomics), "det_fq" (0/1: the stand-alone F(Q) pass stores per-item
+ * partial sums and adds them in item order -- F(Q), G(r), Rw reproducible).  Defaults can also be set with IID_* environment variables
  * before iid_create. */
 int iid_set_option(iid_handle *h, const char *key, int64_t value);
 

@@ -141,6 +141,9 @@ struct iid_handle {
     double *MF = nullptr, *wq_blk = nullptr;  // fused kernel: (T^T T) F and per-block weights
     bool use_fused = true;        // one cooperative launch per evaluation of a small structure
     bool fused_det = true;        // ... bit-reproducible: per-item partial sums, fixed order
+    bool det_fq = true;           // stand-alone F(Q) pass: per-item partial sums + fixed-order reduce
+    double *Sitem_fq = nullptr;   // [this shard's items][qp]
+    size_t Sitem_fq_count = 0;
     double *Sitem = nullptr, *Fi = nullptr, *Fj = nullptr;
     int64_t tri_maxlen = 0;       // longest j range of a triangle item
     // zero-copy I/O of the fused kernel, set by the host entry points around
@@ -279,6 +282,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_ACC_J")) h->acc_j = std::max(0, atoi(s));
     if (const char *s = getenv("IID_FUSED")) h->use_fused = atoi(s) != 0;
     if (const char *s = getenv("IID_FUSED_DET")) h->fused_det = atoi(s) != 0;
+    if (const char *s = getenv("IID_DET_FQ")) h->det_fq = atoi(s) != 0;
     if (const char *s = getenv("IID_ZERO_COPY_SMALL")) h->zero_copy_small = atoi(s) != 0;
     *out = h;
     return 0;
@@ -292,7 +296,7 @@ extern "C" int iid_destroy(iid_handle *h)
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
                     h->inv_na, h->inv_na_d, h->items_tri, h->jobs, h->segs, h->fixes, h->Spart,
-                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->Sitem, h->Fi, h->Fj, h->T,
+                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->Sitem, h->Fi, h->Fj, h->Sitem_fq, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
                     h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf,
                     h->lf_slab, h->lf_mass, h->lf_ctl, h->lf_mirror};
@@ -1098,6 +1102,17 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     } else {
         const int64_t nitems = h->n_items_tri;
         mine = nitems > h->rank ? (nitems - h->rank + h->world - 1) / h->world : 0;
+        if (mode == MODE_FQ && h->det_fq && S && mine > 0) {
+            // deterministic F(Q): every item stores its partial sums, added in
+            // item order by reduce_spart_kernel (no atomics)
+            const size_t cnt = (size_t)mine * h->qp;
+            if (cnt > h->Sitem_fq_count) {
+                int rc = dev_alloc(&h->Sitem_fq, cnt);
+                h->Sitem_fq_count = rc ? 0 : cnt;
+                if (rc) return rc;
+            }
+            p.Sitem = h->Sitem_fq;
+        }
     }
     h->last_pairq = 0.5 * (double)h->n * (double)(h->n - 1) * (double)h->nq / h->world;
     int rc = 0;
@@ -1116,6 +1131,12 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
             else rc = launch_debye64_t<C64, MODE_FORCE>(h, p, mine, st);
         }
         if (rc) return rc;
+    }
+    if (!rows && p.Sitem != nullptr) {
+        reduce_spart_kernel<<<(unsigned)((h->nq + 31) / 32), 1024, 0, st>>>(
+            h->Sitem_fq, (int)mine, (int)h->nq, (int)h->qp, S);
+        ++h->launches;
+        CU(cudaGetLastError());
     }
     if (rows) {
         if (h->n_fixes > 0) {
@@ -2324,6 +2345,7 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "zero_copy") h->zero_copy = value != 0;
     else if (k == "fused") h->use_fused = value != 0;
     else if (k == "fused_det") h->fused_det = value != 0;
+    else if (k == "det_fq") h->det_fq = value != 0;
     else if (k == "acc_j") h->acc_j = (int)std::max<int64_t>(0, value);
     else if (k == "piece_div") {
         h->piece_div = (int)std::max<int64_t>(1, std::min<int64_t>(1024, value));

@@ -427,7 +427,9 @@ __global__ void __launch_bounds__(MAXT, 1) debye64_kernel(const DebyeParams p)
                 v0 += tr[lane * 33 + a];
                 v1 += tr[lane * 33 + a + 1];
             }
-            atomicAdd(&p.S[bin], fweight * (v0 + v1) * (fa[bin] * fb[bin]));
+            const double part = fweight * (v0 + v1) * (fa[bin] * fb[bin]);
+            if (p.Sitem != nullptr) p.Sitem[(size_t)blockIdx.x * p.qp + bin] = part;  // deterministic
+            else atomicAdd(&p.S[bin], part);
         }
     }
 }

@@ -168,6 +168,23 @@ def test_single_atom_and_empty_pair_list():
 
 
 # ---- API behaviour the reference's tests check -----------------------------------
+def test_fq_and_pdf_are_bit_reproducible_at_any_size():
+    """The stand-alone F(Q) pass stores per-item partial sums and adds them in
+    item order (no atomics): F(Q), G(r) and Rw energies reproduce bit for bit
+    (pyiid/tests/test_consistancy.py:8-16), many items and two elements included."""
+    atoms = structures.alloy_sphere(3000, seed=9)
+    for prec in ('fp32', 'fp64'):
+        scat = ElasticScatter(precision=prec)
+        f1, p1 = scat.get_fq(atoms), scat.get_pdf(atoms)
+        for _ in range(3):
+            assert np.array_equal(scat.get_fq(atoms), f1)
+            assert np.array_equal(scat.get_pdf(atoms), p1)
+        be = scat.pdf_backend
+        e1 = be.energy_forces(atoms.get_positions(), p1 * 1.01, 'rw', 1., want_forces=False)[0]
+        e2 = be.energy_forces(atoms.get_positions(), p1 * 1.01, 'rw', 1., want_forces=False)[0]
+        assert e1 == e2
+
+
 def test_smoke_every_method_returns_fresh_nonzero_arrays():
     """tests/test_scatter_smoke.py:13-181 and test_scatter.py:43."""
     atoms = structures.random_atoms(20, 3)
@@ -934,8 +951,9 @@ def test_two_scatter_objects_keep_their_own_handles():
     c0 = s1.backend.launch_count()
     for _ in range(3):
         assert np.array_equal(s1.get_fq(a1), f1) and np.array_equal(s2.get_fq(a2), f2)
-    # per call: staging + F(Q) pass + finish, no re-upload in between
-    assert s1.backend.launch_count() - c0 == 9
+    # per call: staging + F(Q) pass + fixed-order sum of the item partials +
+    # finish, no re-upload in between
+    assert s1.backend.launch_count() - c0 == 12
     assert s1.backend.sizes()['n'] == 30 and s2.backend.sizes()['n'] == 45
     g = s1.get_grad_pdf(structures.random_atoms(1, 0))
     assert g.shape == (1, 3, 4000) and not np.any(g)
