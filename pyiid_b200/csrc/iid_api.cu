@@ -144,6 +144,8 @@ struct iid_handle {
     bool det_fq = true;           // stand-alone F(Q) pass: per-item partial sums + fixed-order reduce
     double *Sitem_fq = nullptr;   // [this shard's items][qp]
     size_t Sitem_fq_count = 0;
+    double *ft_part = nullptr;    // tabulated force pass: [jsplit][np][3] partial sums
+    size_t ft_part_count = 0;
     double *Sitem = nullptr, *Fi = nullptr, *Fj = nullptr;
     int64_t tri_maxlen = 0;       // longest j range of a triangle item
     // zero-copy I/O of the fused kernel, set by the host entry points around
@@ -296,7 +298,7 @@ extern "C" int iid_destroy(iid_handle *h)
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
                     h->inv_na, h->inv_na_d, h->items_tri, h->jobs, h->segs, h->fixes, h->Spart,
-                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->Sitem, h->Fi, h->Fj, h->Sitem_fq, h->T,
+                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->Sitem, h->Fi, h->Fj, h->Sitem_fq, h->ft_part, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
                     h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf,
                     h->lf_slab, h->lf_mass, h->lf_ctl, h->lf_mirror};
@@ -1189,10 +1191,27 @@ static int launch_force(iid_handle *h, const double *wq, double *force, cudaStre
     if (mine > 0) {
         const int jsplit =
             std::max(1, std::min(np / TILE_I, (4 * h->sm_count + mine - 1) / mine));
+        // deterministic: the j shares of a row store their partial forces, added in
+        // share order afterwards (no atomics)
+        double *fpart = nullptr;
+        if (h->det_fq) {
+            const size_t cnt = (size_t)jsplit * np * 3;
+            if (cnt > h->ft_part_count) {
+                int rc = dev_alloc(&h->ft_part, cnt);
+                h->ft_part_count = rc ? 0 : cnt;
+                if (rc) return rc;
+            }
+            fpart = h->ft_part;
+        }
         force_table_kernel<<<dim3((unsigned)mine, (unsigned)jsplit), FT_BLOCK, 0, st>>>(
             h->x, h->y, h->z, h->valid, h->orig, h->tile_type, np, E, h->phi_info, h->phi_tab,
             jsplit, h->rank, h->world, force, wq, (const float *)h->ftab, (const float *)h->inv_na,
-            (int)h->nq, (int)h->qp, h->qbin);
+            (int)h->nq, (int)h->qp, h->qbin, fpart);
+        if (fpart) {
+            force_table_reduce_kernel<<<(3 * np + 255) / 256, 256, 0, st>>>(
+                fpart, jsplit, np, h->orig, h->rank, h->world, force);
+            ++h->launches;
+        }
     }
     h->launches += 3;
     CU(cudaGetLastError());

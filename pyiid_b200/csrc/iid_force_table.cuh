@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(FT_BLOCK) force_table_kernel(
     const int *__restrict__ tile_type, int np, int ntypes, const double *__restrict__ info,
     const float *__restrict__ tab, int jsplit, int row_begin, int row_stride,
     double *__restrict__ force, const double *__restrict__ wq, const float *__restrict__ ftab,
-    const float *__restrict__ inv_na, int nq, int qp, double qbin)
+    const float *__restrict__ inv_na, int nq, int qp, double qbin,
+    double *__restrict__ fpart)  // [jsplit][np][3]: deterministic partial sums (or null: atomics)
 {
     __shared__ double sx[FT_BLOCK], sy[FT_BLOCK], sz[FT_BLOCK];
     __shared__ int st[FT_BLOCK];
@@ -221,12 +222,37 @@ __global__ void __launch_bounds__(FT_BLOCK) force_table_kernel(
             fz = fma(phi, dz, fz);
         }
     }
-    if (vi) {
+    if (fpart != nullptr) {
+        if (gi < np) {
+            double *f = fpart + ((size_t)blockIdx.y * np + gi) * 3;
+            f[0] = vi ? fx : 0.0;
+            f[1] = vi ? fy : 0.0;
+            f[2] = vi ? fz : 0.0;
+        }
+    } else if (vi) {
         const int oi = orig[gi];
         atomicAdd(&force[(size_t)oi * 3 + 0], fx);
         atomicAdd(&force[(size_t)oi * 3 + 1], fy);
         atomicAdd(&force[(size_t)oi * 3 + 2], fz);
     }
+}
+
+// force[orig[g]] (+)= sum over the j shares of fpart[s][g], in share order, for
+// the rows this rank computed (rows row_begin, row_begin + row_stride, ...).
+__global__ void force_table_reduce_kernel(const double *__restrict__ fpart, int jsplit, int np,
+                                          const int *__restrict__ orig, int row_begin,
+                                          int row_stride, double *__restrict__ force)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 3 * np) return;
+    const int g = e / 3, w = e - 3 * g;
+    const int row = g / FT_BLOCK;
+    if (row < row_begin || (row - row_begin) % row_stride != 0) return;
+    const int o = orig[g];
+    if (o < 0) return;
+    double t = 0.0;
+    for (int s = 0; s < jsplit; ++s) t += fpart[((size_t)s * np + g) * 3 + w];
+    force[(size_t)o * 3 + w] += t;  // the only writer of this element in this pass
 }
 
 }  // namespace iid

@@ -183,6 +183,13 @@ def test_fq_and_pdf_are_bit_reproducible_at_any_size():
         e1 = be.energy_forces(atoms.get_positions(), p1 * 1.01, 'rw', 1., want_forces=False)[0]
         e2 = be.energy_forces(atoms.get_positions(), p1 * 1.01, 'rw', 1., want_forces=False)[0]
         assert e1 == e2
+        if prec == 'fp32':
+            # the tabulated force pass (FP32 mode, >= 600 atoms) adds the j shares
+            # of a row in share order: forces reproduce as well
+            r1 = be.energy_forces(atoms.get_positions(), p1 * 1.01, 'rw', 1.)
+            for _ in range(3):
+                r2 = be.energy_forces(atoms.get_positions(), p1 * 1.01, 'rw', 1.)
+                assert r2[0] == r1[0] and np.array_equal(r2[2], r1[2])
 
 
 def test_smoke_every_method_returns_fresh_nonzero_arrays():
