@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256, 1) mix(const float *in, int trips32, int 
 }
 
 template <int MODE>
-static float run(const float *in, int t32, int t64, float *out, int sms)
+static float run(const float *in, int t32, int t64, float *out, int sms, int threads = 256)
 {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
@@ -55,7 +55,7 @@ static float run(const float *in, int t32, int t64, float *out, int sms)
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(e0);
-        mix<MODE><<<sms, 256>>>(in, t32, t64, out);
+        mix<MODE><<<sms, threads>>>(in, t32, t64, out);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;
@@ -95,7 +95,15 @@ int main()
                "lane-FMA/clk/SM\n", m32, m64, ms, 4 * m32 * per_trip * 2 / (ms * 1e-3) / clk,
                4 * m64 * per_trip / (ms * 1e-3) / clk);
     }
-    // the halves alone at 4 warps/SM (one per scheduler)
+    // ONE warp per scheduler: can a lone warp keep the pipe busy?
+    for (int w = 1; w <= 8; w *= 2) {
+        ms = run<0>(in, t32, t64, out, sms, 32 * w);
+        printf("FFMA2, %d warp(s)/SM: %.1f lane-FMA/clk/SM\n", w, w * t32 * per_trip * 2 / (ms * 1e-3) / clk);
+    }
+    for (int w = 1; w <= 8; w *= 2) {
+        ms = run<1>(in, t32, t64, out, sms, 32 * w);
+        printf("DFMA,  %d warp(s)/SM: %.1f lane-FMA/clk/SM\n", w, w * t64 * per_trip / (ms * 1e-3) / clk);
+    }
     cudaFree(in);
     cudaFree(out);
     return 0;
