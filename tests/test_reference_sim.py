@@ -12,37 +12,16 @@ import pytest
 
 from pyiid_b200 import ase_shim
 
-REF = os.environ.get('PYIID_REFERENCE', '/root/reference')
-pytestmark = pytest.mark.skipif(
-    not os.path.isfile(os.path.join(REF, 'pyiid/sim/nuts_hmc.py')),
-    reason='reference mount not present')
+from pyiid.sim import reference
+
+REF = reference.REF
+pytestmark = pytest.mark.skipif(not reference.available(), reason='reference mount not present')
 
 
 def load_reference_sim():
-    ase_shim.install()
-    saved = {k: sys.modules.get(k) for k in ('pyiid', 'pyiid.sim', 'pyiid.sim.nuts_hmc')}
-    pkg = types.ModuleType('pyiid')
-    pkg.__path__ = [os.path.join(REF, 'pyiid')]
-    sys.modules['pyiid'] = pkg
-    try:
-        spec = importlib.util.spec_from_file_location(
-            'pyiid.sim', os.path.join(REF, 'pyiid/sim/__init__.py'),
-            submodule_search_locations=[os.path.join(REF, 'pyiid/sim')])
-        sim = importlib.util.module_from_spec(spec)
-        sys.modules['pyiid.sim'] = sim
-        spec.loader.exec_module(sim)
-        spec2 = importlib.util.spec_from_file_location(
-            'pyiid.sim.nuts_hmc', os.path.join(REF, 'pyiid/sim/nuts_hmc.py'))
-        nuts = importlib.util.module_from_spec(spec2)
-        sys.modules['pyiid.sim.nuts_hmc'] = nuts
-        spec2.loader.exec_module(nuts)
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
-    return sim, nuts
+    """The reference's sim/__init__.py and nuts_hmc.py, executed from the mount
+    by the package's own loader (pyiid/sim/reference.py)."""
+    return reference.load()
 
 
 class Harmonic(ase_shim.Calculator):
@@ -82,3 +61,13 @@ def test_reference_leapfrog_and_nuts_run_on_the_stand_ins(capsys):
     ens = Ensemble(a, temperature=300, escape_level=4, seed=3)
     traj, meta = ens.run(5)
     assert meta['samples_total'] > 0 and len(traj) >= 1
+    # the packaged class: the reference's NUTS with only the step-size search
+    # replaced (float exponent); pyiid.sim itself stays the B200 implementation
+    np.random.seed(1)
+    ens2 = reference.NUTSCanonicalEnsemble(a, temperature=300, escape_level=4, seed=3)
+    assert isinstance(ens2, nuts.NUTSCanonicalEnsemble) and ens2.step_size > 0
+    traj2, meta2 = ens2.run(3)
+    assert meta2['samples_total'] > 0
+    import pyiid.sim
+    from pyiid_b200 import sim as mysim2
+    assert pyiid.sim.leapfrog is mysim2.leapfrog
