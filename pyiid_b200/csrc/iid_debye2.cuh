@@ -664,8 +664,8 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
             fs[(warp * 3 + 1) * 32 + lane] = active ? fiy : 0.f;
             fs[(warp * 3 + 2) * 32 + lane] = active ? fiz : 0.f;
             __syncthreads();
-            if (threadIdx.x < 96) {
-                const int a = threadIdx.x & 31, w = threadIdx.x >> 5;
+            for (int e = threadIdx.x; e < 96; e += blockDim.x) {  // (a block may be one warp)
+                const int a = e & 31, w = e >> 5;
                 double t = 0.0;
                 for (int k = 0; k < nwarp; ++k) t += (double)fs[(k * 3 + w) * 32 + a];
                 p.Fi[((size_t)bx * 32 + a) * 3 + w] = t;

@@ -597,6 +597,34 @@ def test_random_experiments_against_oracle(seed):
         assert len(pdf) == len(scat.get_r())
 
 
+@pytest.mark.parametrize('qmax', [2.0, 45.0])
+def test_very_short_and_very_long_q_grids(qmax):
+    """Q grids outside the default: 20 bins (one warp per block) and 450 bins
+    (more chunks than one block holds: two blocks per item / row job share the
+    Q range), every pass, both precisions, energy + forces included."""
+    exp = {'qmin': 0.0, 'qmax': qmax, 'qbin': .1, 'rmin': 0.0, 'rmax': 20.0, 'rstep': .02}
+    atoms = structures.alloy_sphere(150, seed=12)
+    ideal = structures.alloy_sphere(150, seed=12, sigma=0.0)
+    for prec, tol in (('fp32', TOL32), ('fp64', TOL64)):
+        scat = ElasticScatter(dict(exp), precision=prec)
+        fq, grad, pdf = scat.get_fq(atoms), scat.get_grad_fq(atoms), scat.get_pdf(atoms)
+        pos = atoms.get_positions()
+        opos = pos.astype(np.float32) if prec == 'fp32' else pos
+        sf, sp = atoms.get_array('F(Q) scatter'), atoms.get_array('PDF scatter')
+        assert fq.shape == (int(qmax / .1),)
+        assert nerr(fq, oracle.experiment_fq(opos, sf, scat.exp, 'fp64')) < tol
+        assert nerr(grad, oracle.experiment_grad_fq(opos, sf, scat.exp, 'fp64')) < tol
+        assert nerr(pdf, oracle.experiment_pdf(opos, sp, scat.exp, 'fp64')) < tol
+        assert np.array_equal(grad, scat.get_grad_fq(atoms))
+        target = scat.get_pdf(ideal)
+        a = atoms.copy()
+        a.set_calculator(Calc1D(target_data=target, exp_function=scat.get_pdf,
+                                exp_grad_function=scat.get_grad_pdf, conv=5., potential='rw'))
+        e, f = a.get_potential_energy(), a.get_forces()
+        oe, of, _ = oracle.calc1d_energy_forces(opos, sp, scat.exp, target, 'rw', 5., 'fp64')
+        assert abs(e - oe) < 10 * tol * abs(oe) and nerr(f, of) < 10 * tol
+
+
 def test_sq_iq_follow_the_reference_formulas():
     """get_sq = F/Q + 1 (inf -> 0), get_iq = S * <f>^2 (__init__.py:393-446)."""
     atoms = structures.alloy_sphere(40, seed=9)
