@@ -324,7 +324,14 @@ class _DeviceSystem(_FastSystem):
         """The fused calculator on a single rank (the sharded evaluation goes
         through torch.distributed collectives on the host path)."""
         from .backend import _dist_state
-        return _FastSystem.usable(atoms) and _dist_state()[1] == 1
+        if not _FastSystem.usable(atoms) or _dist_state()[1] != 1:
+            return False
+        # the one-process multi-GPU handle keeps sampler states on device 0, which
+        # needs a structure that one device evaluates (below 2 x 1500 atoms)
+        calc = atoms.get_calculator()
+        plan = getattr(calc, '_plan', None)
+        scat = (plan[0] if plan is not None else calc)._fused
+        return not (getattr(scat, '_device_sel', None) == 'multi' and len(atoms) >= 3000)
 
     def state_of(self, atoms):
         st = _FastSystem.state_of(self, atoms)

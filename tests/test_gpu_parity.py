@@ -426,11 +426,42 @@ def test_one_process_multi_gpu_handle():
         res.append((a.get_potential_energy(), a.get_forces()))
     assert abs(res[0][0] - res[1][0]) < 1e-6 * abs(res[0][0])
     assert nerr(res[1][1], res[0][1]) < TOL32
-    # a small structure stays on one device (sampler path included)
+    # restraints ride along: MultiCalc(Calc1D + rep spring) on all devices
+    from pyiid_b200.spring_calc import Spring
+    from pyiid_b200.multi_calc import MultiCalc
+    res = []
+    for scat in (one, many):
+        a = atoms.copy()
+        c1 = Calc1D(target_data=target, exp_function=scat.get_pdf,
+                    exp_grad_function=scat.get_grad_pdf, conv=100., potential='rw')
+        a.set_calculator(MultiCalc(calc_list=[c1, Spring(k=10., rt=2.9, sp_type='rep')]))
+        res.append((a.get_potential_energy(), a.get_forces()))
+    assert abs(res[0][0] - res[1][0]) < 1e-6 * abs(res[0][0])
+    assert nerr(res[1][1], res[0][1]) < TOL32
+    # a small structure stays on one device, the device-resident sampler included
     small = structures.random_atoms(50, 1)
     assert nerr(many.get_fq(small), one.get_fq(small)) < 1e-6
     assert many.backend.devices()[1] == 1
     assert nerr(many.get_grad_pdf(small), one.get_grad_pdf(small)) < 1e-6
+    ico = structures.icosahedron('Au', 2)
+    tgt = many.get_pdf(ico)
+    trajs = []
+    for scat in (one, many):
+        a = ico.copy()
+        a.positions *= 1.03
+        a.set_calculator(Calc1D(target_data=tgt, exp_function=scat.get_pdf,
+                                exp_grad_function=scat.get_grad_pdf, conv=100., potential='rw'))
+        np.random.seed(2)
+        ens = sim.NUTSCanonicalEnsemble(a, temperature=300, escape_level=4, seed=5)
+        assert ens.device_states
+        traj, _ = ens.run(3)
+        trajs.append(np.array([x.get_positions() for x in traj]))
+    assert trajs[0].shape == trajs[1].shape and np.allclose(trajs[0], trajs[1], atol=1e-9)
+    # a large one cannot keep sampler states on one device: array-level path
+    big = atoms.copy()
+    big.set_calculator(Calc1D(target_data=target, exp_function=many.get_pdf,
+                              exp_grad_function=many.get_grad_pdf, conv=100., potential='rw'))
+    assert sim._FastSystem.usable(big) and not sim._DeviceSystem.usable(big)
 
 
 def test_10k_fp32_agrees_with_fp64_mode(big):
