@@ -656,6 +656,61 @@ def test_very_short_and_very_long_q_grids(qmax):
         assert abs(e - oe) < 10 * tol * abs(oe) and nerr(f, of) < 10 * tol
 
 
+def test_five_element_types():
+    """More element runs than the tabulated force pass takes (<= 4): every run is
+    padded to a multiple of 32 and the row jobs flush once per run."""
+    rs = np.random.RandomState(21)
+    n = 260
+    numbers = rs.choice([26, 28, 46, 47, 79], n)
+    atoms = ase_shim.Atoms(numbers=numbers, positions=structures.fcc_sphere_positions(n, 3.9, 0.05, 3))
+    ideal = ase_shim.Atoms(numbers=numbers, positions=structures.fcc_sphere_positions(n, 3.9, 0.0, 3))
+    exp = oracle.DEFAULT_EXP
+    for prec, tol in (('fp32', TOL32), ('fp64', TOL64)):
+        scat = ElasticScatter(precision=prec)
+        fq, grad, pdf = scat.get_fq(atoms), scat.get_grad_fq(atoms), scat.get_pdf(atoms)
+        pos = atoms.get_positions()
+        opos = pos.astype(np.float32) if prec == 'fp32' else pos
+        sf, sp = atoms.get_array('F(Q) scatter'), atoms.get_array('PDF scatter')
+        assert nerr(fq, oracle.experiment_fq(opos, sf, exp, 'fp64')) < tol
+        assert nerr(grad, oracle.experiment_grad_fq(opos, sf, exp, 'fp64')) < tol
+        assert nerr(pdf, oracle.experiment_pdf(opos, sp, exp, 'fp64')) < tol
+        target = scat.get_pdf(ideal)
+        a = atoms.copy()
+        a.set_calculator(Calc1D(target_data=target, exp_function=scat.get_pdf,
+                                exp_grad_function=scat.get_grad_pdf, conv=5., potential='chi_sq'))
+        e, f = a.get_potential_energy(), a.get_forces()
+        oe, of, _ = oracle.calc1d_energy_forces(opos, sp, exp, target, 'chi_sq', 5., 'fp64')
+        assert abs(e - oe) < 10 * tol * abs(oe) and nerr(f, of) < 10 * tol
+
+
+@pytest.mark.parametrize('potential', ['rw', 'chi_sq'])
+def test_fused_launch_equals_the_launch_sequence(potential):
+    """Small structures evaluate in ONE cooperative launch with the potential in
+    Q space (gc.go = F.(T^T go), gc.gc = F.(T^T T F)); it must give what the
+    sequence of launches (G(r) in r space, potential_kernel, force pass with
+    atomics) gives, deterministic sums or not, with and without a fused spring."""
+    atoms, scat = make_hmc_atoms(5)
+    be = scat.pdf_backend
+    pos, target = atoms.get_positions(), atoms.calc.target_data
+    for springs in ([], [('rep', 10., 2.95)]):
+        be.set_restraints(springs)
+        res = {}
+        for fused, det in ((0, 1), (1, 0), (1, 1)):
+            be.set_option('fused', fused)
+            be.set_option('fused_det', det)
+            for _ in range(4):  # eager, eager, capture, replay
+                out = be.energy_forces(pos, target, potential, 100.)
+            res[fused, det] = (out[0], out[1], out[2], be.restraint_energy)
+        be.set_option('fused', 1)
+        be.set_option('fused_det', 1)
+        e0, s0, f0, r0 = res[0, 1]
+        for key in ((1, 0), (1, 1)):
+            e, sc, f, r = res[key]
+            assert abs(e - e0) < 1e-9 * abs(e0) and abs(sc - s0) < 1e-9 * abs(s0)
+            assert nerr(f, f0) < 2e-6 and abs(r - r0) <= 1e-12 * max(1., abs(r0))
+    be.set_restraints([])
+
+
 def test_sq_iq_follow_the_reference_formulas():
     """get_sq = F/Q + 1 (inf -> 0), get_iq = S * <f>^2 (__init__.py:393-446)."""
     atoms = structures.alloy_sphere(40, seed=9)
