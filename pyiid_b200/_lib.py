@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libiid_b200.so')
+# IID_LIB_PATH: a differently built copy of the library (developer A/B runs)
+LIB_PATH = os.environ.get('IID_LIB_PATH') or os.path.join(_HERE, 'libiid_b200.so')
 
 IID_FP32, IID_FP64 = 0, 1
 IID_POT_RW, IID_POT_CHI_SQ = 0, 1
