@@ -293,6 +293,16 @@ int iid_state_download(iid_handle *h, int slot, double *q_host, double *p_host,
 int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, int centre,
                       const double *target_host, int potential, double conv,
                       double *out_host, double *q_host, double *p_host);
+/* n_steps (<= IID_LF_CHAIN) consecutive steps src -> dst[0] -> dst[1] -> ...
+ * of the same size, queued behind each other with ONE synchronisation: what
+ * buildtree (nuts_hmc.py:15-88) asks for when it grows a subtree of depth j
+ * (2^j leapfrogs in a row).  out_host[n_steps][9], q_host / p_host
+ * [n_steps][n*3] (may be NULL) as iid_leapfrog_host, one row per step. */
+#define IID_LF_CHAIN 16
+int iid_leapfrog_chain_host(iid_handle *h, int src, const int *dst, int n_steps,
+                            double step, int centre, const double *target_host,
+                            int potential, double conv, double *out_host,
+                            double *q_host, double *p_host);
 
 /* Device array -> pageable host memory through pipelined pinned staging,
  * ordered after the work already enqueued on the handle's stream; complete on

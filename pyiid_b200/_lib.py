@@ -16,6 +16,7 @@ IID_FP32, IID_FP64 = 0, 1
 IID_POT_RW, IID_POT_CHI_SQ = 0, 1
 IID_SPRING_REP, IID_SPRING_COM, IID_SPRING_ATT = 0, 1, 2
 IID_MAX_RESTRAINTS = 4
+IID_LF_CHAIN = 16
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -72,6 +73,7 @@ SIGNATURES = {
     'iid_state_upload': [_vp, _int, _vp, _vp, _vp],
     'iid_state_download': [_vp, _int, _vp, _vp, _vp],
     'iid_leapfrog_host': [_vp, _int, _int, _dbl, _int, _vp, _int, _dbl, _vp, _vp, _vp],
+    'iid_leapfrog_chain_host': [_vp, _int, _vp, _int, _dbl, _int, _vp, _int, _dbl, _vp, _vp, _vp],
     'iid_set_option': [_vp, ctypes.c_char_p, _i64],
     'iid_launch_count': [_vp, _pi64],
     'iid_last_kernel_ms': [_vp, ctypes.POINTER(ctypes.c_float),

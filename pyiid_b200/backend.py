@@ -536,6 +536,32 @@ class Backend(object):
         self._target_done(target, tkey)
         return out[0], out[1], out[4], out[5], q, p
 
+    def leapfrog_chain(self, src, dsts, step, center, target, potential='rw', conv=1.):
+        """``len(dsts)`` consecutive leapfrog steps src -> dsts[0] -> dsts[1] ...
+        queued behind each other with one synchronisation
+        (``iid_leapfrog_chain_host``); returns a list of
+        (energy, scale, restraint energy, kinetic energy, q, p), one per step."""
+        if potential not in POTENTIALS:
+            raise NotImplementedError('Potential not implemented')
+        if target is not self._last_target:
+            target = np.ascontiguousarray(target, dtype=np.float64)
+            if target.shape != (self.nr,):
+                raise ValueError('target must have the r-grid length %d' % self.nr)
+            self.sync_shard()
+        if self.world != 1:
+            raise _lib.IIDError('the device-resident leapfrog needs world == 1')
+        m = len(dsts)
+        tptr, tkey = self._target_ptr(target)
+        d = np.asarray(dsts, dtype=np.int32)
+        out = np.empty((m, 9), np.float64)
+        q = np.empty((m, self.n, 3), np.float64)
+        p = np.empty((m, self.n, 3), np.float64)
+        check(self.lib.iid_leapfrog_chain_host(
+            self.h, int(src), d.ctypes.data, m, float(step), int(bool(center)), tptr,
+            POTENTIALS[potential], float(conv), out.ctypes.data, q.ctypes.data, p.ctypes.data))
+        self._target_done(target, tkey)
+        return [(out[i, 0], out[i, 1], out[i, 4], out[i, 5], q[i], p[i]) for i in range(m)]
+
     # -- spring restraints (calc/spring_calc.py) -------------------------------
     def set_restraints(self, springs):
         """rep / att springs [(sp_type, k, rt), ...] evaluated inside

@@ -181,7 +181,10 @@ struct iid_handle {
     int slab_override = 0;
     // CUDA graph of the fused energy+forces sequence (small-N latency)
     GraphSlot ef;  // iid_energy_forces_host
-    GraphSlot lf;  // iid_leapfrog_host
+    GraphSlot lf[IID_LF_CHAIN];  // iid_leapfrog_host / _chain_host: one per ring slot of the pinned staging
+    GraphSlot lf_chain[IID_LF_CHAIN];  // [k-1]: a chain of k steps inside one fused launch
+    int zc_chain = 1;
+    bool chain_in_kernel = true;
     bool use_graph = true;
     // device-resident sampler states (iid_leapfrog_host): slot = (q, p, f)
     double *lf_slab = nullptr;   // [lf_slots][3][3n]
@@ -205,6 +208,7 @@ struct iid_handle {
 };
 
 static int upload_row_jobs(iid_handle *h);
+static void drop_graph(iid_handle *h);
 static int multi_destroy(iid_handle *h);
 static int multi_need_subs(iid_handle *h, int count);
 static int multi_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
@@ -284,6 +288,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_ACC_J")) h->acc_j = std::max(0, atoi(s));
     if (const char *s = getenv("IID_FUSED")) h->use_fused = atoi(s) != 0;
     if (const char *s = getenv("IID_FUSED_DET")) h->fused_det = atoi(s) != 0;
+    if (const char *s = getenv("IID_CHAIN_IN_KERNEL")) h->chain_in_kernel = atoi(s) != 0;
     if (const char *s = getenv("IID_DET_FQ")) h->det_fq = atoi(s) != 0;
     if (const char *s = getenv("IID_ZERO_COPY_SMALL")) h->zero_copy_small = atoi(s) != 0;
     *out = h;
@@ -309,8 +314,7 @@ extern "C" int iid_destroy(iid_handle *h)
     for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    h->ef.drop();
-    h->lf.drop();
+    drop_graph(h);
     if (h->lf_pin) cudaFreeHost(h->lf_pin);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -342,7 +346,8 @@ extern "C" int iid_synchronize(iid_handle *h)
 static void drop_graph(iid_handle *h)
 {
     h->ef.drop();
-    h->lf.drop();
+    for (GraphSlot &g : h->lf) g.drop();
+    for (GraphSlot &g : h->lf_chain) g.drop();
 }
 
 extern "C" int iid_set_shard(iid_handle *h, int rank, int world)
@@ -1821,6 +1826,8 @@ static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
     q.force_out = h->n_restraints ? nullptr : h->zc_force_out;
     q.out_host = h->zc_out;
     q.lf_mirror = (lf && !h->n_restraints) ? h->zc_lf_mirror : nullptr;
+    q.n_chain = (lf && q.lf_mirror) ? h->zc_chain : 1;
+    q.chain_stride = (int)(LF_CTL + 6 * h->n + 16);
     q.n = (int)h->n; q.np = (int)h->np; q.round_f32 = 1;
     q.inv_na_d = h->inv_na_d; q.Mq = h->Mq; q.vgo = h->vgo; q.gogo = h->gogo;
     q.MF = h->MF; q.wq_blk = h->wq_blk;
@@ -2101,7 +2108,7 @@ extern "C" int iid_sampler_setup(iid_handle *h, int64_t n_slots, const double *m
     for (int64_t i = 0; i < h->n; ++i)
         if (!(masses_host[i] > 0.0)) return fail(IID_E_BADARG, "masses must be positive");
     CU(cudaStreamSynchronize(h->stream));
-    h->lf.drop();
+    for (GraphSlot &g : h->lf) g.drop();
     const size_t n3 = (size_t)3 * h->n;
     int rc;
     if (h->lf_slab) { cudaFree(h->lf_slab); h->lf_slab = nullptr; }
@@ -2110,7 +2117,8 @@ extern "C" int iid_sampler_setup(iid_handle *h, int64_t n_slots, const double *m
         (rc = dev_alloc(&h->lf_mirror, 2 * n3 + 16)))
         return rc;
     h->lf_slots = n_slots;
-    const size_t need = LF_CTL + 2 * n3 + 16;
+    // a ring of IID_LF_CHAIN staging slots: step parameters in, mirror of the new state out
+    const size_t need = (size_t)IID_LF_CHAIN * (LF_CTL + 2 * n3 + 16);
     if (need > h->lf_pin_count) {
         if (h->lf_pin) cudaFreeHost(h->lf_pin);
         h->lf_pin = nullptr;
@@ -2120,7 +2128,8 @@ extern "C" int iid_sampler_setup(iid_handle *h, int64_t n_slots, const double *m
     CU(cudaMemcpy(h->lf_mass, masses_host, h->n * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemset(h->lf_slab, 0, (size_t)n_slots * 3 * n3 * sizeof(double)));
     CU(cudaStreamSynchronize(0));
-    for (int w = 0; w < 3; ++w) h->lf_pin[4 + w] = cell_centre[w];
+    for (int r = 0; r < IID_LF_CHAIN; ++r)
+        for (int w = 0; w < 3; ++w) h->lf_pin[(size_t)r * (LF_CTL + 2 * n3 + 16) + 4 + w] = cell_centre[w];
     h->lf_system = true;
     return 0;
 }
@@ -2167,32 +2176,33 @@ extern "C" int iid_state_download(iid_handle *h, int slot, double *q_host, doubl
     return 0;
 }
 
-extern "C" int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, int centre,
-                                 const double *target_host, int potential, double conv,
-                                 double *out_host, double *q_host, double *p_host)
+// Ring slot `ring` of the pinned staging: the step's parameters, then the mirror
+// of the state it produces.
+static inline size_t lf_ring_stride(const iid_handle *h) { return LF_CTL + 6 * (size_t)h->n + 16; }
+
+static void leapfrog_fill(iid_handle *h, int ring, int src, int dst, double step, int centre)
 {
-    if (MULTI(h)) {
-        if (h->active != 1)
-            return fail(IID_E_BADARG, "device-resident sampler states need a one-device structure");
-        return iid_leapfrog_host(h->subs[0], src, dst, step, centre, target_host, potential, conv,
-                                 out_host, q_host, p_host);
-    }
-    NEED(h);
-    if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
-    if (h->world != 1)
-        return fail(IID_E_BADARG, "iid_leapfrog_host needs the whole pair list (world == 1)");
-    int rc;
-    if ((rc = check_slot(h, src)) || (rc = check_slot(h, dst))) return rc;
-    if (src == dst) return fail(IID_E_BADARG, "source and destination slot must differ");
-    if (!out_host) return fail(IID_E_BADARG, "null pointer");
-    const size_t n3 = (size_t)3 * h->n;
-    double *pt = h->pin + 6 * h->n + h->qp + 8 + h->nr;  // target staging of the handle
-    if ((rc = refresh_target(h, target_host, pt))) return rc;
-    double *ctl = h->lf_pin, *mir = ctl + LF_CTL, *po = mir + 2 * n3;
+    double *ctl = h->lf_pin + (size_t)ring * lf_ring_stride(h);
     ctl[0] = step;
     ctl[1] = (double)src;
     ctl[2] = (double)dst;
     ctl[3] = centre ? 1.0 : 0.0;
+}
+
+// The fused kernel can walk a chain of steps inside ONE cooperative launch.
+static bool leapfrog_in_kernel(const iid_handle *h)
+{
+    return h->zero_copy_small && !h->n_restraints && h->chain_in_kernel &&
+           fused_applicable(h, true, false);
+}
+
+// Enqueue n_chain leapfrog steps whose parameters / mirrors live in ring slots
+// ring .. ring + n_chain - 1 of the pinned staging (no synchronisation).
+// n_chain > 1 only with leapfrog_in_kernel().
+static int leapfrog_enqueue(iid_handle *h, int ring, int n_chain, int potential, double conv)
+{
+    const size_t n3 = (size_t)3 * h->n;
+    double *ctl = h->lf_pin + (size_t)ring * lf_ring_stride(h), *mir = ctl + LF_CTL;
     const int n = (int)h->n;
     // small structures: the kernels read the step parameters from, and write the
     // new state's mirror to, the pinned staging directly -- no copy nodes
@@ -2204,9 +2214,11 @@ extern "C" int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, i
                                h->stream));
         h->zc_ctl = zc ? ctl : nullptr;
         h->zc_lf_mirror = zc ? mir : nullptr;  // no restraints: the step finishes in this launch
+        h->zc_chain = n_chain;
         rc2 = enqueue_eval_device(h, potential, conv, true, true);
         h->zc_ctl = nullptr;
         h->zc_lf_mirror = nullptr;
+        h->zc_chain = 1;
         if (rc2) return rc2;
         if (zc && !h->n_restraints) return 0;
         lf_finish_kernel<<<1, 1024, 0, h->stream>>>(zc ? ctl : h->lf_ctl, h->lf_slab, h->lf_mass, n,
@@ -2220,13 +2232,76 @@ extern "C" int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, i
         return 0;
     };
     const bool graphable = h->use_graph && !h->timing;
-    if ((rc = run_graphed(h, h->lf, graphable, potential, conv, false, enqueue))) return rc;
-    CU(cudaStreamSynchronize(h->stream));
+    // one graph per (ring slot, 1 step) and one per (ring slot 0, chain length)
+    GraphSlot &g = n_chain > 1 ? h->lf_chain[n_chain - 1] : h->lf[ring];
+    return run_graphed(h, g, graphable, potential, conv, false, enqueue);
+}
+
+static void leapfrog_collect(iid_handle *h, int ring, double *out_host, double *q_host,
+                             double *p_host)
+{
+    const size_t n3 = (size_t)3 * h->n;
+    const double *mir = h->lf_pin + (size_t)ring * lf_ring_stride(h) + LF_CTL;
+    const double *po = mir + 2 * n3;
     // out: energy, scale, -, -, restraint energy, kinetic energy, shift x y z
     for (int k = 0; k < 9; ++k) out_host[k] = po[k];
     if (!h->n_restraints) out_host[4] = 0.0;
     if (q_host) memcpy(q_host, mir, n3 * sizeof(double));
     if (p_host) memcpy(p_host, mir + n3, n3 * sizeof(double));
+}
+
+extern "C" int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, int centre,
+                                 const double *target_host, int potential, double conv,
+                                 double *out_host, double *q_host, double *p_host)
+{
+    return iid_leapfrog_chain_host(h, src, &dst, 1, step, centre, target_host, potential, conv,
+                                   out_host, q_host, p_host);
+}
+
+// n_steps consecutive leapfrog steps src -> dst[0] -> dst[1] -> ... with ONE
+// synchronisation at the end: the launches queue up behind each other, so the
+// launch latency, the wake-up of the host and its per-call work are paid once
+// per chain instead of once per step (a NUTS subtree of depth j is 2^j such
+// steps in a row, pyiid/sim/nuts_hmc.py:15-88).
+extern "C" int iid_leapfrog_chain_host(iid_handle *h, int src, const int *dst, int n_steps,
+                                       double step, int centre, const double *target_host,
+                                       int potential, double conv, double *out_host,
+                                       double *q_host, double *p_host)
+{
+    if (MULTI(h)) {
+        if (h->active != 1)
+            return fail(IID_E_BADARG, "device-resident sampler states need a one-device structure");
+        return iid_leapfrog_chain_host(h->subs[0], src, dst, n_steps, step, centre, target_host,
+                                       potential, conv, out_host, q_host, p_host);
+    }
+    NEED(h);
+    if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
+    if (h->world != 1)
+        return fail(IID_E_BADARG, "iid_leapfrog_host needs the whole pair list (world == 1)");
+    if (!dst || !out_host || n_steps < 1 || n_steps > IID_LF_CHAIN)
+        return fail(IID_E_BADARG, "need 1 <= n_steps <= IID_LF_CHAIN, dst and out");
+    int rc;
+    if ((rc = check_slot(h, src))) return rc;
+    for (int i = 0; i < n_steps; ++i) {
+        if ((rc = check_slot(h, dst[i]))) return rc;
+        if (dst[i] == (i ? dst[i - 1] : src))
+            return fail(IID_E_BADARG, "source and destination slot must differ");
+    }
+    const size_t n3 = (size_t)3 * h->n;
+    double *pt = h->pin + 6 * h->n + h->qp + 8 + h->nr;  // target staging of the handle
+    if ((rc = refresh_target(h, target_host, pt))) return rc;
+    for (int i = 0; i < n_steps; ++i) leapfrog_fill(h, i, i ? dst[i - 1] : src, dst[i], step, centre);
+    if (n_steps > 1 && leapfrog_in_kernel(h)) {
+        // the whole chain in one cooperative launch
+        if ((rc = leapfrog_enqueue(h, 0, n_steps, potential, conv))) return rc;
+    } else {
+        for (int i = 0; i < n_steps; ++i)
+            if ((rc = leapfrog_enqueue(h, i, 1, potential, conv))) return rc;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n_steps; ++i)
+        leapfrog_collect(h, i, out_host + 9 * (size_t)i, q_host ? q_host + n3 * i : nullptr,
+                         p_host ? p_host + n3 * i : nullptr);
     return 0;
 }
 
@@ -2364,6 +2439,7 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "zero_copy") h->zero_copy = value != 0;
     else if (k == "fused") h->use_fused = value != 0;
     else if (k == "fused_det") h->fused_det = value != 0;
+    else if (k == "chain_in_kernel") h->chain_in_kernel = value != 0;
     else if (k == "det_fq") h->det_fq = value != 0;
     else if (k == "acc_j") h->acc_j = (int)std::max<int64_t>(0, value);
     else if (k == "piece_div") {

@@ -73,7 +73,15 @@ __device__ __forceinline__ void sincos_turns(double u, float &s, float &c)
 // The kernel body, callable from the stand-alone kernel below and from the
 // fused evaluation kernel (iid_fused.cuh): block (bx, by) of a launch with
 // dynamic shared memory `smem_raw`.
-template <int C, int MODE, int TJ2, bool CHEB, int PU = 1>
+// LDCG: the staged positions are read past L1 (the fused kernel rewrites them
+// between the steps of a chain within one launch).
+template <bool LDCG>
+__device__ __forceinline__ double ld_pos(const double *a)
+{
+    return LDCG ? __ldcg(a) : *a;
+}
+
+template <int C, int MODE, int TJ2, bool CHEB, int PU = 1, bool LDCG = false>
 __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char *smem_raw,
                                             const int bx, const int by)
 {
@@ -110,7 +118,7 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
     float fw = (MODE == MODE_GRAD && (diag || !p.grad_split)) ? 0.5f : 1.f;
     const int atype = p.tile_type[itile];
     const int gi = itile * TILE_I + lane;
-    const double xi = p.x[gi], yi = p.y[gi], zi = p.z[gi];
+    const double xi = ld_pos<LDCG>(p.x + gi), yi = ld_pos<LDCG>(p.y + gi), zi = ld_pos<LDCG>(p.z + gi);
     const bool vi = p.valid[gi] != 0.f;
 
     const float *ftab = reinterpret_cast<const float *>(p.ftab);
@@ -182,7 +190,8 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
                 pr[u] = live[u] ? want : pr0;  // a dead slot recomputes pair pr0, stores nothing
                 const int jj = pr[u] >> 5;     // (pr & 31) == lane: this thread's own atom i
                 const int gj = jt + jj;
-                const double dxd = p.x[gj] - xi, dyd = p.y[gj] - yi, dzd = p.z[gj] - zi;
+                const double dxd = ld_pos<LDCG>(p.x + gj) - xi, dyd = ld_pos<LDCG>(p.y + gj) - yi,
+                             dzd = ld_pos<LDCG>(p.z + gj) - zi;
                 const bool keep = vi && p.valid[gj] != 0.f;
                 const double r2 = fma(dxd, dxd, fma(dyd, dyd, dzd * dzd));
                 const float r2f = (float)r2;

@@ -45,6 +45,8 @@ struct FusedParams {
     double *out_host;      // [5] host copy of out4 (or null)
     double *lf_mirror;     // leapfrog: finish the step in this launch (half kick, kinetic
                            // energy, centring) and mirror (q, p, scalars) here (or null)
+    int n_chain;           // leapfrog steps walked by this launch (ctl / lf_mirror of step s
+    int chain_stride;      // at + s * chain_stride doubles); 1 unless lf_mirror is set
     int n, np, round_f32;
     // Q-space stages
     const double *inv_na_d, *Mq, *vgo;
@@ -86,6 +88,11 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
     cg::grid_group grid = cg::this_grid();
     const int nq = q.fq.nq, qp = q.fq.qp;
 
+  for (int cs = 0; cs < q.n_chain; ++cs) {
+    // a chain of leapfrog steps: step cs reads its parameters from, and mirrors
+    // its state to, ring slot cs of the pinned staging.  Everything another block
+    // wrote in an EARLIER step of this launch is read past L1 (ld.cg).
+    const double *ctl = q.ctl + (size_t)cs * q.chain_stride;
     fused_stamp(q, 0);
     // ---- phase 0: staging ---------------------------------------------------------
     {
@@ -99,8 +106,8 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
                 if (q.lf) {
                     // p_half = p + (step/2) f; q' = q + step p_half / m (numpy's
                     // operation order, see lf_stage_kernel)
-                    const double step = q.ctl[0];
-                    const int src = (int)q.ctl[1], dst = (int)q.ctl[2];
+                    const double step = ctl[0];
+                    const int src = (int)ctl[1], dst = (int)ctl[2];
                     const double *qq = lf_slot(q.slab, q.n, src, 0),
                                  *pp = lf_slot(q.slab, q.n, src, 1),
                                  *ff = lf_slot(q.slab, q.n, src, 2);
@@ -109,9 +116,9 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
 #pragma unroll
                     for (int w = 0; w < 3; ++w) {
                         const size_t e = 3 * (size_t)o + w;
-                        const double ph = __dadd_rn(pp[e], __dmul_rn(half, ff[e]));
+                        const double ph = __dadd_rn(__ldcg(pp + e), __dmul_rn(half, __ldcg(ff + e)));
                         pd[e] = ph;
-                        const double qn = __dadd_rn(qq[e], __dmul_rn(step, __ddiv_rn(ph, m)));
+                        const double qn = __dadd_rn(__ldcg(qq + e), __dmul_rn(step, __ddiv_rn(ph, m)));
                         q.pos[e] = qn;
                         c[w] = qn;
                     }
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
 
     // ---- phase 1: F(Q) pass -------------------------------------------------------
     if ((int)blockIdx.x < q.n_items)
-        debye2_body<32, MODE_FQ, 8, CHEB>(q.fq, smem_raw, (int)blockIdx.x, 0);
+        debye2_body<32, MODE_FQ, 8, CHEB, 1, true>(q.fq, smem_raw, (int)blockIdx.x, 0);
     fused_stamp(q, 3);
     grid.sync();
     if (q.fq.Sitem != nullptr) {
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
     if ((int)blockIdx.x < q.n_items) {
         DebyeParams fo = q.fo;
         fo.wq = wq;
-        debye2_body<32, MODE_FORCE, 8, CHEB>(fo, smem_raw, (int)blockIdx.x, 0);
+        debye2_body<32, MODE_FORCE, 8, CHEB, 1, true>(fo, smem_raw, (int)blockIdx.x, 0);
     }
     fused_stamp(q, 8);
     // ---- phase 4: (deterministic) the items' partial forces added in item order;
@@ -273,8 +280,13 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
     if (q.lf_mirror) {
         grid.sync();
         if (blockIdx.x == 0)
-            lf_finish_body(q.ctl, q.slab, q.mass, q.n, q.pos, q.fo.force, q.lf_mirror, q.out4);
+            lf_finish_body(ctl, q.slab, q.mass, q.n, q.pos, q.fo.force,
+                           q.lf_mirror + (size_t)cs * q.chain_stride, q.out4);
+        // the next step's staging reads the state this block is writing and
+        // clears the accumulators it is reading
+        if (cs + 1 < q.n_chain) grid.sync();
     }
+  }
 }
 
 }  // namespace iid

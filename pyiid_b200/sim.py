@@ -19,6 +19,8 @@ from collections import namedtuple
 from copy import deepcopy as dc
 from time import time
 
+import collections
+
 import numpy as np
 from numpy.random import RandomState
 
@@ -228,6 +230,10 @@ class _FastSystem(object):
         self.evals += 1
         return float(e) + be.restraint_energy, f
 
+    def expect(self, n):
+        """Hint: the next ``n`` leapfrog calls continue one trajectory (used
+        by the device-resident system to compute several steps per call)."""
+
     def kinetic(self, p):
         return 0.5 * float(np.vdot(p, p / self.masses))
 
@@ -318,6 +324,21 @@ class _DeviceSystem(_FastSystem):
             be._slot_pool = _SlotPool(self.N_SLOTS)
         self.be = be
         self.pool = be._slot_pool
+        # look-ahead: buildtree grows a subtree of depth j by 2**j leapfrogs in a
+        # row from the tree's edge; `expect(n)` announces them, and `leapfrog`
+        # then computes up to CHAIN of them per native call (one synchronisation
+        # per chain instead of one per step).  States computed ahead but not
+        # asked for (the subtree stopped early) are dropped unseen: results and
+        # the order of the random numbers are those of the step-by-step walk.
+        self._ahead = collections.deque()  # (predecessor state, step, new state)
+        self._expected = 0
+
+    CHAIN = 16
+
+    def expect(self, n):
+        """The next ``n`` leapfrog calls continue one trajectory."""
+        self._expected = int(n)
+        self._ahead.clear()
 
     @staticmethod
     def usable(atoms):
@@ -341,16 +362,32 @@ class _DeviceSystem(_FastSystem):
 
     def leapfrog(self, st, step, center=True):
         calc = self.calc
-        dst = self.pool.take()
+        if self._ahead:
+            prev, stp, new = self._ahead[0]
+            if prev is st and stp == step and center:
+                self._ahead.popleft()
+                self._expected -= 1
+                self.evals += 1
+                return new
+            self._ahead.clear()  # another trajectory: what was computed ahead is void
+        n = max(1, min(self.CHAIN, self._expected)) if center else 1
+        dsts = [self.pool.take() for _ in range(n)]
         try:
-            e, _, e_spring, ke, q, p = self.be.leapfrog(
-                st.slot, dst, step, center, calc.target_data, calc.potential_name,
-                calc.rw_to_eV)
+            res = self.be.leapfrog_chain(st.slot, dsts, step, center, calc.target_data,
+                                         calc.potential_name, calc.rw_to_eV)
         except Exception:
-            self.pool.give(dst)
+            for d in dsts:
+                self.pool.give(d)
             raise
+        states = [_DevState(q, p, float(e) + float(es), None, float(ke), d, self.pool)
+                  for (e, _, es, ke, q, p), d in zip(res, dsts)]
+        prev = states[0]
+        for nxt in states[1:]:
+            self._ahead.append((prev, step, nxt))
+            prev = nxt
+        self._expected -= 1
         self.evals += 1
-        return _DevState(q, p, float(e) + float(e_spring), None, float(ke), dst, self.pool)
+        return states[0]
 
     def to_atoms(self, st):
         if st.f is None:
@@ -485,6 +522,7 @@ class NUTSCanonicalEnsemble(Ensemble):
         acc_sum, leaves = 0., 1
         while keep_going == 1:
             v = self.random_state.choice([-1, 1])
+            system.expect(2 ** depth)  # that many leapfrogs in a row from the tree's edge
             tree = _buildtree_states(system, minus if v == -1 else plus, u, v, depth, e,
                                      e0, self.random_state)
             if v == -1:

@@ -925,6 +925,57 @@ def test_device_resident_leapfrog_equals_array_level_leapfrog(precision):
     assert len(dev.pool.free) == free0
 
 
+def test_chained_leapfrogs_equal_single_steps_bit_for_bit():
+    """iid_leapfrog_chain_host: k steps walked inside ONE cooperative launch
+    (and, with chain_in_kernel off, k launches behind one synchronisation)
+    produce exactly the states of k single-step calls -- positions, momenta,
+    energies and the forces left in the last slot."""
+    atoms, scat = make_hmc_atoms(2, 'fp32')
+    atoms.set_momenta(np.random.RandomState(4).normal(0, 1, (55, 3)))
+    atoms.get_forces()
+    dev = sim._DeviceSystem(atoms)
+    be, calc = dev.be, dev.calc
+    start = dev.state_of(atoms)
+    args = (calc.target_data, calc.potential_name, calc.rw_to_eV)
+    for step in (0.04, -0.02):
+        single, src = [], start.slot
+        for k in range(5):
+            single.append(be.leapfrog(src, 10 + k, step, True, *args))
+            src = 10 + k
+        f_single = be.state_download(14, want=('f',))['f']
+        for in_kernel in (1, 0):
+            be.set_option('chain_in_kernel', in_kernel)
+            n0 = be.launch_count()
+            for rep in range(3):  # eager, capture, replay
+                chain = be.leapfrog_chain(start.slot, [20, 21, 22, 23, 24], step, True, *args)
+            if in_kernel:
+                assert be.launch_count() - n0 == 3  # one launch per chain of five
+            assert len(chain) == 5
+            for a, b in zip(single, chain):
+                for x, y in zip(a, b):
+                    assert np.array_equal(np.asarray(x), np.asarray(y))
+            assert np.array_equal(be.state_download(24, want=('f',))['f'], f_single)
+        be.set_option('chain_in_kernel', 1)
+    # look-ahead in the sampler's system: the same states as the step-by-step walk
+    ref, st = [], start
+    for k in range(6):
+        st = dev.leapfrog(st, 0.03)
+        ref.append(st)
+    dev.expect(6)
+    st = start
+    n0 = be.launch_count()
+    for k in range(6):
+        st = dev.leapfrog(st, 0.03)
+        assert np.array_equal(st.q, ref[k].q) and np.array_equal(st.p, ref[k].p)
+        assert st.pe == ref[k].pe and st.ke == ref[k].ke
+    assert be.launch_count() - n0 == 1
+    # a different trajectory voids what was computed ahead
+    dev.expect(4)
+    a = dev.leapfrog(start, 0.03)
+    b = dev.leapfrog(start, -0.03)
+    assert np.array_equal(a.q, ref[0].q) and not np.array_equal(b.q, ref[0].q)
+
+
 def test_device_state_nuts_equals_array_level_nuts():
     """NUTS with the tree's states resident on the device draws the same random
     numbers and follows the same trajectory as the array-level path."""
