@@ -157,7 +157,7 @@ struct iid_handle {
     bool zero_copy_small = true;
     double *zc_lf_mirror = nullptr;   // leapfrog finished inside the fused launch, mirrored here
     unsigned long long *stamps = nullptr;  // IID_FUSED_STAMPS=1: phase times of the fused kernel
-    double stamp_sum[9] = {0};
+    double stamp_sum[12] = {0};
     int64_t stamp_n = 0;
     // spring restraints fused into iid_energy_forces_host (iid_spring.cuh)
     int n_restraints = 0;
@@ -184,6 +184,7 @@ struct iid_handle {
     GraphSlot lf[IID_LF_CHAIN];  // iid_leapfrog_host / _chain_host: one per ring slot of the pinned staging
     GraphSlot lf_chain[IID_LF_CHAIN];  // [k-1]: a chain of k steps inside one fused launch
     int zc_chain = 1;
+    std::vector<double> lf_mass_h;  // kinetic energy of a step finished inside the fused launch
     bool chain_in_kernel = true;
     bool use_graph = true;
     // device-resident sampler states (iid_leapfrog_host): slot = (q, p, f)
@@ -1851,14 +1852,16 @@ static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(h->stream, &cs);
         if (cs == cudaStreamCaptureStatusNone) {
-            unsigned long long t[9];
+            unsigned long long t[12];
             CU(cudaStreamSynchronize(h->stream));
             CU(cudaMemcpy(t, h->stamps, sizeof(t), cudaMemcpyDeviceToHost));
-            for (int k = 1; k < 9; ++k) h->stamp_sum[k] += (double)(t[k] - t[k - 1]);
+            const int ns = q.lf_mirror ? 12 : 9;
+            for (int k = 1; k < ns; ++k) h->stamp_sum[k] += (double)(t[k] - t[k - 1]);
             if (++h->stamp_n % 200 == 0) {
                 fprintf(stderr, "fused phases (us, mean of %lld):", (long long)h->stamp_n);
-                const char *nm[9] = {"", "stage", "sync", "fq", "sync", "MF", "sync", "pot", "force"};
-                for (int k = 1; k < 9; ++k)
+                const char *nm[12] = {"", "stage", "sync", "fq", "sync", "MF", "sync", "pot", "force",
+                                      "sync", "kick", "sync"};
+                for (int k = 1; k < ns; ++k)
                     fprintf(stderr, " %s %.1f", nm[k], 1e-3 * h->stamp_sum[k] / h->stamp_n);
                 fprintf(stderr, "\n");
             }
@@ -2109,6 +2112,9 @@ extern "C" int iid_sampler_setup(iid_handle *h, int64_t n_slots, const double *m
         if (!(masses_host[i] > 0.0)) return fail(IID_E_BADARG, "masses must be positive");
     CU(cudaStreamSynchronize(h->stream));
     for (GraphSlot &g : h->lf) g.drop();
+    for (GraphSlot &g : h->lf_chain) g.drop();
+    static_assert(LF_CHAIN_MAX == IID_LF_CHAIN, "ring of the pinned staging");
+    h->lf_mass_h.assign(masses_host, masses_host + h->n);
     const size_t n3 = (size_t)3 * h->n;
     int rc;
     if (h->lf_slab) { cudaFree(h->lf_slab); h->lf_slab = nullptr; }
@@ -2246,6 +2252,15 @@ static void leapfrog_collect(iid_handle *h, int ring, double *out_host, double *
     // out: energy, scale, -, -, restraint energy, kinetic energy, shift x y z
     for (int k = 0; k < 9; ++k) out_host[k] = po[k];
     if (!h->n_restraints) out_host[4] = 0.0;
+    if (h->zero_copy_small && !h->n_restraints && fused_applicable(h, true, false)) {
+        // the fused launch finishes the step spread over its grid and leaves the
+        // kinetic energy sum p.p/m / 2 to the host (fixed order: reproducible)
+        const double *p = mir + n3, *m = h->lf_mass_h.data();
+        double ke[3] = {0.0, 0.0, 0.0};
+        for (int64_t a = 0; a < h->n; ++a)
+            for (int w = 0; w < 3; ++w) ke[w] = fma(p[3 * a + w], p[3 * a + w] / m[a], ke[w]);
+        out_host[5] = 0.5 * ((ke[0] + ke[1]) + ke[2]);
+    }
     if (q_host) memcpy(q_host, mir, n3 * sizeof(double));
     if (p_host) memcpy(p_host, mir + n3, n3 * sizeof(double));
 }

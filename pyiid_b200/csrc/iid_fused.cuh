@@ -17,6 +17,9 @@
 //      in Q SPACE -- with gc = T F:  gc.go = F.(T^T go),  gc.gc = F.(M F), so
 //      neither G(r) nor the R x Q matrix is touched -- then the force pass of
 //      its work item (debye2_body<MODE_FORCE>)
+//   4  forces complete (deterministic mode: the items' partial forces added in
+//      item order); leapfrog: second half kick + centring into the destination
+//      state and its host mirror, spread over the grid
 //
 // The Q-space scalars: a = F.vgo, b = F.MF, c = go.go (once per target);
 // scale s = a/b (<= 0: the reference's branches, master_kernel.py:229-230,
@@ -27,6 +30,12 @@
 #include "iid_sampler.cuh"
 
 namespace iid {
+
+#ifdef IID_EXP_NOLDCG  // developer A/B only (wrong for chains)
+constexpr bool FUSED_LDCG = false;
+#else
+constexpr bool FUSED_LDCG = true;
+#endif
 
 struct FusedParams {
     DebyeParams fq;  // F(Q) pass (S = the handle's accumulator)
@@ -59,9 +68,9 @@ struct FusedParams {
     unsigned long long *stamps;  // developer timing: globaltimer at the phase boundaries (or null)
 };
 
-__device__ __forceinline__ void fused_stamp(const FusedParams &q, int k)
+__device__ __forceinline__ void fused_stamp(const FusedParams &q, int k, bool on = true)
 {
-    if (q.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (on && q.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         q.stamps[k] = t;
@@ -88,12 +97,20 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
     cg::grid_group grid = cg::this_grid();
     const int nq = q.fq.nq, qp = q.fq.qp;
 
+  // the step parameters of the whole chain: ONE round trip to the pinned staging
+  // per block and launch
+  __shared__ double ctl_all[LF_CHAIN_MAX * LF_CTL];
+  if (q.lf) {
+      for (int k = threadIdx.x; k < q.n_chain * LF_CTL; k += blockDim.x)
+          ctl_all[k] = q.ctl[(size_t)(k / LF_CTL) * q.chain_stride + k % LF_CTL];
+      __syncthreads();
+  }
   for (int cs = 0; cs < q.n_chain; ++cs) {
-    // a chain of leapfrog steps: step cs reads its parameters from, and mirrors
-    // its state to, ring slot cs of the pinned staging.  Everything another block
-    // wrote in an EARLIER step of this launch is read past L1 (ld.cg).
-    const double *ctl = q.ctl + (size_t)cs * q.chain_stride;
-    fused_stamp(q, 0);
+    // a chain of leapfrog steps: step cs mirrors its state to ring slot cs of the
+    // pinned staging.  Everything another block wrote in an EARLIER step of this
+    // launch is read past L1 (ld.cg).
+    const double *ctl = ctl_all + cs * LF_CTL;
+    fused_stamp(q, 0, cs == 0);
     // ---- phase 0: staging ---------------------------------------------------------
     {
         const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -142,14 +159,14 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
             const_cast<float *>(q.fq.valid)[k] = o >= 0 ? 1.f : 0.f;
         }
     }
-    fused_stamp(q, 1);
+    fused_stamp(q, 1, cs == 0);
     grid.sync();
-    fused_stamp(q, 2);
+    fused_stamp(q, 2, cs == 0);
 
     // ---- phase 1: F(Q) pass -------------------------------------------------------
     if ((int)blockIdx.x < q.n_items)
-        debye2_body<32, MODE_FQ, 8, CHEB, 1, true>(q.fq, smem_raw, (int)blockIdx.x, 0);
-    fused_stamp(q, 3);
+        debye2_body<32, MODE_FQ, 8, CHEB, 1, FUSED_LDCG>(q.fq, smem_raw, (int)blockIdx.x, 0);
+    fused_stamp(q, 3, cs == 0);
     grid.sync();
     if (q.fq.Sitem != nullptr) {
         // deterministic F(Q): the items' partial sums added in item order, one
@@ -163,7 +180,7 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
         }
         grid.sync();
     }
-    fused_stamp(q, 4);
+    fused_stamp(q, 4, cs == 0);
 
     // ---- phase 2: F and this block's rows of M F ------------------------------------
     double *Fs = reinterpret_cast<double *>(smem_raw);  // [qp]
@@ -182,9 +199,9 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
             if (lane == 0) q.MF[row] = acc;
         }
     }
-    fused_stamp(q, 5);
+    fused_stamp(q, 5, cs == 0);
     grid.sync();
-    fused_stamp(q, 6);
+    fused_stamp(q, 6, cs == 0);
 
     // ---- phase 3: potential + weights (every block), then the force pass ------------
     double la = 0.0, lb = 0.0;
@@ -225,17 +242,24 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
         q.out4[4] = 0.0;  // restraint energy, summed by the spring kernels that follow
     }
     __syncthreads();  // wq is complete (block scope) and the scratch is free again
-    fused_stamp(q, 7);
+    fused_stamp(q, 7, cs == 0);
     if ((int)blockIdx.x < q.n_items) {
         DebyeParams fo = q.fo;
         fo.wq = wq;
-        debye2_body<32, MODE_FORCE, 8, CHEB, 1, true>(fo, smem_raw, (int)blockIdx.x, 0);
+        debye2_body<32, MODE_FORCE, 8, CHEB, 1, FUSED_LDCG>(fo, smem_raw, (int)blockIdx.x, 0);
     }
-    fused_stamp(q, 8);
-    // ---- phase 4: (deterministic) the items' partial forces added in item order;
-    // (optional) results straight into the caller's pinned buffer -----------------
+    fused_stamp(q, 8, cs == 0);
+    // ---- phase 4: the forces are complete after one more barrier.  Deterministic
+    // mode adds the items' partial forces in item order; the results go straight
+    // into the caller's pinned buffer (plain evaluation) or through the leapfrog's
+    // second half kick into the destination state and its host mirror ------------
+    const bool finish = q.lf_mirror != nullptr;
+    double *mirror = finish ? q.lf_mirror + (size_t)cs * q.chain_stride : nullptr;
+    __shared__ double lf_shift[3];
+    if (finish) lf_shift_block(ctl, q.pos, q.n, lf_shift);  // while the slowest block finishes
     if (q.fo.Fi != nullptr) {
         grid.sync();
+        fused_stamp(q, 9, cs == 0);
         // one warp per atom, lanes over the items (each lane adds its items in item
         // order, then a butterfly sum: the same order on every run)
         const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,26 +289,36 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
             fz = warp_sum(fz);
             if (lane < 3) {
                 const double f = lane == 0 ? fx : (lane == 1 ? fy : fz);
-                q.fo.force[(size_t)o * 3 + lane] = f;
-                if (q.force_out) q.force_out[(size_t)o * 3 + lane] = f;
+                const size_t e = (size_t)o * 3 + lane;
+                q.fo.force[e] = f;
+                if (q.force_out) q.force_out[e] = f;
+                if (finish) lf_kick(ctl, q.slab, q.n, q.pos, mirror, lf_shift, e, lane, f);
             }
         }
         if (q.force_out && gtid < 5) q.out_host[gtid] = __ldcg(q.out4 + gtid);
-    } else if (q.force_out) {
+    } else if (q.force_out || finish) {
         grid.sync();
         const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-        for (int e = gtid; e < 3 * q.n; e += gsz) q.force_out[e] = __ldcg(q.fo.force + e);
-        if (gtid < 5) q.out_host[gtid] = __ldcg(q.out4 + gtid);
+        for (int e = gtid; e < 3 * q.n; e += gsz) {
+            const double f = __ldcg(q.fo.force + e);
+            if (q.force_out) q.force_out[e] = f;
+            if (finish) lf_kick(ctl, q.slab, q.n, q.pos, mirror, lf_shift, e, e % 3, f);
+        }
+        if (q.force_out && gtid < 5) q.out_host[gtid] = __ldcg(q.out4 + gtid);
     }
-    // ---- phase 5 (optional): the leapfrog's second half kick, one block ----------------
-    if (q.lf_mirror) {
-        grid.sync();
-        if (blockIdx.x == 0)
-            lf_finish_body(ctl, q.slab, q.mass, q.n, q.pos, q.fo.force,
-                           q.lf_mirror + (size_t)cs * q.chain_stride, q.out4);
-        // the next step's staging reads the state this block is writing and
-        // clears the accumulators it is reading
+    if (finish) {
+        // scalars of the step: energy, scale, value, scale_true, restraint energy,
+        // (kinetic energy: summed by the host from the mirrored momenta), shift
+        double *out = mirror + 6 * (size_t)q.n;
+        if (blockIdx.x == 0 && threadIdx.x < 9) {
+            const int k = threadIdx.x;
+            out[k] = k < 5 ? __ldcg(q.out4 + k) : (k == 5 ? 0.0 : lf_shift[k - 6]);
+        }
+        // the next step's staging reads the state written here and clears the
+        // accumulators read here
+        fused_stamp(q, 10, cs == 0);
         if (cs + 1 < q.n_chain) grid.sync();
+        fused_stamp(q, 11, cs == 0);
     }
   }
 }

@@ -21,6 +21,7 @@
 namespace iid {
 
 constexpr int LF_CTL = 8;  // step, src, dst, centre flag, cell centre x y z, -
+constexpr int LF_CHAIN_MAX = 16;  // steps one fused launch can walk (= IID_LF_CHAIN)
 
 __device__ __forceinline__ double *lf_slot(double *slab, int n, int slot, int which)
 {
@@ -170,6 +171,73 @@ __device__ __forceinline__ void lf_finish_body(const double *ctl, double *slab,
         q[k] = x;
         mirror[k] = x;
     }
+}
+
+// The same second half of the step spread over a whole grid (the fused
+// evaluation kernel): every block computes the centring shift of the drifted
+// positions for itself (min / max are exact in any order), then element e of
+// the state is finished by whichever thread holds its force.  The kinetic
+// energy is summed by the host from the mirrored momenta.
+__device__ __forceinline__ void lf_shift_block(const double *ctl, const double *pos, int n,
+                                               double *shift /* shared [3] */)
+{
+    __shared__ double red[6][32];
+    const bool centre = ctl[3] != 0.0;
+    if (!centre) {
+        if (threadIdx.x < 3) shift[threadIdx.x] = 0.0;
+        __syncthreads();
+        return;
+    }
+    double v[6] = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300};
+    for (int a = threadIdx.x; a < n; a += blockDim.x)
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const double x = __ldcg(pos + 3 * a + w);
+            v[w] = fmin(v[w], x);
+            v[3 + w] = fmax(v[3 + w], x);
+        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            v[w] = fmin(v[w], __shfl_xor_sync(0xffffffffu, v[w], o));
+            v[3 + w] = fmax(v[3 + w], __shfl_xor_sync(0xffffffffu, v[3 + w], o));
+        }
+    if (lane == 0)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) red[c][warp] = v[c];
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int w = threadIdx.x;
+        double lo = 1e300, hi = -1e300;
+        for (int k = 0; k < nw; ++k) {
+            lo = fmin(lo, red[w][k]);
+            hi = fmax(hi, red[3 + w][k]);
+        }
+        // numpy: q + (centre - 0.5 * (min + max))
+        shift[w] = __dsub_rn(ctl[4 + w], __dmul_rn(0.5, __dadd_rn(lo, hi)));
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void lf_kick(const double *ctl, double *slab, int n, const double *pos,
+                                        double *mirror, const double *shift, size_t e, int w,
+                                        double f)
+{
+    const double step = ctl[0];
+    const int dst = (int)ctl[2];
+    const bool centre = ctl[3] != 0.0;
+    double *qd = lf_slot(slab, n, dst, 0), *pd = lf_slot(slab, n, dst, 1),
+           *fd = lf_slot(slab, n, dst, 2);
+    const double ph = __ldcg(pd + e), x0 = __ldcg(pos + e);
+    const double pn = __dadd_rn(ph, __dmul_rn(__dmul_rn(0.5, step), f));
+    const double x = centre ? __dadd_rn(x0, shift[w]) : x0;
+    pd[e] = pn;
+    fd[e] = f;
+    qd[e] = x;
+    mirror[e] = x;
+    mirror[3 * (size_t)n + e] = pn;
 }
 
 __global__ void __launch_bounds__(1024) lf_finish_kernel(const double *__restrict__ ctl,
