@@ -42,6 +42,7 @@ extern "C" {
 #define IID_E_NOTRANSFORM (-3)/* iid_set_transform not called yet      */
 #define IID_E_NOMEM (-4)
 #define IID_E_NODEVICE (-5)   /* no CUDA device / wrong architecture   */
+#define IID_E_NOCHAIN (-6)    /* iid_leapfrog_chain_next: that chain was dropped */
 
 typedef struct iid_handle iid_handle;
 
@@ -294,14 +295,27 @@ int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, int centre,
                       const double *target_host, int potential, double conv,
                       double *out_host, double *q_host, double *p_host);
 /* n_steps (<= IID_LF_CHAIN) consecutive steps src -> dst[0] -> dst[1] -> ...
- * of the same size, queued behind each other with ONE synchronisation: what
- * buildtree (nuts_hmc.py:15-88) asks for when it grows a subtree of depth j
- * (2^j leapfrogs in a row).  out_host[n_steps][9], q_host / p_host
- * [n_steps][n*3] (may be NULL) as iid_leapfrog_host, one row per step. */
+ * of the same size: what buildtree (nuts_hmc.py:15-88) asks for when it grows
+ * a subtree of depth j (2^j leapfrogs in a row).  Structures small enough for
+ * the fused evaluation walk the whole chain inside ONE cooperative launch.
+ * out_host[n_steps][9], q_host / p_host [n_steps][n*3] (may be NULL) as
+ * iid_leapfrog_host, one row per step. */
 #define IID_LF_CHAIN 16
 int iid_leapfrog_chain_host(iid_handle *h, int src, const int *dst, int n_steps,
                             double step, int centre, const double *target_host,
                             int potential, double conv, double *out_host,
+                            double *q_host, double *p_host);
+/* The same chain in two halves: _begin enqueues it and returns at once, _next
+ * hands out the steps in order as the device completes them (out_host[9],
+ * q_host / p_host [n*3] or NULL), so the caller's work on step i -- the U-turn
+ * test, the tree bookkeeping -- overlaps the computation of step i + 1.
+ * Steps not collected are dropped by the next call on the handle (which first
+ * waits for the chain); _next for a chain that is not in flight any more
+ * returns IID_E_NOCHAIN. */
+int iid_leapfrog_chain_begin(iid_handle *h, int src, const int *dst, int n_steps,
+                             double step, int centre, const double *target_host,
+                             int potential, double conv, int64_t *chain_id);
+int iid_leapfrog_chain_next(iid_handle *h, int64_t chain_id, double *out_host,
                             double *q_host, double *p_host);
 
 /* Device array -> pageable host memory through pipelined pinned staging,

@@ -74,6 +74,8 @@ SIGNATURES = {
     'iid_state_download': [_vp, _int, _vp, _vp, _vp],
     'iid_leapfrog_host': [_vp, _int, _int, _dbl, _int, _vp, _int, _dbl, _vp, _vp, _vp],
     'iid_leapfrog_chain_host': [_vp, _int, _vp, _int, _dbl, _int, _vp, _int, _dbl, _vp, _vp, _vp],
+    'iid_leapfrog_chain_begin': [_vp, _int, _vp, _int, _dbl, _int, _vp, _int, _dbl, _pi64],
+    'iid_leapfrog_chain_next': [_vp, _i64, _vp, _vp, _vp],
     'iid_set_option': [_vp, ctypes.c_char_p, _i64],
     'iid_launch_count': [_vp, _pi64],
     'iid_last_kernel_ms': [_vp, ctypes.POINTER(ctypes.c_float),
@@ -87,6 +89,11 @@ _lib = None
 
 class IIDError(RuntimeError):
     pass
+
+
+class ChainDropped(IIDError):
+    """iid_leapfrog_chain_next (IID_E_NOCHAIN): the chain was dropped by another
+    call on the handle; its steps have to be asked for again."""
 
 
 def load():
@@ -113,5 +120,7 @@ def load():
 def check(rc):
     if rc != 0:
         msg = load().iid_last_error()
+        if rc == -6:
+            raise ChainDropped(msg.decode() if msg else '?')
         raise IIDError('iid_b200 error %d: %s' % (
             rc, msg.decode() if msg else '?'))

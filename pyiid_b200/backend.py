@@ -562,6 +562,41 @@ class Backend(object):
         self._target_done(target, tkey)
         return [(out[i, 0], out[i, 1], out[i, 4], out[i, 5], q[i], p[i]) for i in range(m)]
 
+    def leapfrog_chain_begin(self, src, dsts, step, center, target, potential='rw', conv=1.):
+        """Enqueue ``len(dsts)`` consecutive leapfrog steps and return at once
+        (``iid_leapfrog_chain_begin``); :meth:`leapfrog_chain_next` hands out
+        the steps in order as the device completes them.  Any other call on
+        this backend first waits for the chain and drops what was not
+        collected.  Returns the chain's id."""
+        if potential not in POTENTIALS:
+            raise NotImplementedError('Potential not implemented')
+        if target is not self._last_target:
+            target = np.ascontiguousarray(target, dtype=np.float64)
+            if target.shape != (self.nr,):
+                raise ValueError('target must have the r-grid length %d' % self.nr)
+            self.sync_shard()
+        if self.world != 1:
+            raise _lib.IIDError('the device-resident leapfrog needs world == 1')
+        tptr, tkey = self._target_ptr(target)
+        d = np.asarray(dsts, dtype=np.int32)
+        cid = ctypes.c_int64(0)
+        check(self.lib.iid_leapfrog_chain_begin(
+            self.h, int(src), d.ctypes.data, len(d), float(step), int(bool(center)), tptr,
+            POTENTIALS[potential], float(conv), ctypes.byref(cid)))
+        self._target_done(target, tkey)
+        return cid.value
+
+    def leapfrog_chain_next(self, chain_id):
+        """The next completed step of chain ``chain_id``: (energy, scale,
+        restraint energy, kinetic energy, q, p); raises
+        :class:`_lib.ChainDropped` when another call dropped the chain."""
+        out = np.empty(9, np.float64)
+        q = np.empty((self.n, 3), np.float64)
+        p = np.empty((self.n, 3), np.float64)
+        check(self.lib.iid_leapfrog_chain_next(self.h, int(chain_id), out.ctypes.data,
+                                               q.ctypes.data, p.ctypes.data))
+        return out[0], out[1], out[4], out[5], q, p
+
     # -- spring restraints (calc/spring_calc.py) -------------------------------
     def set_restraints(self, springs):
         """rep / att springs [(sp_type, k, rt), ...] evaluated inside

@@ -5,6 +5,8 @@
 #include "../../include/iid_b200.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -50,6 +52,7 @@ static int fail(int code, const std::string &msg)
             return fail(IID_E_BADARG, std::string(__func__) +                 \
                         ": not available on a multi-device handle");          \
         CU(cudaSetDevice((h)->device));                                       \
+        if ((h)->chain_left > 0) chain_drain(h); /* a leapfrog chain in flight */ \
     } while (0)
 
 template <typename X>
@@ -146,7 +149,14 @@ struct iid_handle {
     size_t Sitem_fq_count = 0;
     double *ft_part = nullptr;    // tabulated force pass: [jsplit][np][3] partial sums
     size_t ft_part_count = 0;
-    double *Sitem = nullptr, *Fi = nullptr, *Fj = nullptr;
+    // the fused evaluation kernel's fixed-point accumulators (zero between launches)
+    unsigned long long *Sfix = nullptr, *Ffix = nullptr;
+    double *gforce = nullptr;  // [qp] per-bin bound of a pair's force per unit weight
+    double *phi_tab_d = nullptr;  // its float64 radial force table
+    double *ext_ref = nullptr;    // [4] box centre of its previous evaluation + valid flag
+    bool fused_table = true;
+    std::vector<double> gforce_host;
+    double s_fix_scale = 1.0;
     int64_t tri_maxlen = 0;       // longest j range of a triangle item
     // zero-copy I/O of the fused kernel, set by the host entry points around
     // enqueue_eval_device (pinned staging of the handle; null = copy nodes)
@@ -184,6 +194,12 @@ struct iid_handle {
     GraphSlot lf[IID_LF_CHAIN];  // iid_leapfrog_host / _chain_host: one per ring slot of the pinned staging
     GraphSlot lf_chain[IID_LF_CHAIN];  // [k-1]: a chain of k steps inside one fused launch
     int zc_chain = 1;
+    // iid_leapfrog_chain_begin / _next: steps enqueued, steps not yet handed out
+    int chain_n = 0, chain_left = 0;
+    bool chain_flags = false;   // the launch raises a flag per step (in-kernel chain)
+    bool chain_synced = false;  // (otherwise) the stream was synchronised for this chain
+    double lf_seq = 0.0;        // flag value of the last step handed out
+    int64_t chain_id = 0;       // the chain begun last
     std::vector<double> lf_mass_h;  // kinetic energy of a step finished inside the fused launch
     bool chain_in_kernel = true;
     bool use_graph = true;
@@ -210,6 +226,7 @@ struct iid_handle {
 
 static int upload_row_jobs(iid_handle *h);
 static void drop_graph(iid_handle *h);
+static void chain_drain(iid_handle *h);
 static int multi_destroy(iid_handle *h);
 static int multi_need_subs(iid_handle *h, int count);
 static int multi_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
@@ -290,6 +307,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_FUSED")) h->use_fused = atoi(s) != 0;
     if (const char *s = getenv("IID_FUSED_DET")) h->fused_det = atoi(s) != 0;
     if (const char *s = getenv("IID_CHAIN_IN_KERNEL")) h->chain_in_kernel = atoi(s) != 0;
+    if (const char *s = getenv("IID_FUSED_TABLE")) h->fused_table = atoi(s) != 0;
     if (const char *s = getenv("IID_DET_FQ")) h->det_fq = atoi(s) != 0;
     if (const char *s = getenv("IID_ZERO_COPY_SMALL")) h->zero_copy_small = atoi(s) != 0;
     *out = h;
@@ -304,7 +322,7 @@ extern "C" int iid_destroy(iid_handle *h)
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
                     h->inv_na, h->inv_na_d, h->items_tri, h->jobs, h->segs, h->fixes, h->Spart,
-                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->Sitem, h->Fi, h->Fj, h->Sitem_fq, h->ft_part, h->T,
+                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->Sfix, h->Ffix, h->gforce, h->phi_tab_d, h->ext_ref, h->Sitem_fq, h->ft_part, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
                     h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf,
                     h->lf_slab, h->lf_mass, h->lf_ctl, h->lf_mirror};
@@ -827,10 +845,30 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
     h->n_items_tri = (int64_t)tri.size();
     h->tri_maxlen = 0;
     for (const WorkItem &w : tri) h->tri_maxlen = std::max<int64_t>(h->tri_maxlen, w.jend - w.jbegin);
-    // per-item partial sums of the deterministic fused path are sized per structure
-    if (h->Sitem) { cudaFree(h->Sitem); h->Sitem = nullptr; }
-    if (h->Fi) { cudaFree(h->Fi); h->Fi = nullptr; }
-    if (h->Fj) { cudaFree(h->Fj); h->Fj = nullptr; }
+    // the fused evaluation kernel's buffers are sized per structure
+    for (double **b : {&h->MF, &h->wq_blk, &h->gforce, &h->phi_tab_d, &h->ext_ref})
+        if (*b) { cudaFree(*b); *b = nullptr; }
+    for (unsigned long long **b : {&h->Sfix, &h->Ffix})
+        if (*b) { cudaFree(*b); *b = nullptr; }
+    {
+        // fixed-point scale of its F(Q) accumulators: |S[m]| <= pairs * f^2 * Q
+        // (|sin(Qr)/r| <= Q), with room for float32 rounding; and the per-bin
+        // bound of a pair's force per unit weight (force_fix_scale, iid_fused.cuh)
+        h->gforce_host.assign(qp, 0.0);
+        double bound = 0.0;
+        for (int64_t m = 0; m < nq; ++m) {
+            double f2 = 0.0;
+            for (int64_t e = 0; e < n_types; ++e)
+                f2 = std::max(f2, ftable[e * nq + m] * ftable[e * nq + m]);
+            const double Q = (double)m * qbin;
+            bound = std::max(bound, f2 * std::max(Q, 1e-3));
+            h->gforce_host[m] = 0.6 * Q * Q * f2 * std::fabs(inv_na[m]);
+        }
+        bound *= 4.0 * (double)np * (double)np;
+        int e2 = 0;
+        if (bound > 0.0 && std::isfinite(bound)) std::frexp(bound, &e2);
+        h->s_fix_scale = std::ldexp(1.0, 60 - e2);
+    }
     h->run_begin = L.run_begin;
     h->run_end = L.run_end;
     h->run_type_v = L.run_type;
@@ -1773,13 +1811,30 @@ enum { EVAL_ALL = 0, EVAL_FQ = 1, EVAL_REST = 2 };
 // The whole evaluation as ONE cooperative launch (iid_fused.cuh) when the
 // structure is small enough for one work item per SM: FP32 mode, one shard,
 // direct force pass, Q-space weights, the caller wants forces and no G(r).
+// Dynamic shared memory of the fused launch: pair records (two buffers), the
+// force pass's per-pair scalars, and the positions of the item's atoms.
+static size_t fused_smem_bytes(const iid_handle *h, int *ps_off, int *pl)
+{
+    const int nchunk = (int)((h->nq + C32 - 1) / C32);
+    int off = (int)(2 * debye2_buf_bytes(nchunk, 8) + debye2_phi_bytes(nchunk, 8));
+    // the Q-space stages and the table force pass reuse the front of it: F, M F,
+    // a reduction row, the weights of each element pair, the warps' i-side forces
+    const int64_t front = ((2 + h->ntypes * h->ntypes) * h->qp + 32 + (int64_t)nchunk * 96) * 8;
+    off = (int)std::max<int64_t>(off, (front + 15) / 16 * 16);
+    const int len = (int)((TILE_I + h->tri_maxlen + 1) / 2 * 2);
+    if (ps_off) *ps_off = off;
+    if (pl) *pl = len;
+    return (size_t)off + (4 * (size_t)len + 3 * (size_t)h->n) * sizeof(double);
+}
+
 static bool fused_applicable(const iid_handle *h, bool want_forces, bool want_pdf)
 {
     const bool table = h->use_force_table && h->ntypes <= 4 && h->n >= h->force_table_min_n;
     return h->use_fused && h->precision == IID_FP32 && h->cheb && h->world == 1 &&
            want_forces && !want_pdf && h->qspace_wq && !table && !h->timing &&
            h->n_items_tri <= h->sm_count && (h->nq + C32 - 1) / C32 <= 12 &&
-           h->np <= (int64_t)h->sm_count * 384;
+           h->np <= (int64_t)h->sm_count * 384 &&
+           fused_smem_bytes(h, nullptr, nullptr) <= 220 * 1024;
 }
 
 static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
@@ -1805,20 +1860,43 @@ static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
     p.grad_split = 1;
     p.jobs = nullptr; p.segs = nullptr; p.Gside = nullptr;
     p.Gscr = nullptr; p.slot_busy = nullptr; p.n_slots = 0; p.acc_j = 0;
-    if (h->fused_det && !h->Sitem) {
-        const size_t ni = (size_t)std::max<int64_t>(1, h->n_items_tri);
-        if ((rc = dev_alloc(&h->Sitem, ni * h->qp)) || (rc = dev_alloc(&h->Fi, ni * 32 * 3)) ||
-            (rc = dev_alloc(&h->Fj, ni * (size_t)std::max<int64_t>(1, h->tri_maxlen) * 3)))
+    if (!h->Sfix) {
+        if ((rc = dev_alloc(&h->Sfix, 2 * h->qp)) || (rc = dev_alloc(&h->Ffix, 3 * h->n)) ||
+            (rc = dev_alloc(&h->gforce, h->qp)))
             return rc;
+        CU(cudaMemset(h->Sfix, 0, 2 * h->qp * sizeof(unsigned long long)));
+        CU(cudaMemset(h->Ffix, 0, 3 * h->n * sizeof(unsigned long long)));
+        CU(cudaMemcpy(h->gforce, h->gforce_host.data(), h->qp * sizeof(double),
+                      cudaMemcpyHostToDevice));
+        if ((rc = dev_alloc(&h->ext_ref, 8))) return rc;
+        CU(cudaMemset(h->ext_ref, 0, 8 * sizeof(double)));
+        CU(cudaStreamSynchronize(0));
     }
-    p.Sitem = h->fused_det ? h->Sitem : nullptr;
+    p.Sitem = nullptr;
+    p.Sfix = h->Sfix;
+    p.Ffix = nullptr;
+    p.fix_scale = h->s_fix_scale;
     q.fo = p;
     q.fo.S = nullptr;
-    q.fo.Sitem = nullptr;
+    q.fo.Sfix = nullptr;
     q.fo.force = h->force;
-    q.fo.Fi = h->fused_det ? h->Fi : nullptr;
-    q.fo.Fj = h->fused_det ? h->Fj : nullptr;
-    q.fo.fj_len = (int)h->tri_maxlen;
+    q.fo.Ffix = h->Ffix;
+    q.s_scale_inv = 1.0 / h->s_fix_scale;
+    q.gforce = h->gforce;
+    // the force pass as a float64 radial table built inside the launch
+    constexpr int PHI_CAP_FUSED = 16384;
+    const bool tab = h->fused_table && h->ntypes <= 2;
+    if (tab && !h->phi_tab_d) {
+        if ((rc = dev_alloc(&h->phi_tab_d, (size_t)IID_LF_CHAIN * h->ntypes * h->ntypes *
+                                               (PHI_CAP_FUSED + 2 * FT_PAD))))
+            return rc;
+    }
+    q.phi_tab = tab ? h->phi_tab_d : nullptr;
+    q.phi_cap = PHI_CAP_FUSED;
+    q.phi_stride = PHI_CAP_FUSED + 2 * FT_PAD;
+    q.ntypes = (int)h->ntypes;
+    q.tab_h = 0.125 / (h->qbin * (double)h->nq);
+    q.ext_ref = h->ext_ref;
     q.n_items = (int)h->n_items_tri;
     q.lf = lf ? 1 : 0;
     q.ctl = h->zc_ctl ? h->zc_ctl : h->lf_ctl; q.slab = h->lf_slab; q.mass = h->lf_mass;
@@ -1834,10 +1912,13 @@ static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
     q.MF = h->MF; q.wq_blk = h->wq_blk;
     q.potential = potential; q.conv = conv; q.out4 = h->out4;
     static const bool want_stamps = getenv("IID_FUSED_STAMPS") != nullptr;
-    if (want_stamps && !h->stamps) CU(cudaMalloc((void **)&h->stamps, 16 * sizeof(unsigned long long)));
+    if (want_stamps && !h->stamps) {
+        CU(cudaMalloc((void **)&h->stamps, 24 * sizeof(unsigned long long)));
+        CU(cudaMemset(h->stamps, 0, 24 * sizeof(unsigned long long)));
+    }
     q.stamps = h->stamps;
     const int nchunk = (int)((h->nq + C32 - 1) / C32);
-    const size_t smem = 2 * debye2_buf_bytes(nchunk, 8) + debye2_phi_bytes(nchunk, 8);
+    const size_t smem = fused_smem_bytes(h, &q.ps_off, &q.pl);
     static bool attr_done[64] = {false};
     if (!attr_done[h->device & 63]) {
         CU(cudaFuncSetAttribute(fused_eval_kernel<true>,
@@ -1852,7 +1933,7 @@ static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(h->stream, &cs);
         if (cs == cudaStreamCaptureStatusNone) {
-            unsigned long long t[12];
+            unsigned long long t[24];
             CU(cudaStreamSynchronize(h->stream));
             CU(cudaMemcpy(t, h->stamps, sizeof(t), cudaMemcpyDeviceToHost));
             const int ns = q.lf_mirror ? 12 : 9;
@@ -1863,6 +1944,19 @@ static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
                                       "sync", "kick", "sync"};
                 for (int k = 1; k < ns; ++k)
                     fprintf(stderr, " %s %.1f", nm[k], 1e-3 * h->stamp_sum[k] / h->stamp_n);
+                if (q.phi_tab) {
+                    double er[8];
+                    cudaMemcpy(er, h->ext_ref, sizeof(er), cudaMemcpyDeviceToHost);
+                    fprintf(stderr, " | table: radius %.2f A, %d entries; from pot: build %.1f (last "
+                            "block %.1f), sync -> %.1f, forces %.1f (last block %.1f)", er[4],
+                            (int)er[5], 1e-3 * (double)(t[16] - t[7]), 1e-3 * (double)(t[18] - t[7]),
+                            1e-3 * (double)(t[17] - t[7]), 1e-3 * (double)(t[8] - t[7]),
+                            1e-3 * (double)(t[19] - t[7]));
+                }
+                if (q.n_chain >= 4)
+                    fprintf(stderr, " | steps 0-2 of this chain: %.1f %.1f %.1f",
+                            1e-3 * (double)(t[13] - t[12]), 1e-3 * (double)(t[14] - t[13]),
+                            1e-3 * (double)(t[15] - t[14]));
                 fprintf(stderr, "\n");
             }
         }
@@ -2273,28 +2367,33 @@ extern "C" int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, i
                                    out_host, q_host, p_host);
 }
 
-// n_steps consecutive leapfrog steps src -> dst[0] -> dst[1] -> ... with ONE
-// synchronisation at the end: the launches queue up behind each other, so the
+// n_steps consecutive leapfrog steps src -> dst[0] -> dst[1] -> ... (a NUTS
+// subtree of depth j is 2^j such steps in a row, pyiid/sim/nuts_hmc.py:15-88).
+// Small structures walk the whole chain inside ONE cooperative launch; the
 // launch latency, the wake-up of the host and its per-call work are paid once
-// per chain instead of once per step (a NUTS subtree of depth j is 2^j such
-// steps in a row, pyiid/sim/nuts_hmc.py:15-88).
-extern "C" int iid_leapfrog_chain_host(iid_handle *h, int src, const int *dst, int n_steps,
-                                       double step, int centre, const double *target_host,
-                                       int potential, double conv, double *out_host,
-                                       double *q_host, double *p_host)
+// per chain instead of once per step.
+//
+// _begin enqueues the chain and returns; _next hands out the steps in order as
+// they complete: the fused launch raises a flag in the pinned staging after
+// each step, so the host works on step i (kinetic energy, the caller's tree
+// logic) while the device computes step i + 1.  Any other call on the handle
+// first waits for the chain (NEED -> chain_drain).
+extern "C" int iid_leapfrog_chain_begin(iid_handle *h, int src, const int *dst, int n_steps,
+                                        double step, int centre, const double *target_host,
+                                        int potential, double conv, int64_t *chain_id)
 {
     if (MULTI(h)) {
         if (h->active != 1)
             return fail(IID_E_BADARG, "device-resident sampler states need a one-device structure");
-        return iid_leapfrog_chain_host(h->subs[0], src, dst, n_steps, step, centre, target_host,
-                                       potential, conv, out_host, q_host, p_host);
+        return iid_leapfrog_chain_begin(h->subs[0], src, dst, n_steps, step, centre, target_host,
+                                        potential, conv, chain_id);
     }
     NEED(h);
     if (h->nr == 0) return fail(IID_E_NOTRANSFORM, "call iid_set_transform first");
     if (h->world != 1)
         return fail(IID_E_BADARG, "iid_leapfrog_host needs the whole pair list (world == 1)");
-    if (!dst || !out_host || n_steps < 1 || n_steps > IID_LF_CHAIN)
-        return fail(IID_E_BADARG, "need 1 <= n_steps <= IID_LF_CHAIN, dst and out");
+    if (!dst || n_steps < 1 || n_steps > IID_LF_CHAIN)
+        return fail(IID_E_BADARG, "need 1 <= n_steps <= IID_LF_CHAIN and dst");
     int rc;
     if ((rc = check_slot(h, src))) return rc;
     for (int i = 0; i < n_steps; ++i) {
@@ -2302,21 +2401,121 @@ extern "C" int iid_leapfrog_chain_host(iid_handle *h, int src, const int *dst, i
         if (dst[i] == (i ? dst[i - 1] : src))
             return fail(IID_E_BADARG, "source and destination slot must differ");
     }
-    const size_t n3 = (size_t)3 * h->n;
     double *pt = h->pin + 6 * h->n + h->qp + 8 + h->nr;  // target staging of the handle
     if ((rc = refresh_target(h, target_host, pt))) return rc;
-    for (int i = 0; i < n_steps; ++i) leapfrog_fill(h, i, i ? dst[i - 1] : src, dst[i], step, centre);
-    if (n_steps > 1 && leapfrog_in_kernel(h)) {
+    for (int i = 0; i < n_steps; ++i) {
+        leapfrog_fill(h, i, i ? dst[i - 1] : src, dst[i], step, centre);
+        h->lf_pin[(size_t)i * lf_ring_stride(h) + 7] = h->lf_seq + (double)(i + 1);
+    }
+    h->chain_flags = n_steps > 1 && leapfrog_in_kernel(h);
+    if (h->chain_flags) {
         // the whole chain in one cooperative launch
         if ((rc = leapfrog_enqueue(h, 0, n_steps, potential, conv))) return rc;
     } else {
         for (int i = 0; i < n_steps; ++i)
             if ((rc = leapfrog_enqueue(h, i, 1, potential, conv))) return rc;
     }
-    CU(cudaStreamSynchronize(h->stream));
+    h->chain_n = h->chain_left = n_steps;
+    h->chain_synced = false;
+    ++h->chain_id;
+    if (chain_id) *chain_id = h->chain_id;
+    return 0;
+}
+
+static void chain_drain(iid_handle *h)
+{
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->lf_seq += (double)h->chain_n;
+    h->chain_left = h->chain_n = 0;
+}
+
+extern "C" int iid_leapfrog_chain_next(iid_handle *h, int64_t chain_id, double *out_host,
+                                       double *q_host, double *p_host)
+{
+    if (MULTI(h)) return iid_leapfrog_chain_next(h->subs[0], chain_id, out_host, q_host, p_host);
+    if (!h || !out_host) return fail(IID_E_BADARG, "null pointer");
+    if (h->chain_left <= 0 || chain_id != h->chain_id)
+        return fail(IID_E_NOCHAIN, "this leapfrog chain is not in flight (any more)");
+    CU(cudaSetDevice(h->device));
+    static const bool stats = getenv("IID_CHAIN_STATS") != nullptr;  // developer timing
+    const auto t_in = std::chrono::steady_clock::now();
+    const int i = h->chain_n - h->chain_left;
+    if (h->chain_flags && i + 1 < h->chain_n) {
+        // step i of a chain inside one launch: its flag follows its mirror
+        const volatile double *flag =
+            h->lf_pin + (size_t)i * lf_ring_stride(h) + LF_CTL + 6 * (size_t)h->n + 15;
+        const double want = h->lf_seq + (double)(i + 1);
+        for (unsigned spin = 0; *flag != want; ++spin) {
+            if ((spin & 0xfff) == 0xfff) {
+                // the launch ended without raising the flag: an error, or nothing to wait for
+                const cudaError_t e = cudaStreamQuery(h->stream);
+                if (e == cudaSuccess) {
+                    if (*flag == want) break;
+                    chain_drain(h);
+                    g_err = "leapfrog chain ended without completing its steps";
+                    return (int)cudaErrorUnknown;
+                }
+                if (e != cudaErrorNotReady) {
+                    chain_drain(h);
+                    g_err = std::string("leapfrog chain: ") + cudaGetErrorString(e);
+                    return (int)e;
+                }
+            }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    } else if (!h->chain_synced) {
+        const cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) {
+            chain_drain(h);
+            g_err = std::string("leapfrog chain: ") + cudaGetErrorString(e);
+            return (int)e;
+        }
+        h->chain_synced = true;
+    }
+    const auto t_mid = std::chrono::steady_clock::now();
+    leapfrog_collect(h, i, out_host, q_host, p_host);
+    if (stats) {
+        static double wait_us = 0.0, collect_us = 0.0, last_wait = 0.0;
+        static long calls = 0, lasts = 0;
+        const auto t_out = std::chrono::steady_clock::now();
+        const double w = std::chrono::duration<double, std::micro>(t_mid - t_in).count();
+        if (i + 1 < h->chain_n) wait_us += w;
+        else { last_wait += w; ++lasts; }
+        collect_us += std::chrono::duration<double, std::micro>(t_out - t_mid).count();
+        if (++calls % 1000 == 0)
+            fprintf(stderr, "chain_next x%ld: wait %.1f us (inner steps), %.1f us (last step of a "
+                    "chain, %ld of them), collect %.1f us\n", calls,
+                    wait_us / std::max(1L, calls - lasts), last_wait / std::max(1L, lasts), lasts,
+                    collect_us / calls);
+    }
+    if (--h->chain_left == 0) {
+        h->lf_seq += (double)h->chain_n;
+        h->chain_n = 0;
+    }
+    return 0;
+}
+
+extern "C" int iid_leapfrog_chain_host(iid_handle *h, int src, const int *dst, int n_steps,
+                                       double step, int centre, const double *target_host,
+                                       int potential, double conv, double *out_host,
+                                       double *q_host, double *p_host)
+{
+    if (!out_host) return fail(IID_E_BADARG, "null pointer");
+    int64_t id = 0;
+    int rc = iid_leapfrog_chain_begin(h, src, dst, n_steps, step, centre, target_host, potential,
+                                      conv, &id);
+    if (rc) return rc;
+    iid_handle *hh = MULTI(h) ? h->subs[0] : h;
+    const size_t n3 = (size_t)3 * hh->n;
     for (int i = 0; i < n_steps; ++i)
-        leapfrog_collect(h, i, out_host + 9 * (size_t)i, q_host ? q_host + n3 * i : nullptr,
-                         p_host ? p_host + n3 * i : nullptr);
+        if ((rc = iid_leapfrog_chain_next(h, id, out_host + 9 * (size_t)i,
+                                          q_host ? q_host + n3 * i : nullptr,
+                                          p_host ? p_host + n3 * i : nullptr)))
+            return rc;
     return 0;
 }
 
@@ -2455,6 +2654,7 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "fused") h->use_fused = value != 0;
     else if (k == "fused_det") h->fused_det = value != 0;
     else if (k == "chain_in_kernel") h->chain_in_kernel = value != 0;
+    else if (k == "fused_table") h->fused_table = value != 0;
     else if (k == "det_fq") h->det_fq = value != 0;
     else if (k == "acc_j") h->acc_j = (int)std::max<int64_t>(0, value);
     else if (k == "piece_div") {

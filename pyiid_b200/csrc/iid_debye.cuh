@@ -95,14 +95,36 @@ struct DebyeParams {
     float *Gscr;    // [n_slots][3 C][block threads]
     int *slot_busy; // [n_slots] 0 = free
     int n_slots, acc_j;
-    // Deterministic small-structure path (the fused evaluation kernel): instead
-    // of atomics every work item stores its partial sums, added later in item
-    // order.  Null = atomics.
+    // Deterministic F(Q) of the standalone pass: every work item stores its
+    // partial sums, added later in item order.  Null = atomics.
     double *Sitem = nullptr;  // MODE_FQ: [n_items][qp]
-    double *Fi = nullptr;     // MODE_FORCE: [n_items][32][3] forces on the item's i atoms
-    double *Fj = nullptr;     // MODE_FORCE: [n_items][fj_len][3] forces on its j atoms
-    int fj_len = 0;
+    // The fused evaluation kernel: FIXED-POINT accumulators.  Integer addition
+    // is associative, so plain atomics give bit-reproducible sums in ONE phase
+    // (no per-item partials, no ordered second pass).  value = count / fix_scale
+    // with fix_scale a power of two chosen from a rigorous bound of the sum.
+    unsigned long long *Sfix = nullptr;  // MODE_FQ: [2][qp] high word, low word (fix_add2)
+    unsigned long long *Ffix = nullptr;  // MODE_FORCE: [n][3]
+    double fix_scale = 0.0;
 };
+
+__device__ __forceinline__ void fix_add(unsigned long long *a, double v, double scale)
+{
+    atomicAdd(a, (unsigned long long)__double2ll_rn(v * scale));
+}
+
+// Two words: the high word counts units of 1/scale, the low word what the
+// rounding of the high word left, in units of 2^-40 / scale -- the sum keeps
+// every bit a float64 sum could (the pair sums S feed a difference of nearly
+// equal numbers in Rw).  v * scale is exact (power of two); so is the remainder.
+constexpr double FIX_LOW = 1099511627776.0;  // 2^40
+__device__ __forceinline__ void fix_add2(unsigned long long *hi, unsigned long long *lo, double v,
+                                         double scale)
+{
+    const double t = v * scale;
+    const long long h = __double2ll_rn(t);
+    atomicAdd(hi, (unsigned long long)h);
+    atomicAdd(lo, (unsigned long long)__double2ll_rn((t - (double)h) * FIX_LOW));
+}
 
 // sin(2 pi f), cos(2 pi f) for |f| <= 1/8 turn: float32 minimax polynomials on
 // [-pi/4, pi/4] (Cephes sinf/cosf coefficient sets), ~1 ulp.

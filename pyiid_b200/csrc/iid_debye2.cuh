@@ -73,17 +73,13 @@ __device__ __forceinline__ void sincos_turns(double u, float &s, float &c)
 // The kernel body, callable from the stand-alone kernel below and from the
 // fused evaluation kernel (iid_fused.cuh): block (bx, by) of a launch with
 // dynamic shared memory `smem_raw`.
-// LDCG: the staged positions are read past L1 (the fused kernel rewrites them
-// between the steps of a chain within one launch).
-template <bool LDCG>
-__device__ __forceinline__ double ld_pos(const double *a)
-{
-    return LDCG ? __ldcg(a) : *a;
-}
-
-template <int C, int MODE, int TJ2, bool CHEB, int PU = 1, bool LDCG = false>
+// PS: the positions of the item's atoms are staged in shared memory by the
+// caller (the fused evaluation kernel): ps[c * pl + k], c = x, y, z, validity;
+// k = lane for the i atoms, 32 + (j - jbegin) for the j atoms.
+template <int C, int MODE, int TJ2, bool CHEB, int PU = 1, bool PS = false>
 __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char *smem_raw,
-                                            const int bx, const int by)
+                                            const int bx, const int by,
+                                            const double *ps = nullptr, const int pl = 0)
 {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -118,8 +114,9 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
     float fw = (MODE == MODE_GRAD && (diag || !p.grad_split)) ? 0.5f : 1.f;
     const int atype = p.tile_type[itile];
     const int gi = itile * TILE_I + lane;
-    const double xi = ld_pos<LDCG>(p.x + gi), yi = ld_pos<LDCG>(p.y + gi), zi = ld_pos<LDCG>(p.z + gi);
-    const bool vi = p.valid[gi] != 0.f;
+    const double xi = PS ? ps[lane] : p.x[gi], yi = PS ? ps[pl + lane] : p.y[gi],
+                 zi = PS ? ps[2 * pl + lane] : p.z[gi];
+    const bool vi = PS ? ps[3 * pl + lane] != 0.0 : p.valid[gi] != 0.f;
 
     const float *ftab = reinterpret_cast<const float *>(p.ftab);
     const float *fa = ftab + (size_t)atype * p.qp;
@@ -190,9 +187,10 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
                 pr[u] = live[u] ? want : pr0;  // a dead slot recomputes pair pr0, stores nothing
                 const int jj = pr[u] >> 5;     // (pr & 31) == lane: this thread's own atom i
                 const int gj = jt + jj;
-                const double dxd = ld_pos<LDCG>(p.x + gj) - xi, dyd = ld_pos<LDCG>(p.y + gj) - yi,
-                             dzd = ld_pos<LDCG>(p.z + gj) - zi;
-                const bool keep = vi && p.valid[gj] != 0.f;
+                const int sj = 32 + gj - sg.jbegin;
+                const double dxd = (PS ? ps[sj] : p.x[gj]) - xi, dyd = (PS ? ps[pl + sj] : p.y[gj]) - yi,
+                             dzd = (PS ? ps[2 * pl + sj] : p.z[gj]) - zi;
+                const bool keep = vi && (PS ? ps[3 * pl + sj] != 0.0 : p.valid[gj] != 0.f);
                 const double r2 = fma(dxd, dxd, fma(dyd, dyd, dzd * dzd));
                 const float r2f = (float)r2;
                 double y = (double)rsqrtf(r2f);
@@ -423,12 +421,11 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
             const float jy = warp_sum(-phi * d.y);
             const float jz = warp_sum(-phi * d.z);
             const int oj = p.orig[jt + jj];
-            if (p.Fj != nullptr) {  // deterministic: one store per (item, j atom)
-                if (lane == 0) {
-                    double *fj = p.Fj + ((size_t)bx * p.fj_len + (jt + jj - sg.jbegin)) * 3;
-                    fj[0] = (double)jx;
-                    fj[1] = (double)jy;
-                    fj[2] = (double)jz;
+            if (p.Ffix != nullptr) {  // fixed point: bit-reproducible in any order
+                if (lane == 0 && oj >= 0) {
+                    fix_add(p.Ffix + (size_t)oj * 3 + 0, (double)jx, p.fix_scale);
+                    fix_add(p.Ffix + (size_t)oj * 3 + 1, (double)jy, p.fix_scale);
+                    fix_add(p.Ffix + (size_t)oj * 3 + 2, (double)jz, p.fix_scale);
                 }
             } else if (lane == 0 && oj >= 0) {
                 atomicAdd(&p.force[(size_t)oj * 3 + 0], (double)jx);
@@ -665,9 +662,9 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
         }
     }
     if constexpr (MODE == MODE_FORCE) {
-        if (p.Fi != nullptr) {
-            // deterministic i side: the warps' partial forces meet in shared
-            // memory and are added in warp order, one store per (item, atom)
+        if (p.Ffix != nullptr) {
+            // i side: the warps' partial forces meet in shared memory, one
+            // fixed-point atomic per (item, atom, component)
             float *fs = reinterpret_cast<float *>(smem_raw);  // [nwarp][3][32]
             fs[(warp * 3 + 0) * 32 + lane] = active ? fix : 0.f;
             fs[(warp * 3 + 1) * 32 + lane] = active ? fiy : 0.f;
@@ -677,7 +674,8 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
                 const int a = e & 31, w = e >> 5;
                 double t = 0.0;
                 for (int k = 0; k < nwarp; ++k) t += (double)fs[(k * 3 + w) * 32 + a];
-                p.Fi[((size_t)bx * 32 + a) * 3 + w] = t;
+                const int oa = p.orig[itile * TILE_I + a];
+                if (oa >= 0) fix_add(p.Ffix + (size_t)oa * 3 + w, t, p.fix_scale);
             }
             return;
         }
@@ -718,7 +716,8 @@ __device__ __forceinline__ void debye2_body(const DebyeParams &p, unsigned char 
                 v1 += (double)tr[lane * 33 + a + 1];
             }
             const double part = fweight * (v0 + v1) * (double)(fa[bin] * fb[bin]);
-            if (p.Sitem != nullptr) p.Sitem[(size_t)bx * p.qp + bin] = part;  // deterministic
+            if (p.Sfix != nullptr) fix_add2(p.Sfix + bin, p.Sfix + p.qp + bin, part, p.fix_scale);
+            else if (p.Sitem != nullptr) p.Sitem[(size_t)bx * p.qp + bin] = part;  // deterministic
             else atomicAdd(&p.S[bin], part);
         }
     }

@@ -7,19 +7,29 @@
 // graph of 6-7 small launches (staging, F(Q) pass, G(r), potential, weights,
 // force pass) that at 561 atoms spent more time in launch gaps and in the
 // one-block float64 stages than in the two pair sums.  Here the sequence is ONE
-// launch with grid-wide barriers between its phases:
+// launch with three grid-wide barriers:
 //
-//   0  staging: (leapfrog: half kick + drift) element sort, float32 rounding,
-//      clearing of the S and force accumulators
-//   1  F(Q) pass, one work item per block (debye2_body<MODE_FQ>)
+//   0  staging.  Leapfrog: every block computes the half kick + drift of the
+//      ~70 atoms of ITS work item straight into shared memory (no barrier; the
+//      owner thread of each atom also writes the drifted position and the half-
+//      kicked momentum for phase 4).  Plain evaluation: positions from the
+//      caller's pinned buffer to the device, barrier, then the same fill.
+//   1  F(Q) pass of the block's work item (debye2_body<MODE_FQ>), partial sums
+//      added to FIXED-POINT accumulators: integer atomics commute, so the sum
+//      is bit-reproducible without per-item partials or an ordered second pass
+//      --- barrier ---
 //   2  F = 2 S / na;  (M F)[m] for this block's rows of M = T^T T
+//      --- barrier ---
 //   3  every block, redundantly: Rw / chi^2, scale and the chain-rule weights
 //      in Q SPACE -- with gc = T F:  gc.go = F.(T^T go),  gc.gc = F.(M F), so
 //      neither G(r) nor the R x Q matrix is touched -- then the force pass of
-//      its work item (debye2_body<MODE_FORCE>)
-//   4  forces complete (deterministic mode: the items' partial forces added in
-//      item order); leapfrog: second half kick + centring into the destination
-//      state and its host mirror, spread over the grid
+//      its work item (debye2_body<MODE_FORCE>) into fixed-point accumulators
+//      whose scale comes from a bound of the force sum (see force_fix_scale)
+//      --- barrier ---
+//   4  forces to float64; plain evaluation: straight into the caller's pinned
+//      buffer; leapfrog: second half kick + centring into the destination state
+//      and its host mirror, spread over the grid.  A chain of leapfrog steps
+//      loops over 0-4 inside the launch (one more barrier per step).
 //
 // The Q-space scalars: a = F.vgo, b = F.MF, c = go.go (once per target);
 // scale s = a/b (<= 0: the reference's branches, master_kernel.py:229-230,
@@ -31,16 +41,22 @@
 
 namespace iid {
 
-#ifdef IID_EXP_NOLDCG  // developer A/B only (wrong for chains)
-constexpr bool FUSED_LDCG = false;
-#else
-constexpr bool FUSED_LDCG = true;
-#endif
-
 struct FusedParams {
-    DebyeParams fq;  // F(Q) pass (S = the handle's accumulator)
-    DebyeParams fo;  // force pass (wq is set per block)
+    DebyeParams fq;  // F(Q) pass (Sfix = fixed-point accumulator, fix_scale from the host)
+    DebyeParams fo;  // force pass (wq and fix_scale are set per block)
     int n_items;
+    int ps_off, pl;           // shared-memory position cache: byte offset, atoms per row
+    double s_scale_inv;       // 1 / fq.fix_scale
+    const double *gforce;     // [qp] bound of |pair force| per unit |wq| (force_fix_scale)
+    // force pass as a radial table built inside the launch (fused_table_*), or null.
+    // One table per step of a chain: the lookups go through L1 (the pairs of a
+    // work item crowd on a few neighbour distances), which is only safe for
+    // addresses written once per launch.
+    double *phi_tab;          // [chain step][ntypes^2][phi_stride] float64
+    int phi_stride, phi_cap;  // doubles per type pair; entries r = 0 .. (cap-1) h
+    int ntypes;
+    double tab_h;             // grid step: (Q_max h) = 1/8
+    double *ext_ref;          // [4] box centre of the previous evaluation + valid flag
     // staging
     int lf;  // 1 = leapfrog staging from the state slab, 0 = positions in `pos`
     const double *ctl;
@@ -77,6 +93,16 @@ __device__ __forceinline__ void fused_stamp(const FusedParams &q, int k, bool on
     }
 }
 
+// the latest block to pass this point
+__device__ __forceinline__ void fused_stamp_max(const FusedParams &q, int k, bool on = true)
+{
+    if (on && q.stamps && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(q.stamps + k, t);
+    }
+}
+
 __device__ __forceinline__ double block_sum(double v, double *sm)
 {
     v = warp_sum(v);
@@ -89,6 +115,189 @@ __device__ __forceinline__ double block_sum(double v, double *sm)
     return t;
 }
 
+// ---- the force pass as a radial table (small structures) ---------------------
+// For fixed weights the Q sum of a pair's force depends on the pair only through
+// r and the two element types (iid_force_table.cuh):
+//   Phi_ab(r) = sum_m w_ab[m] (Q_m r cos(Q_m r) - sin(Q_m r)) / r^3.
+// The fused kernel tabulates it in FLOAT64 on a uniform grid with Q_max h = 1/8
+// (FT_G lanes per entry, three-term recurrences from exact seeds), barrier, then
+// takes one 8-point Lagrange interpolation per pair: error 1.1e-3 (Q_max h)^8 =
+// 6e-11 |Phi|, so the forces carry the float32 rounding of the positions and
+// nothing else.  At Au561 that is 8 000 entries x 330 bins (2.6 M terms)
+// instead of 157 000 pairs x 330 bins.
+constexpr int FT_PAD = 4;  // entries stored before r = 0 (nodes k-3 .. k+4)
+constexpr int FT_G = 8;    // lanes per table entry
+
+__device__ __forceinline__ void fused_table_build(double *tab, int stride, int ntp, int K,
+                                                  double h, const double *wab, int nq, int qp,
+                                                  double qbin)
+{
+    const int Kp = K + 2 * FT_PAD, total = ntp * Kp;
+    const int epb = blockDim.x / FT_G;  // entries per block and round
+    const int g = threadIdx.x & (FT_G - 1);
+    const int per = (nq + FT_G - 1) / FT_G;
+    const int mb = min(nq, g * per), me = min(nq, mb + per);
+    // every block builds an equal, contiguous share of the entries
+    const int share = (total + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * share, t_end = min(total, t_begin + share);
+    for (int t0 = t_begin; t0 < t_end; t0 += epb) {  // block-uniform
+        const int t = t0 + threadIdx.x / FT_G;
+        const bool ok = t < t_end;
+        const int tt = ok ? t : total - 1;
+        const int pair = tt / Kp, e = tt - pair * Kp;
+        const double r = fabs((double)(e - FT_PAD)) * h;  // Phi is even in r
+        const double *w = wab + (size_t)pair * qp;
+        const bool series = qbin * (double)nq * r < 0.05;  // uniform over the FT_G lanes
+        double phi = 0.0;
+        if (series) {
+            // (x cos x - sin x)/r^3 = Q^3 (-1/3 + x^2/30 - x^4/840), x = Q r
+            for (int m = mb; m < me; ++m) {
+                const double qq = qbin * (double)m, xx = qq * r * qq * r;
+                phi += w[m] * qq * qq * qq * (-1.0 / 3.0 + xx * (1.0 / 30.0 - xx * (1.0 / 840.0)));
+            }
+        } else {
+            const double turns = qbin * r * 0.15915494309189533577;  // theta / 2 pi
+            double sth, cth, sn, cn;
+            sincospi(2.0 * (turns - rint(turns)), &sth, &cth);
+            const double ph = turns * (double)mb;
+            sincospi(2.0 * (ph - rint(ph)), &sn, &cn);
+            // three-term recurrences s[m+1] = 2 cos(theta) s[m] - s[m-1] from bins mb-1, mb
+            double sp = fma(sn, cth, -(cn * sth)), cp = fma(cn, cth, sn * sth);
+            const double tc = cth + cth, kap = qbin * r;
+            double mk = kap * (double)mb;
+            for (int m = mb; m < me; ++m) {
+                phi = fma(w[m], fma(mk, cn, -sn), phi);
+                const double s2 = fma(tc, sn, -sp), c2 = fma(tc, cn, -cp);
+                sp = sn;
+                sn = s2;
+                cp = cn;
+                cn = c2;
+                mk += kap;
+            }
+        }
+#pragma unroll
+        for (int o = FT_G / 2; o > 0; o >>= 1) phi += __shfl_xor_sync(0xffffffffu, phi, o);
+        if (!series) phi /= r * r * r;
+        if (g == 0 && ok) tab[(size_t)pair * stride + e] = phi;
+    }
+}
+
+// Phi summed directly over the Q bins (float64 rotation recurrence): the pairs
+// beyond the tabulated range of an unusually extended structure.
+__device__ double fused_phi_direct(double r, const double *w, int nq, double qbin)
+{
+    const double turns = qbin * r * 0.15915494309189533577;
+    double sth, cth;
+    sincospi(2.0 * (turns - rint(turns)), &sth, &cth);
+    double s = 0.0, c = 1.0, mk = 0.0, phi = 0.0;
+    const double kap = qbin * r;
+    for (int m = 0; m < nq; ++m) {
+        phi = fma(w[m], fma(mk, c, -s), phi);
+        const double sn = fma(s, cth, c * sth);
+        c = fma(c, cth, -(s * sth));
+        s = sn;
+        mk += kap;
+    }
+    return phi / (r * r * r);
+}
+
+// 8-point Lagrange interpolation on the uniform grid: nodes k-3 .. k+4 at
+// t[-3] .. t[4], u in [0, 1) measured from node k.
+__device__ __forceinline__ double lagrange8(const double *t, double u)
+{
+    double v[8], d[8], pre[8], L = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v[i] = t[i - 3];  // (L1: neighbouring pairs share these lines; see phi_tab)
+        d[i] = u - (double)(i - 3);
+    }
+    pre[0] = 1.0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) pre[i] = pre[i - 1] * d[i - 1];
+    // barycentric weights of 8 equispaced nodes: (-1)^(7-i) C(7, i) / 7!
+    const double bw[8] = {-1.0 / 5040.0, 7.0 / 5040.0, -21.0 / 5040.0, 35.0 / 5040.0,
+                          -35.0 / 5040.0, 21.0 / 5040.0, -7.0 / 5040.0, 1.0 / 5040.0};
+    double suf = 1.0;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        L = fma(v[i] * bw[i], pre[i] * suf, L);
+        suf *= d[i];
+    }
+    return L;
+}
+
+// The force pass of one work item from the table: one warp iteration per j atom
+// (lane = atom i); the i side is summed over the warps in shared memory.
+__device__ __forceinline__ void fused_table_forces(const FusedParams &q, const WorkItem wi,
+                                                   const double *ps, int pl, const double *tab,
+                                                   int K, double inv_h, const double *w,
+                                                   double fscale, double *fs /* [nw][3][32] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const bool diag = (wi.info & ITEM_DIAG) != 0;
+    const int len = wi.jend - wi.jbegin;
+    const double xi = ps[lane], yi = ps[pl + lane], zi = ps[2 * pl + lane];
+    const bool vi = ps[3 * pl + lane] != 0.0;
+    const double klast = (double)(K - 5);  // nodes k-3 .. k+4 all tabulated
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for (int jj = warp; jj < len; jj += nw) {
+        const int sj = TILE_I + jj;
+        const double dx = ps[sj] - xi, dy = ps[pl + sj] - yi, dz = ps[2 * pl + sj] - zi;
+        const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+        double phi = 0.0;
+        if (vi && ps[3 * pl + sj] != 0.0 && r2 > 0.0) {  // not a ghost atom, self pair, r == 0
+            double y = (double)rsqrtf((float)r2);
+            y = y * fma(-0.5 * r2, y * y, 1.5);
+            y = y * fma(-0.5 * r2, y * y, 1.5);  // second Newton step: 1e-15
+            const double r = r2 * y, tpos = r * inv_h;
+            if (tpos < klast) {
+                const int k = (int)tpos;
+                phi = lagrange8(tab + k, tpos - (double)k);
+            } else {
+                phi = fused_phi_direct(r, w, q.fq.nq, q.fq.qbin);
+            }
+        }
+        fx = fma(phi, dx, fx);
+        fy = fma(phi, dy, fy);
+        fz = fma(phi, dz, fz);
+        if (!diag) {  // Newton's third law for the j atom
+            const double jx = warp_sum(-phi * dx), jy = warp_sum(-phi * dy),
+                         jz = warp_sum(-phi * dz);
+            const int oj = q.fq.orig[wi.jbegin + jj];
+            if (lane == 0 && oj >= 0) {
+                fix_add(q.fo.Ffix + (size_t)oj * 3 + 0, jx, fscale);
+                fix_add(q.fo.Ffix + (size_t)oj * 3 + 1, jy, fscale);
+                fix_add(q.fo.Ffix + (size_t)oj * 3 + 2, jz, fscale);
+            }
+        }
+    }
+    fs[(warp * 3 + 0) * 32 + lane] = fx;
+    fs[(warp * 3 + 1) * 32 + lane] = fy;
+    fs[(warp * 3 + 2) * 32 + lane] = fz;
+    __syncthreads();
+    for (int e = threadIdx.x; e < 96; e += blockDim.x) {  // (a block may be one warp)
+        const int a = e & 31, c = e >> 5;
+        double t = 0.0;
+        for (int k = 0; k < nw; ++k) t += fs[(k * 3 + c) * 32 + a];
+        const int oa = q.fq.orig[wi.itile * TILE_I + a];
+        if (oa >= 0) fix_add(q.fo.Ffix + (size_t)oa * 3 + c, t, fscale);
+    }
+}
+
+// Power-of-two scale of the fixed-point force accumulators.  One pair adds
+// phi * d to a force component with phi = sum_q w_q [x cos x - sin x] / r^3,
+// x = Q r, |d| <= r, and |x cos x - sin x| <= min(x^3 / 3, x + 1), so
+// |phi d| <= sum_q |w_q| Q^2 max_x min(x / 3, (x + 1) / x^2) < 0.6 sum_q |w_q| Q^2.
+// gforce[m] = 0.6 Q_m^2 max_types f^2 / na (host), bound = n sum_m |wq[m]| gforce[m];
+// every block computes the same number in the same order.
+__device__ __forceinline__ double force_fix_scale(double bound)
+{
+    if (!(bound > 0.0) || !(bound < 1e300)) return 1.0;
+    int e;
+    frexp(bound, &e);  // bound < 2^e
+    return ldexp(1.0, 60 - e);
+}
+
 template <bool CHEB>
 __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
 {
@@ -96,6 +305,15 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     const int nq = q.fq.nq, qp = q.fq.qp;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    const bool has_item = (int)blockIdx.x < q.n_items;
+    double *ps = reinterpret_cast<double *>(smem_raw + q.ps_off);  // [4][pl]
+    const int pl = q.pl;
+    double *pall = ps + 4 * pl;  // [3][n] all positions, caller order
+    __shared__ double ext[8];    // their extent: table range, centring shift
+    __shared__ double cref[4];   // reference point of the extent (phase 0)
+    if (threadIdx.x < 4) cref[threadIdx.x] = q.ext_ref[threadIdx.x];
+    __syncthreads();
 
   // the step parameters of the whole chain: ONE round trip to the pinned staging
   // per block and launch
@@ -105,89 +323,177 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
           ctl_all[k] = q.ctl[(size_t)(k / LF_CTL) * q.chain_stride + k % LF_CTL];
       __syncthreads();
   }
+  const int scs = q.n_chain > 1 ? 1 : 0;  // the step whose phases are stamped (developer timing)
   for (int cs = 0; cs < q.n_chain; ++cs) {
     // a chain of leapfrog steps: step cs mirrors its state to ring slot cs of the
     // pinned staging.  Everything another block wrote in an EARLIER step of this
     // launch is read past L1 (ld.cg).
     const double *ctl = ctl_all + cs * LF_CTL;
-    fused_stamp(q, 0, cs == 0);
+    fused_stamp(q, 0, cs == scs);
+    fused_stamp(q, 12 + cs, cs < 4);  // start of the first four steps of a chain
     // ---- phase 0: staging ---------------------------------------------------------
-    {
-        const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-        for (int e = gtid; e < qp; e += gsz) q.fq.S[e] = 0.0;
-        for (int e = gtid; e < 3 * q.n; e += gsz) q.fo.force[e] = 0.0;
-        for (int k = gtid; k < q.np; k += gsz) {
-            const int o = q.fq.orig[k];
-            double c[3] = {0.0, 0.0, 0.0};
-            if (o >= 0) {
-                if (q.lf) {
-                    // p_half = p + (step/2) f; q' = q + step p_half / m (numpy's
-                    // operation order, see lf_stage_kernel)
-                    const double step = ctl[0];
-                    const int src = (int)ctl[1], dst = (int)ctl[2];
-                    const double *qq = lf_slot(q.slab, q.n, src, 0),
-                                 *pp = lf_slot(q.slab, q.n, src, 1),
-                                 *ff = lf_slot(q.slab, q.n, src, 2);
-                    double *pd = lf_slot(q.slab, q.n, dst, 1);
-                    const double half = __dmul_rn(0.5, step), m = q.mass[o];
+    // Every block holds ALL positions in shared memory (13 KB at Au561): their
+    // extent (table range, centring shift) and the atoms of its own work item come
+    // from there without another trip to L2.
+    // Extent of the positions while they pass through registers: bounding box and
+    // the largest distance from a reference point c (the box centre of the previous
+    // evaluation, i.e. the structure's centre up to one step's drift).  Every pair
+    // distance is <= min(box diagonal, 2 max |x - c|) for ANY c; the table range
+    // only decides how many entries are built, not their values.
+    const bool want_ext = q.phi_tab != nullptr || q.lf_mirror != nullptr;
+    double ev[6] = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300}, ed2 = 0.0;
+    const double rcx = cref[0], rcy = cref[1], rcz = cref[2];
+    auto ext_acc = [&](double x, double y, double z) {
+        ev[0] = fmin(ev[0], x); ev[3] = fmax(ev[3], x);
+        ev[1] = fmin(ev[1], y); ev[4] = fmax(ev[4], y);
+        ev[2] = fmin(ev[2], z); ev[5] = fmax(ev[5], z);
+        const double dx = x - rcx, dy = y - rcy, dz = z - rcz;
+        ed2 = fmax(ed2, fma(dx, dx, fma(dy, dy, dz * dz)));
+    };
+    if (q.lf) {
+        // leapfrog: half kick + drift from the state slab, computed by every block
+        // for itself (no barrier); block (a mod grid) also writes atom a's drifted
+        // position and half-kicked momentum for phase 4
+        const double step = ctl[0], half = __dmul_rn(0.5, step);
+        const int src = (int)ctl[1], dst = (int)ctl[2];
+        const double *qq = lf_slot(q.slab, q.n, src, 0), *pp = lf_slot(q.slab, q.n, src, 1),
+                     *ff = lf_slot(q.slab, q.n, src, 2);
+        double *pd = lf_slot(q.slab, q.n, dst, 1);
+        // two atoms per thread and trip, all loads first: the stores below may
+        // alias them as far as the compiler knows, and one L2 round trip per atom
+        // in a row was 3 us at Au561
+        for (int a0 = threadIdx.x; a0 < q.n; a0 += 2 * blockDim.x) {
+            double xq[2][3], xp[2][3], xf[2][3], m[2];
 #pragma unroll
-                    for (int w = 0; w < 3; ++w) {
-                        const size_t e = 3 * (size_t)o + w;
-                        const double ph = __dadd_rn(__ldcg(pp + e), __dmul_rn(half, __ldcg(ff + e)));
-                        pd[e] = ph;
-                        const double qn = __dadd_rn(__ldcg(qq + e), __dmul_rn(step, __ddiv_rn(ph, m)));
-                        q.pos[e] = qn;
-                        c[w] = qn;
-                    }
-                } else if (q.pos_in) {
+            for (int u = 0; u < 2; ++u) {
+                const int a = min(a0 + u * (int)blockDim.x, q.n - 1);
+                m[u] = q.mass[a];
 #pragma unroll
-                    for (int w = 0; w < 3; ++w) {
-                        c[w] = q.pos_in[3 * (size_t)o + w];
-                        q.pos[3 * (size_t)o + w] = c[w];  // device copy for the kernels that follow
-                    }
-                } else {
-#pragma unroll
-                    for (int w = 0; w < 3; ++w) c[w] = q.pos[3 * (size_t)o + w];
+                for (int w = 0; w < 3; ++w) {
+                    const size_t e = 3 * (size_t)a + w;
+                    xq[u][w] = __ldcg(qq + e);
+                    xp[u][w] = __ldcg(pp + e);
+                    xf[u][w] = __ldcg(ff + e);
                 }
-                if (q.round_f32)
-#pragma unroll
-                    for (int w = 0; w < 3; ++w) c[w] = (double)(float)c[w];
             }
-            const_cast<double *>(q.fq.x)[k] = c[0];
-            const_cast<double *>(q.fq.y)[k] = c[1];
-            const_cast<double *>(q.fq.z)[k] = c[2];
-            const_cast<float *>(q.fq.valid)[k] = o >= 0 ? 1.f : 0.f;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int a = a0 + u * (int)blockDim.x;
+                if (a >= q.n) break;
+                const bool owner = a % (int)gridDim.x == (int)blockIdx.x;
+                double qn[3];
+#pragma unroll
+                for (int w = 0; w < 3; ++w) {
+                    // p_half = p + (step/2) f;  q' = q + step p_half / m (numpy's
+                    // operation order, see lf_stage_kernel)
+                    const double ph = __dadd_rn(xp[u][w], __dmul_rn(half, xf[u][w]));
+                    qn[w] = __dadd_rn(xq[u][w], __dmul_rn(step, __ddiv_rn(ph, m[u])));
+                    pall[w * q.n + a] = qn[w];
+                    if (owner) {
+                        q.pos[3 * (size_t)a + w] = qn[w];
+                        pd[3 * (size_t)a + w] = ph;
+                    }
+                }
+                ext_acc(qn[0], qn[1], qn[2]);
+            }
+        }
+        fused_stamp(q, 1, cs == scs);
+    } else {
+        if (q.pos_in) {
+            for (int e = gtid; e < 3 * q.n; e += gsz) q.pos[e] = q.pos_in[e];
+            fused_stamp(q, 1, cs == scs);
+            grid.sync();
+        } else {
+            fused_stamp(q, 1, cs == scs);
+        }
+        for (int a = threadIdx.x; a < q.n; a += blockDim.x) {
+            double c[3];
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                c[w] = __ldcg(q.pos + 3 * (size_t)a + w);
+                pall[w * q.n + a] = c[w];
+            }
+            ext_acc(c[0], c[1], c[2]);
         }
     }
-    fused_stamp(q, 1, cs == 0);
-    grid.sync();
-    fused_stamp(q, 2, cs == 0);
+    __shared__ double extp[7][12];
+    if (want_ext) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                ev[w] = fmin(ev[w], __shfl_xor_sync(0xffffffffu, ev[w], o));
+                ev[3 + w] = fmax(ev[3 + w], __shfl_xor_sync(0xffffffffu, ev[3 + w], o));
+            }
+            ed2 = fmax(ed2, __shfl_xor_sync(0xffffffffu, ed2, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) extp[c][threadIdx.x >> 5] = ev[c];
+            extp[6][threadIdx.x >> 5] = ed2;
+        }
+    }
+    __syncthreads();
+    if (want_ext && threadIdx.x < 7) {
+        const int c = threadIdx.x, nw = blockDim.x >> 5;
+        double v = extp[c][0];
+        for (int k = 1; k < nw; ++k) v = (c < 3) ? fmin(v, extp[c][k]) : fmax(v, extp[c][k]);
+        ext[c] = v;  // [6]: largest squared distance from the reference point, for now
+    }
+    // the atoms of this block's work item (32 i atoms, then its j range), element-
+    // sorted order, float32-rounded in FP32 mode: both pair passes read these
+    if (has_item) {
+        const WorkItem wi = q.fq.items[blockIdx.x];
+        const int cnt = TILE_I + (wi.jend - wi.jbegin);
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+            const int g = k < TILE_I ? wi.itile * TILE_I + k : wi.jbegin + (k - TILE_I);
+            const int o = q.fq.orig[g];
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                const double c = o >= 0 ? pall[w * q.n + o] : 0.0;
+                ps[w * pl + k] = q.round_f32 ? (double)(float)c : c;
+            }
+            ps[3 * pl + k] = o >= 0 ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    if (want_ext && threadIdx.x == 0) {
+        const double ex = ext[3] - ext[0], ey = ext[4] - ext[1], ez = ext[5] - ext[2];
+        const double half_diag = 0.5 * sqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
+#ifdef IID_DEBUG_EXT
+        if (blockIdx.x == 0)
+            printf("cs %d ext lo %.3f %.3f %.3f hi %.3f %.3f %.3f d2 %.3f half_diag %.3f cref %.3f %.3f %.3f %.1f\n",
+                   cs, ext[0], ext[1], ext[2], ext[3], ext[4], ext[5], ext[6], half_diag, cref[0],
+                   cref[1], cref[2], cref[3]);
+#endif
+        ext[6] = cref[3] != 0.0 ? fmin(half_diag, sqrt(ext[6])) : half_diag;
+        cref[0] = 0.5 * (ext[0] + ext[3]);
+        cref[1] = 0.5 * (ext[1] + ext[4]);
+        cref[2] = 0.5 * (ext[2] + ext[5]);
+        cref[3] = 1.0;  // (read again at the next step's staging, barriers from here)
+    }
+    fused_stamp(q, 2, cs == scs);
 
     // ---- phase 1: F(Q) pass -------------------------------------------------------
-    if ((int)blockIdx.x < q.n_items)
-        debye2_body<32, MODE_FQ, 8, CHEB, 1, FUSED_LDCG>(q.fq, smem_raw, (int)blockIdx.x, 0);
-    fused_stamp(q, 3, cs == 0);
+    if (has_item)
+        debye2_body<32, MODE_FQ, 8, CHEB, 1, true>(q.fq, smem_raw, (int)blockIdx.x, 0, ps, pl);
+    fused_stamp(q, 3, cs == scs);
     grid.sync();
-    if (q.fq.Sitem != nullptr) {
-        // deterministic F(Q): the items' partial sums added in item order, one
-        // warp per Q bin (lanes over items, butterfly sum)
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        for (int m = blockIdx.x * nw + warp; m < nq; m += gridDim.x * nw) {
-            double acc = 0.0;
-            for (int it = lane; it < q.n_items; it += 32) acc += __ldcg(q.fq.Sitem + (size_t)it * qp + m);
-            acc = warp_sum(acc);
-            if (lane == 0) q.fq.S[m] = acc;
-        }
-        grid.sync();
-    }
-    fused_stamp(q, 4, cs == 0);
+    fused_stamp(q, 4, cs == scs);
 
     // ---- phase 2: F and this block's rows of M F ------------------------------------
     double *Fs = reinterpret_cast<double *>(smem_raw);  // [qp]
-    double *Ms = Fs + qp;                               // [qp] M F
+    double *Ms = Fs + qp;                               // [qp] M F, then the weights
     double *red = Ms + qp;                              // [32]
-    for (int m = threadIdx.x; m < qp; m += blockDim.x)
-        Fs[m] = m < nq ? 2.0 * __ldcg(q.fq.S + m) * q.inv_na_d[m] : 0.0;
+    double *wab = red + 32;                             // [ntypes^2][qp] (table force pass)
+    for (int m = threadIdx.x; m < qp; m += blockDim.x) {
+        const double sm = m < nq ? ((double)(long long)__ldcg(q.fq.Sfix + m) +
+                                    (double)(long long)__ldcg(q.fq.Sfix + qp + m) * (1.0 / FIX_LOW)) *
+                                       q.s_scale_inv
+                                 : 0.0;
+        Fs[m] = 2.0 * sm * q.inv_na_d[m];
+        if (blockIdx.x == 0) q.fq.S[m] = sm;  // the handle's pair sums stay current
+    }
     __syncthreads();
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -199,11 +505,14 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
             if (lane == 0) q.MF[row] = acc;
         }
     }
-    fused_stamp(q, 5, cs == 0);
+    fused_stamp(q, 5, cs == scs);
     grid.sync();
-    fused_stamp(q, 6, cs == 0);
+    fused_stamp(q, 6, cs == scs);
 
     // ---- phase 3: potential + weights (every block), then the force pass ------------
+    // (every block has read the F(Q) accumulators: clear them for the next pass)
+    if (blockIdx.x == 0)
+        for (int m = threadIdx.x; m < 2 * qp; m += blockDim.x) q.fq.Sfix[m] = 0ull;
     double la = 0.0, lb = 0.0;
     for (int m = threadIdx.x; m < nq; m += blockDim.x) {
         const double mf = __ldcg(q.MF + m);
@@ -232,8 +541,15 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
     const double coef0 = pref * (scale + gdb);
     const double coef1 = pref * (scale * scale + 2.0 * gdb * scale_true);
     double *wq = q.wq_blk + (size_t)blockIdx.x * qp;
-    for (int m = threadIdx.x; m < qp; m += blockDim.x)
-        wq[m] = m < nq ? q.conv * (coef0 * q.vgo[m] - coef1 * Ms[m]) : 0.0;
+    const bool table = q.phi_tab != nullptr;
+    double lw = 0.0;
+    for (int m = threadIdx.x; m < qp; m += blockDim.x) {
+        const double w = m < nq ? q.conv * (coef0 * q.vgo[m] - coef1 * Ms[m]) : 0.0;
+        if (table) Ms[m] = w;  // (each thread reads and writes its own elements)
+        else wq[m] = w;
+        lw = fma(fabs(w), q.gforce[m], lw);
+    }
+    const double fscale = force_fix_scale((double)q.n * block_sum(lw, red));
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         q.out4[0] = value * q.conv;
         q.out4[1] = scale;
@@ -241,66 +557,61 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
         q.out4[3] = scale_true;
         q.out4[4] = 0.0;  // restraint energy, summed by the spring kernels that follow
     }
-    __syncthreads();  // wq is complete (block scope) and the scratch is free again
-    fused_stamp(q, 7, cs == 0);
-    if ((int)blockIdx.x < q.n_items) {
+    __syncthreads();  // the weights are complete (block scope) and `red` is free again
+    fused_stamp(q, 7, cs == scs);
+    if (table) {
+        // weights of each element pair, the table over r = 0 .. 2 x radius, barrier,
+        // one interpolation per pair of the block's work item
+        const int nt = q.ntypes, ntp = nt * nt;
+        const float *ftab = reinterpret_cast<const float *>(q.fq.ftab);
+        const float *inv_na = reinterpret_cast<const float *>(q.fq.inv_na);
+        for (int idx = threadIdx.x; idx < ntp * qp; idx += blockDim.x) {
+            const int pr = idx / qp, m = idx - pr * qp;
+            wab[idx] = Ms[m] * (double)ftab[(size_t)(pr / nt) * qp + m] *
+                       (double)ftab[(size_t)(pr % nt) * qp + m] * (double)inv_na[m];
+        }
+        __syncthreads();
+        const double h = q.tab_h;
+        const int K = (int)fmin((double)q.phi_cap, ceil(2.0000002 * ext[6] / h) + 8.0);
+        if (q.stamps && blockIdx.x == 0 && threadIdx.x == 0) {  // developer timing
+            q.ext_ref[4] = ext[6];
+            q.ext_ref[5] = (double)K;
+        }
+        double *tab = q.phi_tab + (size_t)cs * ntp * q.phi_stride;
+        fused_table_build(tab, q.phi_stride, ntp, K, h, wab, nq, qp, q.fq.qbin);
+        fused_stamp(q, 16, cs == scs);
+        fused_stamp_max(q, 18, cs == scs);
+        grid.sync();
+        fused_stamp(q, 17, cs == scs);
+        if (has_item) {
+            const WorkItem wi = q.fq.items[blockIdx.x];
+            const int pr = q.fq.tile_type[wi.itile] * nt + (wi.info & 0xffff);
+            fused_table_forces(q, wi, ps, pl, tab + (size_t)pr * q.phi_stride + FT_PAD, K,
+                               1.0 / h, wab + (size_t)pr * qp, fscale, wab + (size_t)ntp * qp);
+        }
+    } else if (has_item) {
         DebyeParams fo = q.fo;
         fo.wq = wq;
-        debye2_body<32, MODE_FORCE, 8, CHEB, 1, FUSED_LDCG>(fo, smem_raw, (int)blockIdx.x, 0);
+        fo.fix_scale = fscale;
+        debye2_body<32, MODE_FORCE, 8, CHEB, 1, true>(fo, smem_raw, (int)blockIdx.x, 0, ps, pl);
     }
-    fused_stamp(q, 8, cs == 0);
-    // ---- phase 4: the forces are complete after one more barrier.  Deterministic
-    // mode adds the items' partial forces in item order; the results go straight
-    // into the caller's pinned buffer (plain evaluation) or through the leapfrog's
-    // second half kick into the destination state and its host mirror ------------
+    fused_stamp(q, 8, cs == scs);
+    fused_stamp_max(q, 19, cs == scs);
+    // ---- phase 4: forces to float64; plain evaluation: results straight into the
+    // caller's pinned buffer; leapfrog: second half kick into the destination state
+    // and its host mirror ----------------------------------------------------------
     const bool finish = q.lf_mirror != nullptr;
     double *mirror = finish ? q.lf_mirror + (size_t)cs * q.chain_stride : nullptr;
     __shared__ double lf_shift[3];
-    if (finish) lf_shift_block(ctl, q.pos, q.n, lf_shift);  // while the slowest block finishes
-    if (q.fo.Fi != nullptr) {
-        grid.sync();
-        fused_stamp(q, 9, cs == 0);
-        // one warp per atom, lanes over the items (each lane adds its items in item
-        // order, then a butterfly sum: the same order on every run)
-        const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        for (int g = blockIdx.x * nw + warp; g < q.np; g += gridDim.x * nw) {
-            const int o = q.fq.orig[g];
-            if (o < 0) continue;  // warp-uniform
-            const int tile = g / TILE_I, a = g - tile * TILE_I;
-            double fx = 0.0, fy = 0.0, fz = 0.0;
-            for (int it = lane; it < q.n_items; it += 32) {
-                const WorkItem wi = q.fq.items[it];
-                if (wi.itile == tile) {
-                    const double *fi = q.fo.Fi + ((size_t)it * 32 + a) * 3;
-                    fx += __ldcg(fi);
-                    fy += __ldcg(fi + 1);
-                    fz += __ldcg(fi + 2);
-                }
-                if (!(wi.info & ITEM_DIAG) && g >= wi.jbegin && g < wi.jend) {
-                    const double *fj = q.fo.Fj + ((size_t)it * q.fo.fj_len + (g - wi.jbegin)) * 3;
-                    fx += __ldcg(fj);
-                    fy += __ldcg(fj + 1);
-                    fz += __ldcg(fj + 2);
-                }
-            }
-            fx = warp_sum(fx);
-            fy = warp_sum(fy);
-            fz = warp_sum(fz);
-            if (lane < 3) {
-                const double f = lane == 0 ? fx : (lane == 1 ? fy : fz);
-                const size_t e = (size_t)o * 3 + lane;
-                q.fo.force[e] = f;
-                if (q.force_out) q.force_out[e] = f;
-                if (finish) lf_kick(ctl, q.slab, q.n, q.pos, mirror, lf_shift, e, lane, f);
-            }
-        }
-        if (q.force_out && gtid < 5) q.out_host[gtid] = __ldcg(q.out4 + gtid);
-    } else if (q.force_out || finish) {
-        grid.sync();
-        const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    if (finish && threadIdx.x < 3) lf_shift[threadIdx.x] = lf_shift_of(ctl, ext, threadIdx.x);
+    grid.sync();  // (also a block barrier: lf_shift is visible)
+    fused_stamp(q, 9, cs == scs);
+    {
+        const double inv = 1.0 / fscale;  // a power of two
         for (int e = gtid; e < 3 * q.n; e += gsz) {
-            const double f = __ldcg(q.fo.force + e);
+            const double f = (double)(long long)__ldcg(q.fo.Ffix + e) * inv;
+            q.fo.Ffix[e] = 0ull;  // clear for the next pass
+            q.fo.force[e] = f;
             if (q.force_out) q.force_out[e] = f;
             if (finish) lf_kick(ctl, q.slab, q.n, q.pos, mirror, lf_shift, e, e % 3, f);
         }
@@ -314,13 +625,24 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
             const int k = threadIdx.x;
             out[k] = k < 5 ? __ldcg(q.out4 + k) : (k == 5 ? 0.0 : lf_shift[k - 6]);
         }
-        // the next step's staging reads the state written here and clears the
-        // accumulators read here
-        fused_stamp(q, 10, cs == 0);
-        if (cs + 1 < q.n_chain) grid.sync();
-        fused_stamp(q, 11, cs == 0);
+        // the next step's staging reads the state written here
+        fused_stamp(q, 10, cs == scs);
+        if (cs + 1 < q.n_chain) {
+            grid.sync();
+            // every block's share of the mirror is written: tell the host that step
+            // cs is complete (iid_leapfrog_chain_next polls this word; the last
+            // step's completion is the end of the launch)
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                __threadfence_system();
+                *reinterpret_cast<volatile double *>(out + 15) = ctl[7];
+            }
+        }
+        fused_stamp(q, 11, cs == scs);
     }
   }
+  // (cref was last written by thread 0, barriers ago)
+  if (blockIdx.x == 0 && threadIdx.x < 4 && (q.phi_tab != nullptr || q.lf_mirror != nullptr))
+      q.ext_ref[threadIdx.x] = cref[threadIdx.x];
 }
 
 }  // namespace iid

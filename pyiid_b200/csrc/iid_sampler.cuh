@@ -174,51 +174,18 @@ __device__ __forceinline__ void lf_finish_body(const double *ctl, double *slab,
 }
 
 // The same second half of the step spread over a whole grid (the fused
-// evaluation kernel): every block computes the centring shift of the drifted
-// positions for itself (min / max are exact in any order), then element e of
-// the state is finished by whichever thread holds its force.  The kinetic
-// energy is summed by the host from the mirrored momenta.
-__device__ __forceinline__ void lf_shift_block(const double *ctl, const double *pos, int n,
-                                               double *shift /* shared [3] */)
+// evaluation kernel): every block computes the extent of the drifted positions
+// for itself (min / max are exact in any order) -- the centring shift follows
+// from the bounding box -- then element e of the state is finished by whichever
+// thread holds its force.  The kinetic energy is summed by the host from the
+// mirrored momenta.
+//
+// ext (shared, [8]): bounding box lo x y z, hi x y z of the drifted positions
+// (phase 0 of the fused kernel).
+// numpy: q + (centre - 0.5 * (min + max))
+__device__ __forceinline__ double lf_shift_of(const double *ctl, const double *ext, int w)
 {
-    __shared__ double red[6][32];
-    const bool centre = ctl[3] != 0.0;
-    if (!centre) {
-        if (threadIdx.x < 3) shift[threadIdx.x] = 0.0;
-        __syncthreads();
-        return;
-    }
-    double v[6] = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300};
-    for (int a = threadIdx.x; a < n; a += blockDim.x)
-#pragma unroll
-        for (int w = 0; w < 3; ++w) {
-            const double x = __ldcg(pos + 3 * a + w);
-            v[w] = fmin(v[w], x);
-            v[3 + w] = fmax(v[3 + w], x);
-        }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int w = 0; w < 3; ++w) {
-            v[w] = fmin(v[w], __shfl_xor_sync(0xffffffffu, v[w], o));
-            v[3 + w] = fmax(v[3 + w], __shfl_xor_sync(0xffffffffu, v[3 + w], o));
-        }
-    if (lane == 0)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) red[c][warp] = v[c];
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        const int w = threadIdx.x;
-        double lo = 1e300, hi = -1e300;
-        for (int k = 0; k < nw; ++k) {
-            lo = fmin(lo, red[w][k]);
-            hi = fmax(hi, red[3 + w][k]);
-        }
-        // numpy: q + (centre - 0.5 * (min + max))
-        shift[w] = __dsub_rn(ctl[4 + w], __dmul_rn(0.5, __dadd_rn(lo, hi)));
-    }
-    __syncthreads();
+    return ctl[3] != 0.0 ? __dsub_rn(ctl[4 + w], __dmul_rn(0.5, __dadd_rn(ext[w], ext[3 + w]))) : 0.0;
 }
 
 __device__ __forceinline__ void lf_kick(const double *ctl, double *slab, int n, const double *pos,

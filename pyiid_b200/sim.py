@@ -25,6 +25,7 @@ import numpy as np
 from numpy.random import RandomState
 
 from . import ase_shim
+from . import _lib
 
 if ase_shim.have_real_ase():  # pragma: no cover
     from ase.optimize.optimize import Optimizer
@@ -326,19 +327,31 @@ class _DeviceSystem(_FastSystem):
         self.pool = be._slot_pool
         # look-ahead: buildtree grows a subtree of depth j by 2**j leapfrogs in a
         # row from the tree's edge; `expect(n)` announces them, and `leapfrog`
-        # then computes up to CHAIN of them per native call (one synchronisation
-        # per chain instead of one per step).  States computed ahead but not
-        # asked for (the subtree stopped early) are dropped unseen: results and
-        # the order of the random numbers are those of the step-by-step walk.
-        self._ahead = collections.deque()  # (predecessor state, step, new state)
+        # then ENQUEUES up to CHAIN of them in one native call (one cooperative
+        # launch walks the whole chain) and collects them one by one as the
+        # device completes them, so the tree logic of step i runs while the
+        # device computes step i + 1.  Steps enqueued but not asked for (the
+        # subtree stopped early) are dropped unseen: results and the order of
+        # the random numbers are those of the step-by-step walk.
+        self._ahead = collections.deque()  # destination slots of the chain in flight
+        self._ahead_prev = None            # the state the next step of the chain starts from
+        self._ahead_step = 0.
+        self._ahead_id = 0
         self._expected = 0
 
     CHAIN = 16
 
     def expect(self, n):
         """The next ``n`` leapfrog calls continue one trajectory."""
+        self._drop_ahead()
         self._expected = int(n)
-        self._ahead.clear()
+
+    def _drop_ahead(self):
+        """Forget the chain in flight (the native library waits for it and drops
+        its uncollected steps at the next call)."""
+        while self._ahead:
+            self.pool.give(self._ahead.popleft())
+        self._ahead_prev = None
 
     @staticmethod
     def usable(atoms):
@@ -355,6 +368,7 @@ class _DeviceSystem(_FastSystem):
         return not (getattr(scat, '_device_sel', None) == 'multi' and len(atoms) >= 3000)
 
     def state_of(self, atoms):
+        self._drop_ahead()  # (the upload below is another call on the handle)
         st = _FastSystem.state_of(self, atoms)
         slot = self.pool.take()
         self.be.state_upload(slot, st.q, st.p, st.f)
@@ -362,35 +376,41 @@ class _DeviceSystem(_FastSystem):
 
     def leapfrog(self, st, step, center=True):
         calc = self.calc
+        if self._ahead and not (self._ahead_prev is st and self._ahead_step == step and center):
+            self._drop_ahead()  # another trajectory: what was enqueued ahead is void
+        res = None
         if self._ahead:
-            prev, stp, new = self._ahead[0]
-            if prev is st and stp == step and center:
-                self._ahead.popleft()
-                self._expected -= 1
-                self.evals += 1
-                return new
-            self._ahead.clear()  # another trajectory: what was computed ahead is void
-        n = max(1, min(self.CHAIN, self._expected)) if center else 1
-        dsts = [self.pool.take() for _ in range(n)]
-        try:
-            res = self.be.leapfrog_chain(st.slot, dsts, step, center, calc.target_data,
-                                         calc.potential_name, calc.rw_to_eV)
-        except Exception:
-            for d in dsts:
-                self.pool.give(d)
-            raise
-        states = [_DevState(q, p, float(e) + float(es), None, float(ke), d, self.pool)
-                  for (e, _, es, ke, q, p), d in zip(res, dsts)]
-        prev = states[0]
-        for nxt in states[1:]:
-            self._ahead.append((prev, step, nxt))
-            prev = nxt
+            try:
+                res = self.be.leapfrog_chain_next(self._ahead_id)
+            except _lib.ChainDropped:  # another call on the backend came in between
+                self._drop_ahead()
+        if res is None:
+            n = max(1, min(self.CHAIN, self._expected)) if center else 1
+            dsts = [self.pool.take() for _ in range(n)]
+            try:
+                self._ahead_id = self.be.leapfrog_chain_begin(
+                    st.slot, dsts, step, center, calc.target_data, calc.potential_name,
+                    calc.rw_to_eV)
+                self._ahead.extend(dsts)
+                self._ahead_step = step
+                res = self.be.leapfrog_chain_next(self._ahead_id)
+            except Exception:
+                if not self._ahead:
+                    for d in dsts:
+                        self.pool.give(d)
+                self._drop_ahead()
+                raise
+        e, _, es, ke, q, p = res
+        new = _DevState(q, p, float(e) + float(es), None, float(ke), self._ahead.popleft(),
+                        self.pool)
+        self._ahead_prev = new if self._ahead else None
         self._expected -= 1
         self.evals += 1
-        return states[0]
+        return new
 
     def to_atoms(self, st):
         if st.f is None:
+            self._drop_ahead()  # (the download is another call on the handle)
             st.f = self.be.state_download(st.slot, want=('f',))['f']
         return _FastSystem.to_atoms(self, st)
 

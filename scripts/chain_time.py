@@ -16,17 +16,22 @@ slots = [dev.pool.take() for _ in range(17)]
 tgt = calc.target_data
 for n in (1, 2, 4, 8, 16):
     for _ in range(6):
-        be.leapfrog_chain(slots[0], slots[1:1 + n], 1e-3, True, tgt, 'rw', 100.)
+        be.leapfrog_chain(st.slot, slots[1:1 + n], 1e-3, True, tgt, 'rw', 100.)
     t = time.perf_counter(); reps = 100
     for _ in range(reps):
-        be.leapfrog_chain(slots[0], slots[1:1 + n], 1e-3, True, tgt, 'rw', 100.)
+        be.leapfrog_chain(st.slot, slots[1:1 + n], 1e-3, True, tgt, 'rw', 100.)
     dt = (time.perf_counter() - t) / reps
     print('chain of %2d: %.1f us per call, %.1f us per step' % (n, dt * 1e6, dt * 1e6 / n))
 # through the system with look-ahead
 for exp in (1, 8, 64):
     s0 = st
+    for rep in range(4):  # graph capture of this chain length
+        dev.expect(exp)
+        s = s0
+        for k in range(exp):
+            s = dev.leapfrog(s, 1e-3)
     t = time.perf_counter(); cnt = 0
-    for rep in range(20):
+    for rep in range(40):
         dev.expect(exp)
         s = s0
         for k in range(exp):

@@ -688,26 +688,35 @@ def test_fused_launch_equals_the_launch_sequence(potential):
     """Small structures evaluate in ONE cooperative launch with the potential in
     Q space (gc.go = F.(T^T go), gc.gc = F.(T^T T F)); it must give what the
     sequence of launches (G(r) in r space, potential_kernel, force pass with
-    atomics) gives, deterministic sums or not, with and without a fused spring."""
+    atomics) gives, with and without a fused spring; its fixed-point sums make
+    repeated evaluations bit-identical."""
     atoms, scat = make_hmc_atoms(5)
     be = scat.pdf_backend
     pos, target = atoms.get_positions(), atoms.calc.target_data
     for springs in ([], [('rep', 10., 2.95)]):
         be.set_restraints(springs)
         res = {}
-        for fused, det in ((0, 1), (1, 0), (1, 1)):
+        for fused, table in ((0, 0), (1, 0), (1, 1)):
             be.set_option('fused', fused)
-            be.set_option('fused_det', det)
+            be.set_option('fused_table', table)
+            outs = []
             for _ in range(4):  # eager, eager, capture, replay
                 out = be.energy_forces(pos, target, potential, 100.)
-            res[fused, det] = (out[0], out[1], out[2], be.restraint_energy)
+                outs.append((out[0], out[1], np.array(out[2]), be.restraint_energy))
+            res[fused, table] = outs[-1]
+            if fused and not springs:
+                for o in outs[:-1]:
+                    assert o[0] == outs[-1][0] and o[1] == outs[-1][1]
+                    assert np.array_equal(o[2], outs[-1][2])
         be.set_option('fused', 1)
-        be.set_option('fused_det', 1)
-        e0, s0, f0, r0 = res[0, 1]
+        be.set_option('fused_table', 1)
+        e0, s0, f0, r0 = res[0, 0]
         for key in ((1, 0), (1, 1)):
             e, sc, f, r = res[key]
             assert abs(e - e0) < 1e-9 * abs(e0) and abs(sc - s0) < 1e-9 * abs(s0)
-            assert nerr(f, f0) < 2e-6 and abs(r - r0) <= 1e-12 * max(1., abs(r0))
+            assert nerr(f, f0) < 2e-6 and abs(r - r0) <= 1e-12 * max(1., abs(r0)), (key, nerr(f, f0))
+        print('fused forces vs launch sequence:', potential, springs,
+              nerr(res[1, 0][2], f0), nerr(res[1, 1][2], f0))
     be.set_restraints([])
 
 
@@ -974,6 +983,25 @@ def test_chained_leapfrogs_equal_single_steps_bit_for_bit():
     a = dev.leapfrog(start, 0.03)
     b = dev.leapfrog(start, -0.03)
     assert np.array_equal(a.q, ref[0].q) and not np.array_equal(b.q, ref[0].q)
+    # the two halves of the native call: steps are handed out as they complete;
+    # another call on the handle waits for the chain and drops the rest
+    from pyiid_b200 import _lib
+    cid = be.leapfrog_chain_begin(start.slot, [30, 31, 32, 33], 0.03, True, *args)
+    one = be.leapfrog_chain_next(cid)
+    two = be.leapfrog_chain_next(cid)
+    assert np.array_equal(one[4], ref[0].q) and np.array_equal(two[4], ref[1].q)
+    assert np.array_equal(two[5], ref[1].p) and float(two[0]) == ref[1].pe
+    got = be.state_download(33)  # (the chain ran to its end before this call)
+    assert np.array_equal(got['q'], ref[3].q) and np.array_equal(got['p'], ref[3].p)
+    with pytest.raises(_lib.ChainDropped):
+        be.leapfrog_chain_next(cid)
+    # the sampler's system recovers from a chain dropped behind its back
+    dev.expect(5)
+    st = dev.leapfrog(start, 0.03)
+    be.state_download(st.slot, want=('f',))
+    for k in range(1, 5):
+        st = dev.leapfrog(st, 0.03)
+        assert np.array_equal(st.q, ref[k].q) and np.array_equal(st.p, ref[k].p)
 
 
 def test_device_state_nuts_equals_array_level_nuts():
@@ -1173,6 +1201,10 @@ def test_qspace_chain_rule_weights_equal_rspace(potential, precision):
     be.set_transform(sc.exp['rstep'], sc.pdf_qbin, sc.get_r(), 0.0)
     pos = g['positions'] * 1.02
     targets = [g['target_pdf_f32'], 0.5 * g['target_pdf_f32'][::-1].copy()]
+    # like with like: both sides take the direct float32 force pass (the fused
+    # launch's float64 radial table differs from it by the direct pass's own
+    # rounding, checked below)
+    be.set_option('fused_table', 0)
     for tg in targets:
         res = {}
         for q in (1, 0):
@@ -1183,3 +1215,9 @@ def test_qspace_chain_rule_weights_equal_rspace(potential, precision):
         (e1, s1, f1, _), (e0, s0, f0, _) = res[1], res[0]
         assert abs(e1 - e0) <= 1e-12 * abs(e0) and abs(s1 - s0) <= 1e-12 * abs(s0)
         assert nerr(f1, f0) < (1e-9 if precision == 'fp64' else 2e-6)
+        if precision == 'fp32':
+            be.set_option('fused_table', 1)
+            e2, s2, f2, _ = be.energy_forces(pos, tg, potential, 10.)
+            be.set_option('fused_table', 0)
+            assert e2 == e1 and s2 == s1 and nerr(f2, f1) < TOL32
+    be.set_option('fused_table', 1)
