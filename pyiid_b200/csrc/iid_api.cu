@@ -440,8 +440,8 @@ static int pick_small_slab(const std::vector<int> &run_begin, const std::vector<
 {
     constexpr int GRAN = 8, FIXED = 12;
     const int ntile = np / TILE_I;
-    int best = TILE_I;
-    long best_cost = -1;
+    int best = TILE_I, best1 = TILE_I;
+    long best_cost = -1, best1_cost = -1;
     std::vector<int> lens;
     std::vector<long> load;
     for (int cap = GRAN; cap <= 512; cap += GRAN) {
@@ -470,7 +470,17 @@ static int pick_small_slab(const std::vector<int> &run_begin, const std::vector<
             best_cost = cost;
             best = cap;
         }
+        // one item per SM lets the whole evaluation run as ONE cooperative launch
+        // (iid_fused.cuh), which is worth more than a tighter makespan of the
+        // pair passes alone: remember the best single-wave list as well
+        if ((int)lens.size() <= slots && (best1_cost < 0 || cost < best1_cost)) {
+            best1_cost = cost;
+            best1 = cap;
+        }
     }
+    // (cost is in j atoms per SM, ~0.25 us each over the two pair passes; the
+    // single launch saves ~35 us of launch gaps and one-block stages)
+    if (best1_cost > 0 && best1_cost - best_cost < 140) return best1;
     return best;
 }
 
@@ -1830,8 +1840,11 @@ static size_t fused_smem_bytes(const iid_handle *h, int *ps_off, int *pl)
 static bool fused_applicable(const iid_handle *h, bool want_forces, bool want_pdf)
 {
     const bool table = h->use_force_table && h->ntypes <= 4 && h->n >= h->force_table_min_n;
+    // (with its own in-launch radial table the fused kernel also covers the sizes
+    // where the launch sequence would switch to the tabulated force pass)
+    const bool own_table = h->fused_table && h->ntypes <= 2;
     return h->use_fused && h->precision == IID_FP32 && h->cheb && h->world == 1 &&
-           want_forces && !want_pdf && h->qspace_wq && !table && !h->timing &&
+           want_forces && !want_pdf && h->qspace_wq && (!table || own_table) && !h->timing &&
            h->n_items_tri <= h->sm_count && (h->nq + C32 - 1) / C32 <= 12 &&
            h->np <= (int64_t)h->sm_count * 384 &&
            fused_smem_bytes(h, nullptr, nullptr) <= 220 * 1024;
