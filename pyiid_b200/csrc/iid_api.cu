@@ -1908,7 +1908,7 @@ static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
     q.phi_cap = PHI_CAP_FUSED;
     q.phi_stride = PHI_CAP_FUSED + 2 * FT_PAD;
     q.ntypes = (int)h->ntypes;
-    q.tab_h = 0.125 / (h->qbin * (double)h->nq);
+    q.tab_h = FT_QH / (h->qbin * (double)h->nq);
     q.ext_ref = h->ext_ref;
     q.n_items = (int)h->n_items_tri;
     q.lf = lf ? 1 : 0;

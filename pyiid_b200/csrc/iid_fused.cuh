@@ -55,7 +55,7 @@ struct FusedParams {
     double *phi_tab;          // [chain step][ntypes^2][phi_stride] float64
     int phi_stride, phi_cap;  // doubles per type pair; entries r = 0 .. (cap-1) h
     int ntypes;
-    double tab_h;             // grid step: (Q_max h) = 1/8
+    double tab_h;             // grid step: FT_QH / Q_max
     double *ext_ref;          // [4] box centre of the previous evaluation + valid flag
     // staging
     int lf;  // 1 = leapfrog staging from the state slab, 0 = positions in `pos`
@@ -119,14 +119,18 @@ __device__ __forceinline__ double block_sum(double v, double *sm)
 // For fixed weights the Q sum of a pair's force depends on the pair only through
 // r and the two element types (iid_force_table.cuh):
 //   Phi_ab(r) = sum_m w_ab[m] (Q_m r cos(Q_m r) - sin(Q_m r)) / r^3.
-// The fused kernel tabulates it in FLOAT64 on a uniform grid with Q_max h = 1/8
+// The fused kernel tabulates it in FLOAT64 on a uniform grid with Q_max h = 1/3
 // (FT_G lanes per entry, three-term recurrences from exact seeds), barrier, then
-// takes one 8-point Lagrange interpolation per pair: error 1.1e-3 (Q_max h)^8 =
-// 6e-11 |Phi|, so the forces carry the float32 rounding of the positions and
-// nothing else.  At Au561 that is 8 000 entries x 330 bins (2.6 M terms)
-// instead of 157 000 pairs x 330 bins.
-constexpr int FT_PAD = 4;  // entries stored before r = 0 (nodes k-3 .. k+4)
-constexpr int FT_G = 8;    // lanes per table entry
+// takes one 12-point Lagrange interpolation per pair: error 2.2e-4 (Q_max h)^12
+// = 4e-10 |Phi|, so the forces carry the float32 rounding of the positions and
+// nothing else.  At Au561 that is 2 200 entries x 330 bins (0.7 M terms)
+// instead of 157 000 pairs x 330 bins; a coarse grid with a long stencil keeps
+// the build short when a hot trajectory has spread the structure out.
+constexpr int FT_PTS = 12;            // interpolation points
+constexpr int FT_LEFT = FT_PTS / 2 - 1;  // nodes k - FT_LEFT .. k + FT_PTS - 1 - FT_LEFT
+constexpr int FT_PAD = FT_PTS / 2;    // entries stored before r = 0
+constexpr int FT_G = 8;               // lanes per table entry
+constexpr double FT_QH = 1.0 / 3.0;   // Q_max h
 
 __device__ __forceinline__ void fused_table_build(double *tab, int stride, int ntp, int K,
                                                   double h, const double *wab, int nq, int qp,
@@ -201,26 +205,33 @@ __device__ double fused_phi_direct(double r, const double *w, int nq, double qbi
     return phi / (r * r * r);
 }
 
-// 8-point Lagrange interpolation on the uniform grid: nodes k-3 .. k+4 at
-// t[-3] .. t[4], u in [0, 1) measured from node k.
-__device__ __forceinline__ double lagrange8(const double *t, double u)
+// FT_PTS-point Lagrange interpolation on the uniform grid: nodes k - FT_LEFT ..
+// k + FT_PTS - 1 - FT_LEFT at t[-FT_LEFT] .., u in [0, 1) measured from node k.
+// Error of 12 points: max |prod (u - j)| / 12! = 2.2e-4 times (Q_max h)^12.
+__host__ __device__ constexpr double ft_bary(int i)
 {
-    double v[8], d[8], pre[8], L = 0.0;
+    // barycentric weight of node i of FT_PTS equispaced nodes: (-1)^(n-i) C(n, i) / n!
+    double c = 1.0, f = 1.0;
+    for (int k = 1; k <= FT_PTS - 1; ++k) f *= (double)k;
+    for (int k = 0; k < i; ++k) c = c * (double)(FT_PTS - 1 - k) / (double)(k + 1);
+    return (((FT_PTS - 1 - i) & 1) ? -c : c) / f;
+}
+
+__device__ __forceinline__ double lagrange_pts(const double *t, double u)
+{
+    double v[FT_PTS], d[FT_PTS], pre[FT_PTS], L = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        v[i] = t[i - 3];  // (L1: neighbouring pairs share these lines; see phi_tab)
-        d[i] = u - (double)(i - 3);
+    for (int i = 0; i < FT_PTS; ++i) {
+        v[i] = t[i - FT_LEFT];  // (L1: neighbouring pairs share these lines; see phi_tab)
+        d[i] = u - (double)(i - FT_LEFT);
     }
     pre[0] = 1.0;
 #pragma unroll
-    for (int i = 1; i < 8; ++i) pre[i] = pre[i - 1] * d[i - 1];
-    // barycentric weights of 8 equispaced nodes: (-1)^(7-i) C(7, i) / 7!
-    const double bw[8] = {-1.0 / 5040.0, 7.0 / 5040.0, -21.0 / 5040.0, 35.0 / 5040.0,
-                          -35.0 / 5040.0, 21.0 / 5040.0, -7.0 / 5040.0, 1.0 / 5040.0};
+    for (int i = 1; i < FT_PTS; ++i) pre[i] = pre[i - 1] * d[i - 1];
     double suf = 1.0;
 #pragma unroll
-    for (int i = 7; i >= 0; --i) {
-        L = fma(v[i] * bw[i], pre[i] * suf, L);
+    for (int i = FT_PTS - 1; i >= 0; --i) {
+        L = fma(v[i] * ft_bary(i), pre[i] * suf, L);
         suf *= d[i];
     }
     return L;
@@ -238,7 +249,7 @@ __device__ __forceinline__ void fused_table_forces(const FusedParams &q, const W
     const int len = wi.jend - wi.jbegin;
     const double xi = ps[lane], yi = ps[pl + lane], zi = ps[2 * pl + lane];
     const bool vi = ps[3 * pl + lane] != 0.0;
-    const double klast = (double)(K - 5);  // nodes k-3 .. k+4 all tabulated
+    const double klast = (double)(K - FT_PTS);  // every node of the stencil is tabulated
     double fx = 0.0, fy = 0.0, fz = 0.0;
     for (int jj = warp; jj < len; jj += nw) {
         const int sj = TILE_I + jj;
@@ -252,7 +263,7 @@ __device__ __forceinline__ void fused_table_forces(const FusedParams &q, const W
             const double r = r2 * y, tpos = r * inv_h;
             if (tpos < klast) {
                 const int k = (int)tpos;
-                phi = lagrange8(tab + k, tpos - (double)k);
+                phi = lagrange_pts(tab + k, tpos - (double)k);
             } else {
                 phi = fused_phi_direct(r, w, q.fq.nq, q.fq.qbin);
             }
@@ -572,7 +583,7 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
         }
         __syncthreads();
         const double h = q.tab_h;
-        const int K = (int)fmin((double)q.phi_cap, ceil(2.0000002 * ext[6] / h) + 8.0);
+        const int K = (int)fmin((double)q.phi_cap, ceil(2.0000002 * ext[6] / h) + (double)(FT_PTS + 2));
         if (q.stamps && blockIdx.x == 0 && threadIdx.x == 0) {  // developer timing
             q.ext_ref[4] = ext[6];
             q.ext_ref[5] = (double)K;
@@ -613,31 +624,37 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
             q.fo.Ffix[e] = 0ull;  // clear for the next pass
             q.fo.force[e] = f;
             if (q.force_out) q.force_out[e] = f;
-            if (finish) lf_kick(ctl, q.slab, q.n, q.pos, mirror, lf_shift, e, e % 3, f);
-        }
-        if (q.force_out && gtid < 5) q.out_host[gtid] = __ldcg(q.out4 + gtid);
-    }
-    if (finish) {
-        // scalars of the step: energy, scale, value, scale_true, restraint energy,
-        // (kinetic energy: summed by the host from the mirrored momenta), shift
-        double *out = mirror + 6 * (size_t)q.n;
-        if (blockIdx.x == 0 && threadIdx.x < 9) {
-            const int k = threadIdx.x;
-            out[k] = k < 5 ? __ldcg(q.out4 + k) : (k == 5 ? 0.0 : lf_shift[k - 6]);
-        }
-        // the next step's staging reads the state written here
-        fused_stamp(q, 10, cs == scs);
-        if (cs + 1 < q.n_chain) {
-            grid.sync();
-            // every block's share of the mirror is written: tell the host that step
-            // cs is complete (iid_leapfrog_chain_next polls this word; the last
-            // step's completion is the end of the launch)
-            if (blockIdx.x == 0 && threadIdx.x == 0) {
-                __threadfence_system();
-                *reinterpret_cast<volatile double *>(out + 15) = ctl[7];
+            if (finish) {
+                double mx, mp;
+                lf_kick(ctl, q.slab, q.n, q.pos, lf_shift, e, e % 3, f, mx, mp);
+                mirror[e] = mx;
+                mirror[3 * (size_t)q.n + e] = mp;
             }
         }
-        fused_stamp(q, 11, cs == scs);
+        if (q.force_out && gtid < 5) q.out_host[gtid] = __ldcg(q.out4 + gtid);
+        if (finish) {
+            // scalars of the step: energy, scale, value, scale_true, restraint energy,
+            // (kinetic energy: summed by the host from the mirrored momenta), shift
+            double *out = mirror + 6 * (size_t)q.n;
+            if (blockIdx.x == 0 && threadIdx.x < 9) {
+                const int k = threadIdx.x;
+                out[k] = k < 5 ? __ldcg(q.out4 + k) : (k == 5 ? 0.0 : lf_shift[k - 6]);
+            }
+            fused_stamp(q, 10, cs == scs);
+            if (cs + 1 < q.n_chain) {
+                grid.sync();  // the next step's staging reads the new state
+                // Every block's share of the mirror was written before the barrier:
+                // tell the host that step cs is complete (iid_leapfrog_chain_next
+                // polls this word; the last step's completion is the end of the
+                // launch).  The system-wide fence costs its thread ~1 us: the LAST
+                // block raises the flag, whose work item is the shortest (or none).
+                if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+                    __threadfence_system();
+                    *reinterpret_cast<volatile double *>(out + 15) = ctl[7];
+                }
+            }
+            fused_stamp(q, 11, cs == scs);
+        }
     }
   }
   // (cref was last written by thread 0, barriers ago)

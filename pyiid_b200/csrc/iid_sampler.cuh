@@ -188,9 +188,11 @@ __device__ __forceinline__ double lf_shift_of(const double *ctl, const double *e
     return ctl[3] != 0.0 ? __dsub_rn(ctl[4 + w], __dmul_rn(0.5, __dadd_rn(ext[w], ext[3 + w]))) : 0.0;
 }
 
+// Second half kick and centring of element e into the destination state; the
+// new coordinate and momentum are returned for the host mirror.
 __device__ __forceinline__ void lf_kick(const double *ctl, double *slab, int n, const double *pos,
-                                        double *mirror, const double *shift, size_t e, int w,
-                                        double f)
+                                        const double *shift, size_t e, int w, double f, double &x,
+                                        double &pn)
 {
     const double step = ctl[0];
     const int dst = (int)ctl[2];
@@ -198,13 +200,11 @@ __device__ __forceinline__ void lf_kick(const double *ctl, double *slab, int n, 
     double *qd = lf_slot(slab, n, dst, 0), *pd = lf_slot(slab, n, dst, 1),
            *fd = lf_slot(slab, n, dst, 2);
     const double ph = __ldcg(pd + e), x0 = __ldcg(pos + e);
-    const double pn = __dadd_rn(ph, __dmul_rn(__dmul_rn(0.5, step), f));
-    const double x = centre ? __dadd_rn(x0, shift[w]) : x0;
+    pn = __dadd_rn(ph, __dmul_rn(__dmul_rn(0.5, step), f));
+    x = centre ? __dadd_rn(x0, shift[w]) : x0;
     pd[e] = pn;
     fd[e] = f;
     qd[e] = x;
-    mirror[e] = x;
-    mirror[3 * (size_t)n + e] = pn;
 }
 
 __global__ void __launch_bounds__(1024) lf_finish_kernel(const double *__restrict__ ctl,
