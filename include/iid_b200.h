@@ -335,9 +335,11 @@ int iid_download_host(iid_handle *h, const void *dev, void *host, int64_t bytes)
  * arrays), "acc_j" (FP32 full gradient: j atoms per float32 partial sum before
  * it is parked and re-started, 0 = one accumulator over the whole row),
  * "fused" (0/1: small structures evaluate in ONE cooperative launch),
- * "fused_det" (0/1: that launch adds its per-item partial sums in a fixed
- * order -- bit-reproducible energies, forces and sampler trajectories --
- * instead of atomics), "det_fq" (0/1: the stand-alone F(Q) pass stores per-item
+ * "fused_table" (0/1: that launch takes its force pass from a float64 radial
+ * table it builds itself, up to two element types; 0 = direct pass over the
+ * Q bins), "chain_in_kernel" (0/1: a leapfrog chain is ONE launch; 0 = one
+ * launch per step behind one synchronisation), "fused_det" (accepted, no
+ * effect: the launch's fixed-point sums are always bit-reproducible), "det_fq" (0/1: the stand-alone F(Q) pass stores per-item
  * partial sums and adds them in item order -- F(Q), G(r), Rw reproducible).  Defaults can also be set with IID_* environment variables
  * before iid_create. */
 int iid_set_option(iid_handle *h, const char *key, int64_t value);
