@@ -720,6 +720,69 @@ def test_fused_launch_equals_the_launch_sequence(potential):
     be.set_restraints([])
 
 
+def _fused_backend(atoms, ideal, precision='fp32'):
+    scat = ElasticScatter(precision=precision)
+    target = scat.get_pdf(ideal)
+    scat._ensure_wrapped(atoms)
+    be = scat._load(atoms, scat.pdf_qbin, 'PDF')
+    be.set_transform(scat.exp['rstep'], scat.pdf_qbin, scat.get_r(), scat.exp['qmin'])
+    return be, target
+
+
+def test_fused_force_table_two_elements_and_far_pairs():
+    """The radial force table of the fused launch: (1) a two-element structure
+    (one table per ordered element pair) against the FP64 handle and the direct
+    pass; (2) a structure stretched beyond the table's last entry -- two
+    clusters 400 A apart -- whose far pairs are summed directly over the Q
+    bins; (3) three element types keep the direct pass."""
+    atoms = structures.alloy_sphere(300, seed=3)
+    ideal = atoms.copy()
+    atoms.positions = atoms.positions * 1.03 + np.random.RandomState(1).normal(0, 0.03, (300, 3))
+    pos = atoms.get_positions()
+    be64, target = _fused_backend(atoms, ideal, 'fp64')
+    e64, s64, f64 = be64.energy_forces(pos, target, 'rw', 1.)[:3]
+    be, target = _fused_backend(atoms, ideal)
+    res = {}
+    for table in (0, 1):
+        be.set_option('fused_table', table)
+        be.energy_forces(pos, target, 'rw', 1.)  # (first call: the target's one-time kernels)
+        n0 = be.launch_count()
+        res[table] = be.energy_forces(pos, target, 'rw', 1.)[:3]
+        assert be.launch_count() - n0 == 1  # the fused launch either way
+        assert abs(res[table][0] - e64) < 1e-6 * abs(e64)
+        assert nerr(res[table][2], f64) < TOL32
+    assert res[0][0] == res[1][0] and nerr(res[1][2], res[0][2]) < 2e-6
+    # far pairs
+    far = structures.icosahedron('Au', 2)
+    far.positions[30:] += [400., 0., 0.]
+    ideal = structures.icosahedron('Au', 2)
+    be, target = _fused_backend(far, ideal)
+    pos = far.get_positions()
+    out = {}
+    for table in (0, 1):
+        be.set_option('fused_table', table)
+        out[table] = be.energy_forces(pos, target, 'rw', 1.)[:3]
+        again = be.energy_forces(pos, target, 'rw', 1.)[:3]
+        assert np.array_equal(np.asarray(again[2]), np.asarray(out[table][2]))
+    assert out[0][0] == out[1][0] and nerr(out[1][2], out[0][2]) < 2e-6
+    be.set_option('fused_table', 1)
+    # three element types: direct pass inside the fused launch
+    base = structures.alloy_sphere(120, seed=5)
+    numbers = np.array(base.get_atomic_numbers())
+    numbers[::3] = 47
+    tri = ase_shim.Atoms(numbers=numbers, positions=base.get_positions())
+    ideal = tri.copy()
+    tri.positions *= 1.02
+    pos = tri.get_positions()
+    be64, target = _fused_backend(tri, ideal, 'fp64')
+    f64 = be64.energy_forces(pos, target, 'rw', 1.)[2]
+    be, target = _fused_backend(tri, ideal)
+    be.energy_forces(pos, target, 'rw', 1.)
+    n0 = be.launch_count()
+    f32 = be.energy_forces(pos, target, 'rw', 1.)[2]
+    assert be.launch_count() - n0 == 1 and nerr(f32, f64) < TOL32
+
+
 def test_sq_iq_follow_the_reference_formulas():
     """get_sq = F/Q + 1 (inf -> 0), get_iq = S * <f>^2 (__init__.py:393-446)."""
     atoms = structures.alloy_sphere(40, seed=9)
