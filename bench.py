@@ -315,6 +315,29 @@ def hmc_extra():
                        'NUTS(T=1000, escape_level=8, seed=0)',
            'energy_force_evals_per_s': evals_per_s,
            'pairq_per_eval': 561 * 560 // 2 * 330}
+    # native leapfrog on device-resident states: one call per step, and a chain of
+    # 16 steps inside one cooperative launch (what a NUTS subtree asks for)
+    a0 = atoms.copy()
+    a0.set_calculator(calc)
+    a0.set_momenta(np.random.RandomState(0).normal(0, 1, (len(a0), 3)))
+    a0.get_forces()
+    dsys = sim._DeviceSystem(a0)
+    st0 = dsys.state_of(a0)
+    slots = [dsys.pool.take() for _ in range(16)]
+    for n_chain, key in ((1, 'leapfrog_native_us_single_step'),
+                         (16, 'leapfrog_native_us_per_step_chain_of_16')):
+        for _ in range(6):
+            be.leapfrog_chain(st0.slot, slots[:n_chain], 1e-3, True, target, 'rw', 100.)
+        n0, t = be.launch_count(), time.perf_counter()
+        reps = 100
+        for _ in range(reps):
+            be.leapfrog_chain(st0.slot, slots[:n_chain], 1e-3, True, target, 'rw', 100.)
+        out[key] = (time.perf_counter() - t) / reps / n_chain * 1e6
+        out['launches_per_' + ('step' if n_chain == 1 else 'chain_of_16')] = \
+            (be.launch_count() - n0) / reps
+    for s_ in slots:
+        dsys.pool.give(s_)
+    del st0, dsys
     # default: tree states resident on the device (one native call per leapfrog);
     # then the array-level host path and the Atoms-level (reference-style) path
     for fast, dev, tag in ((True, True, ''), (True, False, '_array_level_path'),

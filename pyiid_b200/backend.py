@@ -185,6 +185,7 @@ class Backend(object):
         self._last_target = None
         self._target_key = None
         self._restraints = []
+        self._chain = None
         self.restraint_energy = 0.0
         self.n = self.nq = self.nr = 0
         self.rank, self.world = 0, 1
@@ -584,18 +585,32 @@ class Backend(object):
             self.h, int(src), d.ctypes.data, len(d), float(step), int(bool(center)), tptr,
             POTENTIALS[potential], float(conv), ctypes.byref(cid)))
         self._target_done(target, tkey)
+        # result rows of the whole chain in three allocations (this runs once per
+        # leapfrog of a sampler: per-step allocations and pointer look-ups count)
+        m = len(d)
+        out = np.empty((m, 9), np.float64)
+        q = np.empty((m, self.n, 3), np.float64)
+        p = np.empty((m, self.n, 3), np.float64)
+        self._chain = [cid.value, 0, out, q, p, out.ctypes.data, q.ctypes.data, p.ctypes.data,
+                       self.n * 24]
         return cid.value
 
     def leapfrog_chain_next(self, chain_id):
         """The next completed step of chain ``chain_id``: (energy, scale,
         restraint energy, kinetic energy, q, p); raises
         :class:`_lib.ChainDropped` when another call dropped the chain."""
-        out = np.empty(9, np.float64)
-        q = np.empty((self.n, 3), np.float64)
-        p = np.empty((self.n, 3), np.float64)
-        check(self.lib.iid_leapfrog_chain_next(self.h, int(chain_id), out.ctypes.data,
-                                               q.ctypes.data, p.ctypes.data))
-        return out[0], out[1], out[4], out[5], q, p
+        c = self._chain
+        if c is None or c[0] != chain_id:
+            raise _lib.ChainDropped('this leapfrog chain is not in flight (any more)')
+        i = c[1]
+        rc = self.lib.iid_leapfrog_chain_next(self.h, chain_id, c[5] + 72 * i, c[6] + c[8] * i,
+                                              c[7] + c[8] * i)
+        if rc:
+            self._chain = None
+            check(rc)
+        c[1] = i + 1
+        o = c[2][i]
+        return o[0], o[1], o[4], o[5], c[3][i], c[4][i]
 
     # -- spring restraints (calc/spring_calc.py) -------------------------------
     def set_restraints(self, springs):

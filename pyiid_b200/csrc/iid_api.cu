@@ -200,7 +200,7 @@ struct iid_handle {
     bool chain_synced = false;  // (otherwise) the stream was synchronised for this chain
     double lf_seq = 0.0;        // flag value of the last step handed out
     int64_t chain_id = 0;       // the chain begun last
-    std::vector<double> lf_mass_h;  // kinetic energy of a step finished inside the fused launch
+    std::vector<double> lf_mass_h;  // 1/m: kinetic energy of a step finished inside the fused launch
     bool chain_in_kernel = true;
     bool use_graph = true;
     // device-resident sampler states (iid_leapfrog_host): slot = (q, p, f)
@@ -2221,7 +2221,8 @@ extern "C" int iid_sampler_setup(iid_handle *h, int64_t n_slots, const double *m
     for (GraphSlot &g : h->lf) g.drop();
     for (GraphSlot &g : h->lf_chain) g.drop();
     static_assert(LF_CHAIN_MAX == IID_LF_CHAIN, "ring of the pinned staging");
-    h->lf_mass_h.assign(masses_host, masses_host + h->n);
+    h->lf_mass_h.resize(h->n);
+    for (int64_t i = 0; i < h->n; ++i) h->lf_mass_h[i] = 1.0 / masses_host[i];
     const size_t n3 = (size_t)3 * h->n;
     int rc;
     if (h->lf_slab) { cudaFree(h->lf_slab); h->lf_slab = nullptr; }
@@ -2362,11 +2363,13 @@ static void leapfrog_collect(iid_handle *h, int ring, double *out_host, double *
     if (h->zero_copy_small && !h->n_restraints && fused_applicable(h, true, false)) {
         // the fused launch finishes the step spread over its grid and leaves the
         // kinetic energy sum p.p/m / 2 to the host (fixed order: reproducible)
-        const double *p = mir + n3, *m = h->lf_mass_h.data();
-        double ke[3] = {0.0, 0.0, 0.0};
-        for (int64_t a = 0; a < h->n; ++a)
-            for (int w = 0; w < 3; ++w) ke[w] = fma(p[3 * a + w], p[3 * a + w] / m[a], ke[w]);
-        out_host[5] = 0.5 * ((ke[0] + ke[1]) + ke[2]);
+        const double *p = mir + n3, *im = h->lf_mass_h.data();  // (inverse masses)
+        double ke[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int64_t a = 0; a < h->n; ++a) {
+            const double px = p[3 * a], py = p[3 * a + 1], pz = p[3 * a + 2];
+            ke[a & 3] = fma(fma(px, px, fma(py, py, pz * pz)), im[a], ke[a & 3]);
+        }
+        out_host[5] = 0.5 * ((ke[0] + ke[1]) + (ke[2] + ke[3]));
     }
     if (q_host) memcpy(q_host, mir, n3 * sizeof(double));
     if (p_host) memcpy(p_host, mir + n3, n3 * sizeof(double));
