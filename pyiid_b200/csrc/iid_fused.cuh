@@ -471,12 +471,6 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
     if (want_ext && threadIdx.x == 0) {
         const double ex = ext[3] - ext[0], ey = ext[4] - ext[1], ez = ext[5] - ext[2];
         const double half_diag = 0.5 * sqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
-#ifdef IID_DEBUG_EXT
-        if (blockIdx.x == 0)
-            printf("cs %d ext lo %.3f %.3f %.3f hi %.3f %.3f %.3f d2 %.3f half_diag %.3f cref %.3f %.3f %.3f %.1f\n",
-                   cs, ext[0], ext[1], ext[2], ext[3], ext[4], ext[5], ext[6], half_diag, cref[0],
-                   cref[1], cref[2], cref[3]);
-#endif
         ext[6] = cref[3] != 0.0 ? fmin(half_diag, sqrt(ext[6])) : half_diag;
         cref[0] = 0.5 * (ext[0] + ext[3]);
         cref[1] = 0.5 * (ext[1] + ext[4]);

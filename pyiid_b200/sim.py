@@ -65,9 +65,18 @@ def classical_dynamics(atoms, stepsize, n_steps):
     if _DeviceSystem.usable(atoms):
         system = _DeviceSystem(atoms)
         st = system.state_of(atoms)
-        for _ in range(n_steps):
-            st = system.leapfrog(st, stepsize)
-            traj.append(system.to_atoms(st))
+        done = 0
+        while done < n_steps:
+            # a batch of steps as chains on the device, then their frames (the
+            # download of a frame's forces is another call on the handle)
+            batch = min(64, n_steps - done)
+            system.expect(batch)
+            states = []
+            for _ in range(batch):
+                st = system.leapfrog(st, stepsize)
+                states.append(st)
+            traj.extend(system.to_atoms(s) for s in states)
+            done += batch
         return traj
     for _ in range(n_steps):
         traj.append(leapfrog(traj[-1], stepsize))
