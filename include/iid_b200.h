@@ -300,7 +300,7 @@ int iid_leapfrog_host(iid_handle *h, int src, int dst, double step, int centre,
  * the fused evaluation walk the whole chain inside ONE cooperative launch.
  * out_host[n_steps][9], q_host / p_host [n_steps][n*3] (may be NULL) as
  * iid_leapfrog_host, one row per step. */
-#define IID_LF_CHAIN 16
+#define IID_LF_CHAIN 64
 int iid_leapfrog_chain_host(iid_handle *h, int src, const int *dst, int n_steps,
                             double step, int centre, const double *target_host,
                             int potential, double conv, double *out_host,

@@ -16,7 +16,7 @@ IID_FP32, IID_FP64 = 0, 1
 IID_POT_RW, IID_POT_CHI_SQ = 0, 1
 IID_SPRING_REP, IID_SPRING_COM, IID_SPRING_ATT = 0, 1, 2
 IID_MAX_RESTRAINTS = 4
-IID_LF_CHAIN = 16
+IID_LF_CHAIN = 64
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64

@@ -21,7 +21,7 @@
 namespace iid {
 
 constexpr int LF_CTL = 8;  // step, src, dst, centre flag, cell centre x y z, -
-constexpr int LF_CHAIN_MAX = 16;  // steps one fused launch can walk (= IID_LF_CHAIN)
+constexpr int LF_CHAIN_MAX = 64;  // steps one fused launch can walk (= IID_LF_CHAIN)
 
 __device__ __forceinline__ double *lf_slot(double *slab, int n, int slot, int which)
 {

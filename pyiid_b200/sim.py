@@ -348,7 +348,7 @@ class _DeviceSystem(_FastSystem):
         self._ahead_id = 0
         self._expected = 0
 
-    CHAIN = 16
+    CHAIN = 64
 
     def expect(self, n):
         """The next ``n`` leapfrog calls continue one trajectory."""

@@ -22,7 +22,7 @@ atoms.get_forces()
 dev = sim._DeviceSystem(atoms)
 st = dev.state_of(atoms)
 be = dev.be
-slots = [dev.pool.take() for _ in range(17)]
+slots = [dev.pool.take() for _ in range(65)]
 tgt = calc.target_data
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 acc = np.zeros(n + 1)

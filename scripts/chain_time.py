@@ -12,9 +12,9 @@ atoms.get_forces()
 dev = sim._DeviceSystem(atoms)
 st = dev.state_of(atoms)
 be = dev.be
-slots = [dev.pool.take() for _ in range(17)]
+slots = [dev.pool.take() for _ in range(65)]
 tgt = calc.target_data
-for n in (1, 2, 4, 8, 16):
+for n in (1, 2, 4, 8, 16, 64):
     for _ in range(6):
         be.leapfrog_chain(st.slot, slots[1:1 + n], 1e-3, True, tgt, 'rw', 100.)
     t = time.perf_counter(); reps = 100

@@ -23,6 +23,6 @@ dev = sim._DeviceSystem(atoms)
 st = dev.state_of(atoms)
 be = dev.be
 be.set_option("graph", int(os.environ.get("LF_GRAPH", "0")))
-slots = [dev.pool.take() for _ in range(17)]
+slots = [dev.pool.take() for _ in range(65)]
 for _ in range(int(os.environ.get("LF_REPS", "400"))):
     be.leapfrog_chain(st.slot, slots[1:1 + n], 1e-3, True, calc.target_data, 'rw', 100.)

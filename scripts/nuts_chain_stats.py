@@ -22,7 +22,7 @@ calc = Calc1D(target_data=target, exp_function=scat.get_pdf,
 atoms.set_calculator(calc)
 atoms.get_forces()
 
-for chain in (1, 4, 16):
+for chain in (1, 16, 64):
     sim._DeviceSystem.CHAIN = chain
     np.random.seed(0)
     a = atoms.copy()
