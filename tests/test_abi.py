@@ -82,6 +82,24 @@ def test_shard_plan_partitions_the_pair_list():
                     assert max(slots) <= 1.15 * (sum(slots) / world) + 32 * 4096
 
 
+def test_small_structures_get_a_single_wave_triangle_list():
+    """Structures of the sampler's size get a triangle list with at most one
+    item per SM (the whole evaluation then runs as one cooperative launch,
+    iid_fused.cuh) that still covers every tile pair once; larger ones keep the
+    list with the shortest makespan over several waves."""
+    lib = _lib.load()
+    for n, one_wave in ((55, True), (147, True), (309, True), (561, True), (700, True),
+                        (923, True), (1100, True), (1415, False), (3000, False)):
+        types = np.zeros(n, np.int32)
+        v = [ctypes.c_int64(0) for _ in range(4)]
+        assert lib.iid_plan_shard(n, types.ctypes.data, 1, 148, 1, 0, 1,
+                                  *[ctypes.byref(x) for x in v]) == 0
+        total, slots, npad = v[0].value, v[2].value, v[3].value
+        nt = npad // 32
+        assert slots == (nt * (nt - 1) // 2 + nt) * 1024
+        assert (total <= 148) == one_wave, (n, total)
+
+
 def test_shard_plan_property_random_structures():
     """Property form of the test above (hypothesis): any element mix, any
     world size -- the ranks' slices partition the work list, the triangle list
