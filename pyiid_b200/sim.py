@@ -244,6 +244,10 @@ class _FastSystem(object):
         """Hint: the next ``n`` leapfrog calls continue one trajectory (used
         by the device-resident system to compute several steps per call)."""
 
+    def close(self):
+        """End of the system's use (the device-resident system returns the
+        slots of steps it enqueued ahead)."""
+
     def kinetic(self, p):
         return 0.5 * float(np.vdot(p, p / self.masses))
 
@@ -361,6 +365,18 @@ class _DeviceSystem(_FastSystem):
         while self._ahead:
             self.pool.give(self._ahead.popleft())
         self._ahead_prev = None
+
+    def close(self):
+        """Return the slots of steps enqueued ahead but never asked for (a
+        subtree that stopped early at the end of an iteration)."""
+        self._expected = 0
+        self._drop_ahead()
+
+    def __del__(self):
+        try:
+            self._drop_ahead()
+        except Exception:  # interpreter shutdown: the pool may be gone already
+            pass
 
     @staticmethod
     def usable(atoms):
@@ -578,6 +594,7 @@ class NUTSCanonicalEnsemble(Ensemble):
                 if self.verbose:
                     print('\t \t \tjmax emergency escape at {}'.format(depth))
                 keep_going = 0
+        system.close()  # steps enqueued ahead of a subtree that stopped early
         w = 1. / (self.m + self.t0)
         self.sim_hbar = (1 - w) * self.sim_hbar + \
             w * (self.accept_target - acc_sum / leaves)

@@ -1067,6 +1067,22 @@ def test_chained_leapfrogs_equal_single_steps_bit_for_bit():
         assert np.array_equal(st.q, ref[k].q) and np.array_equal(st.p, ref[k].p)
 
 
+def test_nuts_returns_every_device_slot():
+    """Steps enqueued ahead of a subtree that stops early (U-turn, divergence,
+    end of the iteration) hold device slots; every one of them is back in the
+    pool after the iteration, over many iterations."""
+    import gc
+    atoms, scat = make_hmc_atoms(2, 'fp32')
+    np.random.seed(2)
+    ens = sim.NUTSCanonicalEnsemble(atoms, temperature=1000, escape_level=5, seed=4, fast=True,
+                                    device_states=True)
+    ens.run(25)
+    gc.collect()
+    pool = scat.pdf_backend._slot_pool
+    assert len(pool.free) == sim._DeviceSystem.N_SLOTS and len(set(pool.free)) == len(pool.free)
+    assert ens.leapfrogs > 100
+
+
 def test_device_state_nuts_equals_array_level_nuts():
     """NUTS with the tree's states resident on the device draws the same random
     numbers and follows the same trajectory as the array-level path."""
