@@ -77,6 +77,7 @@ def classical_dynamics(atoms, stepsize, n_steps):
                 states.append(st)
             traj.extend(system.to_atoms(s) for s in states)
             done += batch
+        system.close()
         return traj
     for _ in range(n_steps):
         traj.append(leapfrog(traj[-1], stepsize))
