@@ -1897,7 +1897,7 @@ static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
     q.s_scale_inv = 1.0 / h->s_fix_scale;
     q.gforce = h->gforce;
     // the force pass as a float64 radial table built inside the launch
-    constexpr int PHI_CAP_FUSED = 16384;
+    constexpr int PHI_CAP_FUSED = 32768;  // 436 A at Q_max = 25 (64 chain steps x 262 KB per element pair)
     const bool tab = h->fused_table && h->ntypes <= 2;
     if (tab && !h->phi_tab_d) {
         if ((rc = dev_alloc(&h->phi_tab_d, (size_t)IID_LF_CHAIN * h->ntypes * h->ntypes *
