@@ -733,7 +733,7 @@ def test_fused_force_table_two_elements_and_far_pairs():
     """The radial force table of the fused launch: (1) a two-element structure
     (one table per ordered element pair) against the FP64 handle and the direct
     pass; (2) a structure stretched beyond the table's last entry -- two
-    clusters 400 A apart -- whose far pairs are summed directly over the Q
+    clusters 1000 A apart -- whose far pairs are summed directly over the Q
     bins; (3) three element types keep the direct pass."""
     atoms = structures.alloy_sphere(300, seed=3)
     ideal = atoms.copy()
@@ -754,7 +754,7 @@ def test_fused_force_table_two_elements_and_far_pairs():
     assert res[0][0] == res[1][0] and nerr(res[1][2], res[0][2]) < 2e-6
     # far pairs
     far = structures.icosahedron('Au', 2)
-    far.positions[30:] += [400., 0., 0.]
+    far.positions[30:] += [1000., 0., 0.]
     ideal = structures.icosahedron('Au', 2)
     be, target = _fused_backend(far, ideal)
     pos = far.get_positions()
