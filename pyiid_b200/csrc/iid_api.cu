@@ -20,6 +20,7 @@
 #include "iid_debye2.cuh"
 #include "iid_debye64.cuh"
 #include "iid_force_table.cuh"
+#include "iid_fq_hist.cuh"
 #include "iid_fused.cuh"
 #include "iid_sampler.cuh"
 #include "iid_small.cuh"
@@ -149,6 +150,13 @@ struct iid_handle {
     size_t Sitem_fq_count = 0;
     double *ft_part = nullptr;    // tabulated force pass: [jsplit][np][3] partial sums
     size_t ft_part_count = 0;
+    // F(Q) pass through a radial pair histogram (iid_fq_hist.cuh): FP32 mode, large structures
+    bool fq_hist = true;
+    int64_t fq_hist_min_n = 1200;
+    double *hist_info = nullptr;            // [4] grid step, its inverse, nodes in use, gate
+    unsigned long long *hist_C = nullptr;   // [element pairs][FH_CAP] fixed point, zero between passes
+    int *hist_order = nullptr;              // [n_items_tri] item indices sorted by element pair
+    double *hist_Spart = nullptr;           // [element pairs][chunks][qp] partial sums of the transform
     // the fused evaluation kernel's fixed-point accumulators (zero between launches)
     unsigned long long *Sfix = nullptr, *Ffix = nullptr;
     double *gforce = nullptr;  // [qp] per-bin bound of a pair's force per unit weight
@@ -308,6 +316,8 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_FUSED_DET")) h->fused_det = atoi(s) != 0;
     if (const char *s = getenv("IID_CHAIN_IN_KERNEL")) h->chain_in_kernel = atoi(s) != 0;
     if (const char *s = getenv("IID_FUSED_TABLE")) h->fused_table = atoi(s) != 0;
+    if (const char *s = getenv("IID_FQ_HIST")) h->fq_hist = atoi(s) != 0;
+    if (const char *s = getenv("IID_FQ_HIST_MIN_N")) h->fq_hist_min_n = std::max(2, atoi(s));
     if (const char *s = getenv("IID_DET_FQ")) h->det_fq = atoi(s) != 0;
     if (const char *s = getenv("IID_ZERO_COPY_SMALL")) h->zero_copy_small = atoi(s) != 0;
     *out = h;
@@ -322,7 +332,7 @@ extern "C" int iid_destroy(iid_handle *h)
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
                     h->inv_na, h->inv_na_d, h->items_tri, h->jobs, h->segs, h->fixes, h->Spart,
-                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->Sfix, h->Ffix, h->gforce, h->phi_tab_d, h->ext_ref, h->Sitem_fq, h->ft_part, h->T,
+                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->Sfix, h->Ffix, h->gforce, h->phi_tab_d, h->ext_ref, h->hist_info, h->hist_C, h->hist_order, h->hist_Spart, h->Sitem_fq, h->ft_part, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
                     h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf,
                     h->lf_slab, h->lf_mass, h->lf_ctl, h->lf_mirror};
@@ -853,6 +863,29 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
         (rc = dev_alloc(&h->wq, qp)) || (rc = dev_alloc(&h->force, 3 * n)))
         return rc;
     h->n_items_tri = (int64_t)tri.size();
+    {
+        // the histogram F(Q) pass walks the items grouped by element pair (a block
+        // keeps ONE pair's histogram in shared memory), longest first within a pair
+        std::vector<int> order(tri.size());
+        for (size_t k = 0; k < tri.size(); ++k) order[k] = (int)k;
+        auto pair_of = [&](int k) {
+            const int ta = tile_type[tri[k].itile], tb = tri[k].info & 0xffff;
+            return ta >= tb ? ta * (ta + 1) / 2 + tb : tb * (tb + 1) / 2 + ta;
+        };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const int pa = pair_of(a), pb = pair_of(b);
+            if (pa != pb) return pa < pb;
+            return (tri[a].jend - tri[a].jbegin) > (tri[b].jend - tri[b].jbegin);
+        });
+        int rc2 = dev_alloc(&h->hist_order, std::max<size_t>(1, order.size()));
+        if (rc2) return rc2;
+        if (!order.empty())
+            CU(cudaMemcpy(h->hist_order, order.data(), order.size() * sizeof(int),
+                          cudaMemcpyHostToDevice));
+        for (double **b : {&h->hist_info, &h->hist_Spart})
+            if (*b) { cudaFree(*b); *b = nullptr; }
+        if (h->hist_C) { cudaFree(h->hist_C); h->hist_C = nullptr; }
+    }
     h->tri_maxlen = 0;
     for (const WorkItem &w : tri) h->tri_maxlen = std::max<int64_t>(h->tri_maxlen, w.jend - w.jbegin);
     // the fused evaluation kernel's buffers are sized per structure
@@ -1094,6 +1127,70 @@ static int launch_debye64_t(iid_handle *h, const DebyeParams &p, int64_t nblocks
 constexpr int C32 = 32;  // Q bins per warp, float32 kernels
 constexpr int C64 = 16;  // Q bins per warp, float64 kernels
 
+// F(Q) pass through the radial pair histogram (iid_fq_hist.cuh): FP32 mode,
+// large structures.  Leaves this shard's pair sums in S; `gate` tells the direct
+// kernel launched behind it whether it still has to run.
+static bool fq_hist_applicable(const iid_handle *h)
+{
+    return h->fq_hist && h->precision == IID_FP32 && h->n >= h->fq_hist_min_n && h->qp <= 384 &&
+           h->ntypes <= 5;
+}
+
+constexpr int FH_NCHUNK = (FH_CAP + FHT_E - 1) / FHT_E;
+
+// Buffers of the histogram pass (sized per structure; before the first launch,
+// outside any stream capture).
+static int fq_hist_prepare(iid_handle *h)
+{
+    int rc;
+    const int ntp = (int)(h->ntypes * (h->ntypes + 1) / 2);
+    constexpr int NCHUNK = FH_NCHUNK;
+    if (!h->hist_info) {
+        if ((rc = dev_alloc(&h->hist_info, 4)) ||
+            (rc = dev_alloc(&h->hist_C, (size_t)ntp * FH_CAP)) ||
+            (rc = dev_alloc(&h->hist_Spart, (size_t)ntp * NCHUNK * h->qp)))
+            return rc;
+        CU(cudaMemset(h->hist_C, 0, (size_t)ntp * FH_CAP * sizeof(unsigned long long)));
+        CU(cudaMemset(h->hist_info, 0, 4 * sizeof(double)));
+        CU(cudaStreamSynchronize(0));
+        static bool attr_done[64] = {false};
+        if (!attr_done[h->device & 63]) {
+            CU(cudaFuncSetAttribute(fq_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    2 * FH_CAP * (int)sizeof(int)));
+            attr_done[h->device & 63] = true;
+        }
+    }
+    return 0;
+}
+
+static int launch_fq_hist(iid_handle *h, double *S, cudaStream_t st)
+{
+    const int ntp = (int)(h->ntypes * (h->ntypes + 1) / 2);
+    constexpr int NCHUNK = FH_NCHUNK;
+    const double hstep = FT_QH / (h->qbin * (double)h->nq);
+    fq_hist_grid_kernel<<<1, 1024, 0, st>>>(h->x, h->y, h->z, h->valid, (int)h->np, hstep,
+                                            h->hist_info);
+    HistParams p;
+    p.x = h->x; p.y = h->y; p.z = h->z; p.valid = h->valid;
+    p.tile_type = h->tile_type;
+    p.items = h->items_tri;
+    p.order = h->hist_order;
+    p.n_items = (int)h->n_items_tri;
+    p.rank = h->rank; p.world = h->world;
+    p.info = h->hist_info;
+    p.C = h->hist_C;
+    p.stride = FH_CAP;
+    fq_hist_kernel<<<h->sm_count, FH_THREADS, 2 * FH_CAP * sizeof(int), st>>>(p);
+    fq_hist_transform_kernel<<<dim3(NCHUNK, ntp), 384, 0, st>>>(
+        h->hist_C, FH_CAP, h->hist_info, reinterpret_cast<const float *>(h->ftab), (int)h->ntypes,
+        (int)h->nq, (int)h->qp, h->qbin, h->hist_Spart);
+    reduce_spart_kernel<<<(unsigned)((h->nq + 31) / 32), 1024, 0, st>>>(
+        h->hist_Spart, ntp * NCHUNK, (int)h->nq, (int)h->qp, S);
+    h->launches += 4;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 static int launch_debye(iid_handle *h, int mode, void *G, double *S, const double *wq,
                         double *force, cudaStream_t st)
 {
@@ -1112,6 +1209,7 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     p.grad_split = h->grad_split ? 1 : 0;
     p.jobs = h->jobs; p.segs = h->segs; p.Gside = nullptr;
     int64_t mine;
+    bool hist = false;
     if (rows) {
         // row jobs of this shard; S = per-job partial sums; the pieces of the
         // split rows go through the side buffer
@@ -1158,7 +1256,14 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     } else {
         const int64_t nitems = h->n_items_tri;
         mine = nitems > h->rank ? (nitems - h->rank + h->world - 1) / h->world : 0;
-        if (mode == MODE_FQ && h->det_fq && S && mine > 0) {
+        hist = mode == MODE_FQ && S && mine > 0 && fq_hist_applicable(h);
+        if (hist) {
+            // radial pair histogram (iid_fq_hist.cuh); the direct kernel below only
+            // runs if the structure does not fit it (gate), adding into S
+            int rc0 = fq_hist_prepare(h);
+            if (rc0) return rc0;
+            p.gate = h->hist_info;
+        } else if (mode == MODE_FQ && h->det_fq && S && mine > 0) {
             // deterministic F(Q): every item stores its partial sums, added in
             // item order by reduce_spart_kernel (no atomics)
             const size_t cnt = (size_t)mine * h->qp;
@@ -1172,6 +1277,12 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
     }
     h->last_pairq = 0.5 * (double)h->n * (double)(h->n - 1) * (double)h->nq / h->world;
     int rc = 0;
+    const bool timing = h->timing;
+    if (hist) {
+        if (timing) CU(cudaEventRecord(h->ev0, st));
+        if ((rc = launch_fq_hist(h, S, st))) return rc;
+        h->timing = false;  // (the events bracket the whole pass, not the gated kernel)
+    }
     if (mine > 0) {
         if (h->precision == IID_FP32 && h->cheb) {
             if (mode == MODE_FQ) rc = launch_debye2_t<C32, MODE_FQ, true>(h, p, mine, st);
@@ -1187,6 +1298,13 @@ static int launch_debye(iid_handle *h, int mode, void *G, double *S, const doubl
             else rc = launch_debye64_t<C64, MODE_FORCE>(h, p, mine, st);
         }
         if (rc) return rc;
+    }
+    if (hist) {
+        h->timing = timing;
+        if (timing) {
+            CU(cudaEventRecord(h->ev1, st));
+            h->ev_pending = true;
+        }
     }
     if (!rows && p.Sitem != nullptr) {
         reduce_spart_kernel<<<(unsigned)((h->nq + 31) / 32), 1024, 0, st>>>(
@@ -2671,6 +2789,8 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "fused_det") h->fused_det = value != 0;
     else if (k == "chain_in_kernel") h->chain_in_kernel = value != 0;
     else if (k == "fused_table") h->fused_table = value != 0;
+    else if (k == "fq_hist") h->fq_hist = value != 0;
+    else if (k == "fq_hist_min_n") h->fq_hist_min_n = std::max<int64_t>(2, value);
     else if (k == "det_fq") h->det_fq = value != 0;
     else if (k == "acc_j") h->acc_j = (int)std::max<int64_t>(0, value);
     else if (k == "piece_div") {

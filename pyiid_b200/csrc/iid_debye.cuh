@@ -105,6 +105,9 @@ struct DebyeParams {
     unsigned long long *Sfix = nullptr;  // MODE_FQ: [2][qp] high word, low word (fix_add2)
     unsigned long long *Ffix = nullptr;  // MODE_FORCE: [n][3]
     double fix_scale = 0.0;
+    // The stand-alone F(Q) kernel behind the histogram pass (iid_fq_hist.cuh): it
+    // runs only when gate[3] == 0, i.e. the structure did not fit the histogram.
+    const double *gate = nullptr;
 };
 
 __device__ __forceinline__ void fix_add(unsigned long long *a, double v, double scale)

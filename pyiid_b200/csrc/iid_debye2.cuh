@@ -727,6 +727,7 @@ template <int C, int MODE, int MAXT, int MINB, int TJ2, bool CHEB, int PU = 1>
 __global__ void __launch_bounds__(MAXT, MINB) debye2_kernel(const DebyeParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (MODE == MODE_FQ && p.gate != nullptr && p.gate[3] != 0.0) return;  // the histogram pass ran
     debye2_body<C, MODE, TJ2, CHEB, PU>(p, smem_raw, (int)blockIdx.x, (int)blockIdx.y);
 }
 

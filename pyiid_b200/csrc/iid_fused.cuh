@@ -38,6 +38,7 @@
 #include <cooperative_groups.h>
 #include "iid_debye2.cuh"
 #include "iid_sampler.cuh"
+#include "iid_stencil.cuh"
 
 namespace iid {
 
@@ -126,11 +127,7 @@ __device__ __forceinline__ double block_sum(double v, double *sm)
 // nothing else.  At Au561 that is 2 200 entries x 330 bins (0.7 M terms)
 // instead of 157 000 pairs x 330 bins; a coarse grid with a long stencil keeps
 // the build short when a hot trajectory has spread the structure out.
-constexpr int FT_PTS = 12;            // interpolation points
-constexpr int FT_LEFT = FT_PTS / 2 - 1;  // nodes k - FT_LEFT .. k + FT_PTS - 1 - FT_LEFT
-constexpr int FT_PAD = FT_PTS / 2;    // entries stored before r = 0
 constexpr int FT_G = 8;               // lanes per table entry
-constexpr double FT_QH = 1.0 / 3.0;   // Q_max h
 
 __device__ __forceinline__ void fused_table_build(double *tab, int stride, int ntp, int K,
                                                   double h, const double *wab, int nq, int qp,
@@ -208,15 +205,6 @@ __device__ double fused_phi_direct(double r, const double *w, int nq, double qbi
 // FT_PTS-point Lagrange interpolation on the uniform grid: nodes k - FT_LEFT ..
 // k + FT_PTS - 1 - FT_LEFT at t[-FT_LEFT] .., u in [0, 1) measured from node k.
 // Error of 12 points: max |prod (u - j)| / 12! = 2.2e-4 times (Q_max h)^12.
-__host__ __device__ constexpr double ft_bary(int i)
-{
-    // barycentric weight of node i of FT_PTS equispaced nodes: (-1)^(n-i) C(n, i) / n!
-    double c = 1.0, f = 1.0;
-    for (int k = 1; k <= FT_PTS - 1; ++k) f *= (double)k;
-    for (int k = 0; k < i; ++k) c = c * (double)(FT_PTS - 1 - k) / (double)(k + 1);
-    return (((FT_PTS - 1 - i) & 1) ? -c : c) / f;
-}
-
 __device__ __forceinline__ double lagrange_pts(const double *t, double u)
 {
     double v[FT_PTS], d[FT_PTS], pre[FT_PTS], L = 0.0;

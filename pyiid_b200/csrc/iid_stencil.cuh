@@ -1,0 +1,27 @@
+// iid_stencil.cuh -- the interpolation stencil shared by the radial tables:
+// the force table of the fused evaluation kernel (iid_fused.cuh, values
+// interpolated FROM a uniform r grid) and the pair histogram of the F(Q) pass
+// (iid_fq_hist.cuh, pair weights spread ONTO the same grid -- the adjoint).
+// FT_PTS-point Lagrange interpolation on a grid with Q_max h = FT_QH: the
+// functions involved are band limited by Q_max, so the error is
+// max |prod (u - j)| / FT_PTS! * (Q_max h)^FT_PTS = 2.2e-4 * 3^-12 = 4e-10 of
+// their amplitude.
+#pragma once
+
+namespace iid {
+
+constexpr int FT_PTS = 12;               // interpolation points
+constexpr int FT_LEFT = FT_PTS / 2 - 1;  // nodes k - FT_LEFT .. k + FT_PTS - 1 - FT_LEFT
+constexpr int FT_PAD = FT_PTS / 2;       // entries stored before r = 0
+constexpr double FT_QH = 1.0 / 3.0;      // Q_max h
+
+__host__ __device__ constexpr double ft_bary(int i)
+{
+    // barycentric weight of node i of FT_PTS equispaced nodes: (-1)^(n-i) C(n, i) / n!
+    double c = 1.0, f = 1.0;
+    for (int k = 1; k <= FT_PTS - 1; ++k) f *= (double)k;
+    for (int k = 0; k < i; ++k) c = c * (double)(FT_PTS - 1 - k) / (double)(k + 1);
+    return (((FT_PTS - 1 - i) & 1) ? -c : c) / f;
+}
+
+}  // namespace iid

@@ -541,6 +541,77 @@ def test_sharded_partials_sum_to_the_whole():
     assert nerr(g_sum, g_ref) < 1e-12
 
 
+def test_fq_through_the_pair_histogram():
+    """FP32 mode, large structures: the F(Q) pair sum goes through a radial pair
+    histogram (iid_fq_hist.cuh).  It must give the direct pass's F(Q) (both are
+    within 1e-5 of the float64 oracle; the histogram is the more accurate one),
+    bit-reproducibly, for one / two / three element types, on both Q grids, as
+    shards that add up, and fall back to the direct kernel when the structure
+    does not fit the histogram."""
+    import torch
+    rs = np.random.RandomState(3)
+    tri_numbers = rs.choice([79, 78, 47], 1500)
+    cases = [structures.fcc_sphere('Au', 2000), structures.alloy_sphere(1800, seed=3),
+             ase_shim.Atoms(numbers=tri_numbers,
+                            positions=structures.fcc_sphere_positions(1500, 3.9, 0.05, 3))]
+    for atoms in cases:
+        scat = ElasticScatter()
+        scat._ensure_wrapped(atoms)
+        pos = atoms.get_positions()
+        for kind, qb, key in (('fq', scat.exp['qbin'], 'F(Q) scatter'),
+                              ('PDF', scat.pdf_qbin, 'PDF scatter')):
+            be = scat._load(atoms, qb, kind)
+            assert be.n >= 1200  # the histogram pass is the default at this size
+            f_hist = be.fq(pos)
+            n0 = be.launch_count()
+            assert np.array_equal(be.fq(pos), f_hist)
+            per_call = be.launch_count() - n0
+            be.set_option('fq_hist', 0)
+            f_direct = be.fq(pos)
+            be.set_option('fq_hist', 1)
+            assert nerr(f_hist, f_direct) < 5e-7, (kind, nerr(f_hist, f_direct))
+            if kind == 'fq':
+                exp = dict(scat.exp)
+                ref = oracle.experiment_fq(pos.astype(np.float32), atoms.get_array(key), exp,
+                                           'fp64', nthreads=8)
+                assert nerr(f_hist, ref) < 2e-6 and nerr(f_direct, ref) < TOL32
+                assert per_call == 7  # staging, grid, histogram, transform, sum, gated direct, finish
+    # shards: the ranks' pair histograms are partial sums of S
+    atoms = cases[1]
+    scat = ElasticScatter()
+    scat._ensure_wrapped(atoms)
+    be = scat._load(atoms, scat.exp['qbin'], 'fq')
+    pos = atoms.get_positions()
+    f_ref = be.fq(pos)
+    lib, h = be.lib, be.h
+    dev = 'cuda:%d' % be.device
+    with be._on_stream():
+        p = torch.from_numpy(pos).to(dev)
+        s_tot = torch.zeros(be.nq, dtype=torch.float64, device=dev)
+        for rank in range(3):
+            assert lib.iid_set_shard(h, rank, 3) == 0
+            s = torch.zeros_like(s_tot)
+            assert lib.iid_fq_partial(h, p.data_ptr(), s.data_ptr(), None) == 0
+            s_tot += s
+        assert lib.iid_set_shard(h, 0, 1) == 0
+        f = torch.zeros_like(s_tot)
+        assert lib.iid_fq_finish(h, s_tot.data_ptr(), f.data_ptr(), None) == 0
+        f_sum = f.cpu().numpy()
+    assert nerr(f_sum, f_ref) < 1e-12
+    # a structure that does not fit the histogram: the gated direct kernel runs
+    far = structures.fcc_sphere('Au', 1300)
+    far.positions[650:] += [800., 0., 0.]
+    scat = ElasticScatter()
+    scat._ensure_wrapped(far)
+    be = scat._load(far, scat.exp['qbin'], 'fq')
+    pos = far.get_positions()
+    f_gate = be.fq(pos)
+    be.set_option('fq_hist', 0)
+    f_direct = be.fq(pos)
+    be.set_option('fq_hist', 1)
+    assert nerr(f_gate, f_direct) < 2e-7 and np.abs(f_gate).max() > 0
+
+
 # ---- samplers on the device calculator -------------------------------------------------
 def make_hmc_atoms(shells=2, precision='fp32'):
     scat = ElasticScatter(precision=precision)
