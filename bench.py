@@ -392,6 +392,16 @@ def config3_extra():
                 fn(pos)
                 ts.append(be.last_kernel_ms()[0])
             out['%s_kernel_ms_%s' % (name, prec)] = min(ts)
+        if prec == 'fp32':
+            # the default F(Q) pass at this size is the radial pair histogram
+            # (O(N^2 + K Q)); the direct O(N^2 Q) kernel for the roofline of SURVEY 8d
+            be.set_option('fq_hist', 0)
+            ts = []
+            for _ in range(3):
+                be.fq(pos)
+                ts.append(be.last_kernel_ms()[0])
+            out['fq_direct_kernel_ms_fp32'] = min(ts)
+            be.set_option('fq_hist', 1)
         be.set_timing(False)
         bp = scat._load(atoms, scat.pdf_qbin, 'PDF')
         bp.set_transform(scat.exp['rstep'], scat.pdf_qbin, scat.get_r(), 0.0)
@@ -413,12 +423,19 @@ def config3_extra():
         pass
     sms = sm.value or 148
     roof = {}
-    t = out['fq_kernel_ms_fp32'] * 1e-3
+    t = out['fq_direct_kernel_ms_fp32'] * 1e-3
     roof['fq_fp32'] = {'achieved': pairq / t, 'peak': sms * clk * 16, 'unit': UNIT,
                        'frac': pairq / t / (sms * clk * 16),
-                       'note': 'above 1: the SFU count of the bound is not executed, sin comes '
-                               'from FP32 recurrences',
+                       'note': 'the direct O(N^2 Q) kernel (fq_hist = 0).  Above 1: the SFU count '
+                               'of the bound is not executed, sin comes from FP32 recurrences',
                        'executed_lane_fma_frac_of_measured_ffma2': pairq * 2.6 / t / peaks['ffma2']}
+    t = out['fq_kernel_ms_fp32'] * 1e-3
+    roof['fq_hist_fp32'] = {'achieved': pairq / t, 'unit': UNIT, 'peak': None, 'frac': None,
+                            'pairs_per_s': 0.5 * n * (n - 1) / t,
+                            'note': 'the shipped F(Q) pass at this size: radial pair histogram, '
+                                    'O(N^2 + K Q) -- no pair*Q bound applies; it is bound by 24 '
+                                    '32-bit shared-memory atomics per pair (bank conflicts), '
+                                    '%.1f SM cycles per pair' % (t * sms * clk / (0.5 * n * (n - 1)))}
     t = out['fq_grad_kernel_ms_fp32'] * 1e-3
     roof['fq_grad_fp32'] = {'achieved': pairq / t, 'peak': sms * clk * 8, 'unit': UNIT,
                             'frac': pairq / t / (sms * clk * 8),

@@ -339,7 +339,11 @@ int iid_download_host(iid_handle *h, const void *dev, void *host, int64_t bytes)
  * table it builds itself, up to two element types; 0 = direct pass over the
  * Q bins), "chain_in_kernel" (0/1: a leapfrog chain is ONE launch; 0 = one
  * launch per step behind one synchronisation), "fused_det" (accepted, no
- * effect: the launch's fixed-point sums are always bit-reproducible), "det_fq" (0/1: the stand-alone F(Q) pass stores per-item
+ * effect: the launch's fixed-point sums are always bit-reproducible),
+ * "fq_hist" (0/1: FP32 mode, the F(Q)-only pass of structures of at least
+ * "fq_hist_min_n" atoms goes through a fixed-point radial pair histogram,
+ * O(N^2 + K Q), bit-reproducible; 0 = the direct O(N^2 Q) kernel),
+ * "det_fq" (0/1: the stand-alone F(Q) pass stores per-item
  * partial sums and adds them in item order -- F(Q), G(r), Rw reproducible).  Defaults can also be set with IID_* environment variables
  * before iid_create. */
 int iid_set_option(iid_handle *h, const char *key, int64_t value);
