@@ -529,6 +529,8 @@ def config5_extra(world):
                         'all-reduce of the F(Q) pair sums' % (n, nq),
             'n_gpus': world, 'ms_per_evaluation': 1e3 * dt, 'pairq_per_s': pairq / dt,
             'frac_of_f_only_bound': pairq / dt / (world * sms * clk * 16),
+            'note': 'FP32 mode runs the F(Q) pass as a radial pair histogram (O(N^2 + K Q), DESIGN '
+                    '4.1b): the pair*Q bound of SURVEY 8d does not apply to it (fraction above 1)',
             'rw_fp32': e, 'scale_fp32': scale,
             'ms_per_evaluation_fp64': 1e3 * res['fp64'][0], 'rw_fp64': res['fp64'][1],
             'rw_fp32_vs_fp64_rel': abs(e - res['fp64'][1]) / abs(res['fp64'][1])}
