@@ -109,6 +109,13 @@ int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
  * iid_energy_forces*. */
 int iid_set_transform(iid_handle *h, int64_t nr, int64_t nq, const double *T);
 
+/* Host-only: the Lagrange weights w[n_points] of the radial stencil for a
+ * point u in [0, 1) past grid node k (node k - left + i gets w[i]) and the grid
+ * step in units of 1/Q_max.  The fused evaluation's force table interpolates
+ * with this stencil and the F(Q) pair histogram spreads with it; w must hold
+ * at least 16 doubles. */
+int iid_stencil_weights(double u, double *w, int *n_points, int *left, double *qmax_h);
+
 /* Host-only (no device): the sharding plan iid_set_structure + iid_set_shard
  * would produce -- total work items, this rank's items and the (i, j) slots
  * they cover, for the triangle (F(Q), force) or square (gradient) list. */

@@ -250,6 +250,28 @@ static int multi_energy_forces_host(iid_handle *h, const double *pos_host,
 
 // ---------------------------------------------------------------------------
 extern "C" int iid_version(void) { return 200; }
+
+// Host-only: the FT_PTS Lagrange weights of the radial stencil (iid_stencil.cuh)
+// for a point u in [0, 1) past node k: node k - *left + i gets w[i].  The force
+// table of the fused kernel interpolates with them, the F(Q) pair histogram
+// spreads with them; exposed so that the stencil can be checked without a device.
+extern "C" int iid_stencil_weights(double u, double *w, int *n_points, int *left, double *qmax_h)
+{
+    if (!w) return fail(IID_E_BADARG, "null pointer");
+    double d[FT_PTS], pre[FT_PTS];
+    for (int i = 0; i < FT_PTS; ++i) d[i] = u - (double)(i - FT_LEFT);
+    pre[0] = 1.0;
+    for (int i = 1; i < FT_PTS; ++i) pre[i] = pre[i - 1] * d[i - 1];
+    double suf = 1.0;
+    for (int i = FT_PTS - 1; i >= 0; --i) {
+        w[i] = ft_bary(i) * pre[i] * suf;
+        suf *= d[i];
+    }
+    if (n_points) *n_points = FT_PTS;
+    if (left) *left = FT_LEFT;
+    if (qmax_h) *qmax_h = FT_QH;
+    return 0;
+}
 extern "C" const char *iid_last_error(void) { return g_err.c_str(); }
 
 extern "C" int iid_device_count(int *count)

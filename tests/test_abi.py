@@ -100,6 +100,40 @@ def test_small_structures_get_a_single_wave_triangle_list():
         assert (total <= 148) == one_wave, (n, total)
 
 
+def test_radial_stencil_interpolates_band_limited_functions():
+    """The Lagrange stencil shared by the fused kernel's force table and the
+    F(Q) pair histogram (iid_stencil.cuh): the weights are a partition of unity,
+    reproduce polynomials, and interpolate sin(Q r)/r on a grid with
+    Q_max h = 1/3 to 4e-10 of its amplitude -- the figure DESIGN.md quotes."""
+    lib = _lib.load()
+    w = np.zeros(16)
+    npts, left = ctypes.c_int(0), ctypes.c_int(0)
+    qh = ctypes.c_double(0.)
+    assert lib.iid_stencil_weights(0.25, w.ctypes.data, ctypes.byref(npts), ctypes.byref(left),
+                                   ctypes.byref(qh)) == 0
+    n, lft, qmax_h = npts.value, left.value, qh.value
+    assert n == 12 and lft == 5 and abs(qmax_h - 1. / 3.) < 1e-15
+    rs = np.random.RandomState(0)
+    qmax, worst = 25., 0.
+    h = qmax_h / qmax
+    for _ in range(400):
+        u, k = rs.rand(), rs.randint(0, 9000)
+        assert lib.iid_stencil_weights(u, w.ctypes.data, None, None, None) == 0
+        ww = w[:n]
+        assert abs(ww.sum() - 1.) < 1e-12
+        nodes = (k - lft + np.arange(n)) * h
+        r = (k + u) * h
+        assert abs(ww.dot(nodes ** 3) - r ** 3) < 1e-9 * max(1., r ** 3)
+        for q in (qmax, 0.6 * qmax, 3.):
+            g = np.where(nodes != 0, np.sin(q * nodes) / np.where(nodes != 0, nodes, 1.), q)
+            exact = np.sin(q * r) / r if r > 0 else q
+            worst = max(worst, abs(ww.dot(g) - exact) / q)
+    assert worst < 4e-10, worst
+    # at a node the stencil is the identity
+    assert lib.iid_stencil_weights(0., w.ctypes.data, None, None, None) == 0
+    assert abs(w[lft] - 1.) < 1e-15 and np.abs(np.delete(w[:n], lft)).max() < 1e-15
+
+
 def test_shard_plan_property_random_structures():
     """Property form of the test above (hypothesis): any element mix, any
     world size -- the ranks' slices partition the work list, the triangle list
