@@ -344,7 +344,10 @@ int iid_download_host(iid_handle *h, const void *dev, void *host, int64_t bytes)
  * "fused" (0/1: small structures evaluate in ONE cooperative launch),
  * "fused_table" (0/1: that launch takes its force pass from a float64 radial
  * table it builds itself, up to two element types; 0 = direct pass over the
- * Q bins), "chain_in_kernel" (0/1: a leapfrog chain is ONE launch; 0 = one
+ * Q bins), "fused_hist" (0/1: that launch sums F(Q) through a fixed-point
+ * radial pair histogram in shared memory when the structure's bounding box
+ * fits it, bit-reproducible; 0 = its direct pass over the Q bins),
+ * "chain_in_kernel" (0/1: a leapfrog chain is ONE launch; 0 = one
  * launch per step behind one synchronisation), "fused_det" (accepted, no
  * effect: the launch's fixed-point sums are always bit-reproducible),
  * "fq_hist" (0/1: FP32 mode, the F(Q)-only pass of structures of at least

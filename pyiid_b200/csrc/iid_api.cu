@@ -161,6 +161,8 @@ struct iid_handle {
     unsigned long long *Sfix = nullptr, *Ffix = nullptr;
     double *gforce = nullptr;  // [qp] per-bin bound of a pair's force per unit weight
     double *phi_tab_d = nullptr;  // its float64 radial force table
+    unsigned long long *fused_C = nullptr;  // its radial pair histogram (F(Q) phase)
+    bool fused_hist = true;
     double *ext_ref = nullptr;    // [4] box centre of its previous evaluation + valid flag
     bool fused_table = true;
     std::vector<double> gforce_host;
@@ -338,6 +340,7 @@ extern "C" int iid_create(int device, int precision, iid_handle **out)
     if (const char *s = getenv("IID_FUSED_DET")) h->fused_det = atoi(s) != 0;
     if (const char *s = getenv("IID_CHAIN_IN_KERNEL")) h->chain_in_kernel = atoi(s) != 0;
     if (const char *s = getenv("IID_FUSED_TABLE")) h->fused_table = atoi(s) != 0;
+    if (const char *s = getenv("IID_FUSED_HIST")) h->fused_hist = atoi(s) != 0;
     if (const char *s = getenv("IID_FQ_HIST")) h->fq_hist = atoi(s) != 0;
     if (const char *s = getenv("IID_FQ_HIST_MIN_N")) h->fq_hist_min_n = std::max(2, atoi(s));
     if (const char *s = getenv("IID_DET_FQ")) h->det_fq = atoi(s) != 0;
@@ -354,7 +357,7 @@ extern "C" int iid_destroy(iid_handle *h)
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->x, h->y, h->z, h->valid, h->orig, h->tile_type, h->ftab,
                     h->inv_na, h->inv_na_d, h->items_tri, h->jobs, h->segs, h->fixes, h->Spart,
-                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->Sfix, h->Ffix, h->gforce, h->phi_tab_d, h->ext_ref, h->hist_info, h->hist_C, h->hist_order, h->hist_Spart, h->Sitem_fq, h->ft_part, h->T,
+                    h->Gside, h->Gscr, h->slot_busy, h->MF, h->wq_blk, h->Sfix, h->Ffix, h->gforce, h->phi_tab_d, h->fused_C, h->ext_ref, h->hist_info, h->hist_C, h->hist_order, h->hist_Spart, h->Sitem_fq, h->ft_part, h->T,
                     h->pos, h->S, h->F, h->Gr, h->cr, h->wq, h->out4, h->force,
                     h->target, h->Gfull, h->phi_tab, h->phi_info, h->Mq, h->vgo, h->coef, h->sp_buf,
                     h->lf_slab, h->lf_mass, h->lf_ctl, h->lf_mirror};
@@ -913,7 +916,7 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
     // the fused evaluation kernel's buffers are sized per structure
     for (double **b : {&h->MF, &h->wq_blk, &h->gforce, &h->phi_tab_d, &h->ext_ref})
         if (*b) { cudaFree(*b); *b = nullptr; }
-    for (unsigned long long **b : {&h->Sfix, &h->Ffix})
+    for (unsigned long long **b : {&h->Sfix, &h->Ffix, &h->fused_C})
         if (*b) { cudaFree(*b); *b = nullptr; }
     {
         // fixed-point scale of its F(Q) accumulators: |S[m]| <= pairs * f^2 * Q
@@ -2050,6 +2053,20 @@ static int launch_fused(iid_handle *h, int potential, double conv, bool lf)
     q.ntypes = (int)h->ntypes;
     q.tab_h = FT_QH / (h->qbin * (double)h->nq);
     q.ext_ref = h->ext_ref;
+    // F(Q) phase through the pair histogram: as many nodes as the pair-record
+    // region of the shared memory holds in two 32-bit words each
+    {
+        int ps_off0 = 0;
+        fused_smem_bytes(h, &ps_off0, nullptr);
+        q.fq_cstride = (ps_off0 / 8) & ~31;
+    }
+    if (h->fused_hist && !h->fused_C) {
+        const size_t cnt = (size_t)(h->ntypes * (h->ntypes + 1) / 2) * q.fq_cstride;
+        if ((rc = dev_alloc(&h->fused_C, cnt))) return rc;
+        CU(cudaMemset(h->fused_C, 0, cnt * sizeof(unsigned long long)));
+        CU(cudaStreamSynchronize(0));
+    }
+    q.fq_C = h->fused_hist ? h->fused_C : nullptr;
     q.n_items = (int)h->n_items_tri;
     q.lf = lf ? 1 : 0;
     q.ctl = h->zc_ctl ? h->zc_ctl : h->lf_ctl; q.slab = h->lf_slab; q.mass = h->lf_mass;
@@ -2811,6 +2828,7 @@ extern "C" int iid_set_option(iid_handle *h, const char *key, int64_t value)
     else if (k == "fused_det") h->fused_det = value != 0;
     else if (k == "chain_in_kernel") h->chain_in_kernel = value != 0;
     else if (k == "fused_table") h->fused_table = value != 0;
+    else if (k == "fused_hist") h->fused_hist = value != 0;
     else if (k == "fq_hist") h->fq_hist = value != 0;
     else if (k == "fq_hist_min_n") h->fq_hist_min_n = std::max<int64_t>(2, value);
     else if (k == "det_fq") h->det_fq = value != 0;

@@ -52,6 +52,32 @@ struct HistParams {
     int stride;
 };
 
+// One pair: its unit weight over the nodes k - FT_LEFT .. k + FT_PTS - 1 - FT_LEFT of
+// a two-word fixed-point histogram in shared memory (units of 2^-28; high word
+// 2^-12, low word 16 bits).  u in [0, 1) past node k.
+__device__ __forceinline__ void fq_hist_spread(int *hi_s, unsigned *lo_s, int k, float u)
+{
+    // Lagrange weights (barycentric form by prefix / suffix products; float32: 1e-7
+    // of a unit weight)
+    float d[FT_PTS], pre[FT_PTS];
+#pragma unroll
+    for (int i = 0; i < FT_PTS; ++i) d[i] = u - (float)(i - FT_LEFT);
+    pre[0] = 1.f;
+#pragma unroll
+    for (int i = 1; i < FT_PTS; ++i) pre[i] = pre[i - 1] * d[i - 1];
+    float suf = 1.f;
+    int *hp = hi_s + (k - FT_LEFT + FT_PAD);
+    unsigned *lp = lo_s + (k - FT_LEFT + FT_PAD);
+#pragma unroll
+    for (int i = FT_PTS - 1; i >= 0; --i) {
+        const float w = (float)ft_bary(i) * 268435456.f * pre[i] * suf;  // 2^28
+        suf *= d[i];
+        const int q = __float2int_rn(w);
+        atomicAdd(hp + i, q >> 16);             // floor: q = hi 2^16 + lo
+        atomicAdd(lp + i, (unsigned)(q & 0xffff));
+    }
+}
+
 // info[0] = h, info[1] = 1/h, info[2] = K (nodes r = 0 .. (K-1) h), info[3] = gate
 __global__ void __launch_bounds__(1024) fq_hist_grid_kernel(const double *__restrict__ x,
                                                             const double *__restrict__ y,
@@ -173,25 +199,7 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fq_hist_kernel(const HistParams
                     const double tpos = r2 * y * inv_h;
                     const int k = (int)tpos;
                     const float u = (float)(tpos - (double)k);
-                    // Lagrange weights of the nodes k - FT_LEFT .. (barycentric form by
-                    // prefix / suffix products; float32: 1e-7 of a unit weight)
-                    float d[FT_PTS], pre[FT_PTS];
-#pragma unroll
-                    for (int i = 0; i < FT_PTS; ++i) d[i] = u - (float)(i - FT_LEFT);
-                    pre[0] = 1.f;
-#pragma unroll
-                    for (int i = 1; i < FT_PTS; ++i) pre[i] = pre[i - 1] * d[i - 1];
-                    float suf = 1.f;
-                    int *hp = hi_s + (k - FT_LEFT + FT_PAD);
-                    unsigned *lp = lo_s + (k - FT_LEFT + FT_PAD);
-#pragma unroll
-                    for (int i = FT_PTS - 1; i >= 0; --i) {
-                        const float w = (float)ft_bary(i) * 268435456.f * pre[i] * suf;  // 2^28
-                        suf *= d[i];
-                        const int q = __float2int_rn(w);
-                        atomicAdd(hp + i, q >> 16);             // floor: q = hi 2^16 + lo
-                        atomicAdd(lp + i, (unsigned)(q & 0xffff));
-                    }
+                    fq_hist_spread(hi_s, lo_s, k, u);
                 }
             }
             since_fold += (unsigned)blockDim.x;

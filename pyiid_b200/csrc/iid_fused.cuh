@@ -39,6 +39,7 @@
 #include "iid_debye2.cuh"
 #include "iid_sampler.cuh"
 #include "iid_stencil.cuh"
+#include "iid_fq_hist.cuh"
 
 namespace iid {
 
@@ -58,6 +59,12 @@ struct FusedParams {
     int ntypes;
     double tab_h;             // grid step: FT_QH / Q_max
     double *ext_ref;          // [4] box centre of the previous evaluation + valid flag
+    // F(Q) phase through the radial pair histogram (iid_fq_hist.cuh), or null: the
+    // block spreads the pairs of its work item into a shared-memory histogram,
+    // adds it to the global one, and after a barrier every block turns its share
+    // of the nodes into partial pair sums (fixed point as the direct pass)
+    unsigned long long *fq_C;  // [element pairs][fq_cstride] units of 2^-28, zero between passes
+    int fq_cstride;            // nodes per element pair = shared-memory capacity
     // staging
     int lf;  // 1 = leapfrog staging from the state slab, 0 = positions in `pos`
     const double *ctl;
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
     // evaluation, i.e. the structure's centre up to one step's drift).  Every pair
     // distance is <= min(box diagonal, 2 max |x - c|) for ANY c; the table range
     // only decides how many entries are built, not their values.
-    const bool want_ext = q.phi_tab != nullptr || q.lf_mirror != nullptr;
+    const bool want_ext = q.phi_tab != nullptr || q.lf_mirror != nullptr || q.fq_C != nullptr;
     double ev[6] = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300}, ed2 = 0.0;
     const double rcx = cref[0], rcy = cref[1], rcz = cref[2];
     auto ext_acc = [&](double x, double y, double z) {
@@ -460,6 +467,7 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
         const double ex = ext[3] - ext[0], ey = ext[4] - ext[1], ez = ext[5] - ext[2];
         const double half_diag = 0.5 * sqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
         ext[6] = cref[3] != 0.0 ? fmin(half_diag, sqrt(ext[6])) : half_diag;
+        ext[7] = half_diag;  // (independent of the reference point)
         cref[0] = 0.5 * (ext[0] + ext[3]);
         cref[1] = 0.5 * (ext[1] + ext[4]);
         cref[2] = 0.5 * (ext[2] + ext[5]);
@@ -468,9 +476,128 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
     fused_stamp(q, 2, cs == scs);
 
     // ---- phase 1: F(Q) pass -------------------------------------------------------
-    if (has_item)
-        debye2_body<32, MODE_FQ, 8, CHEB, 1, true>(q.fq, smem_raw, (int)blockIdx.x, 0, ps, pl);
-    fused_stamp(q, 3, cs == scs);
+    // Through the radial pair histogram when the structure's bounding box fits the
+    // shared-memory histogram (block-uniform AND grid-uniform: every block has the
+    // same extent), else the direct pass.  The CHOICE follows the box diagonal alone:
+    // ext[6] also depends on the reference point, i.e. on the previous evaluation,
+    // and the two passes round differently -- the same positions must take the same
+    // pass whatever came before.  The number of nodes in use (Kh) may follow ext[6]:
+    // it bounds every pair distance, and unused nodes hold zeros.
+    __syncthreads();  // ext[6], ext[7] (thread 0, above)
+    const double hgrid = q.tab_h;
+    const int Kh = (int)fmin(2e9, ceil(2.0000002 * ext[6] / hgrid) + (double)(FT_PTS + 2));
+    const bool hist = q.fq_C != nullptr &&
+                      fmin(2e9, ceil(2.0000002 * ext[7] / hgrid)) + (double)(FT_PTS + 2 + 2 * FT_PAD) <=
+                          (double)q.fq_cstride;
+    if (hist) {
+        const int Kp = Kh + 2 * FT_PAD;
+        int *hi_s = reinterpret_cast<int *>(smem_raw);
+        unsigned *lo_s = reinterpret_cast<unsigned *>(hi_s + q.fq_cstride);
+        for (int e = threadIdx.x; e < Kp; e += blockDim.x) { hi_s[e] = 0; lo_s[e] = 0u; }
+        __syncthreads();
+        if (has_item) {
+            const WorkItem wi = q.fq.items[blockIdx.x];
+            const bool diag = (wi.info & ITEM_DIAG) != 0;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+            const int len = wi.jend - wi.jbegin;
+            const double xi = ps[lane], yi = ps[pl + lane], zi = ps[2 * pl + lane];
+            const bool vi = ps[3 * pl + lane] != 0.0;
+            const double inv_h = 1.0 / hgrid;
+            for (int jj = warp; jj < len; jj += nw) {
+                const int sj = TILE_I + jj;
+                // a diagonal item holds both orders of its pairs: count i > j
+                if (vi && ps[3 * pl + sj] != 0.0 && (!diag || jj < lane)) {
+                    const double dx = ps[sj] - xi, dy = ps[pl + sj] - yi, dz = ps[2 * pl + sj] - zi;
+                    const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                    if (r2 > 0.0) {
+                        double y = (double)rsqrtf((float)r2);
+                        y = y * fma(-0.5 * r2, y * y, 1.5);
+                        y = y * fma(-0.5 * r2, y * y, 1.5);  // second Newton step: 1e-15
+                        const double tpos = r2 * y * inv_h;
+                        const int k = (int)tpos;
+                        fq_hist_spread(hi_s, lo_s, k, (float)(tpos - (double)k));
+                    }
+                }
+            }
+            __syncthreads();
+            const int ta = q.fq.tile_type[wi.itile], tb = wi.info & 0xffff;
+            const int pair = ta >= tb ? ta * (ta + 1) / 2 + tb : tb * (tb + 1) / 2 + ta;
+            unsigned long long *C = q.fq_C + (size_t)pair * q.fq_cstride;
+            for (int e = threadIdx.x; e < Kp; e += blockDim.x) {
+                const long long v = (long long)hi_s[e] * 65536ll + (long long)lo_s[e];
+                if (v != 0) atomicAdd(C + e, (unsigned long long)v);
+            }
+        }
+        fused_stamp(q, 3, cs == scs);
+        grid.sync();
+        // Every block: chunks of FUSED_HCH nodes dealt round-robin, all Q bins (thread
+        // = bin, three-term recurrence over a chunk's nodes from exact seeds), partial
+        // sums into Sfix.  The chunk grid is FIXED (not derived from the number of
+        // nodes in use, which follows the extent's reference point and so the history
+        // of evaluations): a chunk past the occupied range holds zeros and adds
+        // nothing, so the pair sums are bit-identical whatever K was.
+        {
+            constexpr int FUSED_HCH = 16;
+            const int ntp = q.ntypes * (q.ntypes + 1) / 2;
+            double *cs_s = reinterpret_cast<double *>(smem_raw);  // [ntp][FUSED_HCH] C / |r|
+            const int m = threadIdx.x;
+            const double Q = q.fq.qbin * (double)m;
+            const double turn = Q * hgrid * 0.15915494309189533577;
+            double sth, cth;
+            sincospi(2.0 * (turn - rint(turn)), &sth, &cth);
+            const double tc = cth + cth;
+            const float *ftab = reinterpret_cast<const float *>(q.fq.ftab);
+            double tot = 0.0;
+            bool added = false;
+            for (int e0 = blockIdx.x * FUSED_HCH; e0 < Kp; e0 += gridDim.x * FUSED_HCH) {
+                const int ne = min(FUSED_HCH, Kp - e0);
+                // (seeds first: they do not depend on the histogram's loads)
+                double s0, c0;
+                const double t0 = turn * (double)(e0 - FT_PAD);
+                sincospi(2.0 * (t0 - rint(t0)), &s0, &c0);
+                bool any = false;
+                __syncthreads();  // cs_s of the previous chunk is consumed
+                for (int idx = threadIdx.x; idx < ntp * FUSED_HCH; idx += blockDim.x) {
+                    const int pr = idx / FUSED_HCH, e = idx - pr * FUSED_HCH;
+                    double v = 0.0;
+                    if (e < ne) {
+                        unsigned long long *c = q.fq_C + (size_t)pr * q.fq_cstride + e0 + e;
+                        const long long iv = (long long)__ldcg(c);
+                        if (iv != 0) *c = 0ull;  // clear for the next pass
+                        const double r = fabs((double)(e0 + e - FT_PAD)) * hgrid;
+                        v = (double)iv * (1.0 / 268435456.0) * (r > 0.0 ? 1.0 / r : 1.0);
+                        any |= iv != 0;
+                    }
+                    cs_s[idx] = v;
+                }
+                if (__syncthreads_or(any) == 0) continue;  // an empty chunk (block-uniform)
+                if (m < nq) {
+                    const double sp0 = fma(s0, cth, -(c0 * sth));
+                    const int ezero = FT_PAD - e0;  // index of the r = 0 node in this chunk (if any)
+                    int a = 0, b = 0;
+                    for (int pr = 0; pr < ntp; ++pr) {
+                        double acc = 0.0, sn0 = s0, sp = sp0;
+#pragma unroll
+                        for (int e = 0; e < FUSED_HCH; ++e) {
+                            const double sv = (e < ezero) ? -sn0 : sn0;  // sin(Q |r|)
+                            acc = fma(cs_s[pr * FUSED_HCH + e], e == ezero ? Q : sv, acc);
+                            const double sn = fma(tc, sn0, -sp);
+                            sp = sn0;
+                            sn0 = sn;
+                        }
+                        tot = fma(acc, (double)ftab[(size_t)a * qp + m] * (double)ftab[(size_t)b * qp + m], tot);
+                        if (++b > a) { ++a; b = 0; }  // pair = a (a + 1) / 2 + b, a >= b
+                    }
+                    added = true;
+                }
+            }
+            if (added) fix_add2(q.fq.Sfix + m, q.fq.Sfix + qp + m, tot, q.fq.fix_scale);
+        }
+    } else {
+        if (has_item)
+            debye2_body<32, MODE_FQ, 8, CHEB, 1, true>(q.fq, smem_raw, (int)blockIdx.x, 0, ps, pl);
+        fused_stamp(q, 3, cs == scs);
+    }
     grid.sync();
     fused_stamp(q, 4, cs == scs);
 

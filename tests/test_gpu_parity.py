@@ -784,7 +784,9 @@ def test_fused_launch_equals_the_launch_sequence(potential):
         e0, s0, f0, r0 = res[0, 0]
         for key in ((1, 0), (1, 1)):
             e, sc, f, r = res[key]
-            assert abs(e - e0) < 1e-9 * abs(e0) and abs(sc - s0) < 1e-9 * abs(s0)
+            # (the fused launch sums F(Q) through its radial pair histogram: float32
+            # interpolation weights, 1e-7 of a pair's term)
+            assert abs(e - e0) < 1e-7 * abs(e0) and abs(sc - s0) < 1e-7 * abs(s0)
             assert nerr(f, f0) < 2e-6 and abs(r - r0) <= 1e-12 * max(1., abs(r0)), (key, nerr(f, f0))
         print('fused forces vs launch sequence:', potential, springs,
               nerr(res[1, 0][2], f0), nerr(res[1, 1][2], f0))
@@ -852,6 +854,56 @@ def test_fused_force_table_two_elements_and_far_pairs():
     n0 = be.launch_count()
     f32 = be.energy_forces(pos, target, 'rw', 1.)[2]
     assert be.launch_count() - n0 == 1 and nerr(f32, f64) < TOL32
+
+
+def test_fused_histogram_phase_against_direct_phase_and_fp64():
+    """The fused launch sums F(Q) through a radial pair histogram in shared
+    memory (iid_fused.cuh phase 1; the reference's pair sum is
+    pyiid/experiments/elasticscatter/kernels/cpu_flat.py:70-91).  Against the
+    direct pair pass of the same launch and the FP64 handle: one and two
+    elements, perturbed and perfectly symmetric positions (many pairs on one
+    node), bit-identical when repeated and whatever was evaluated before; a
+    structure whose bounding box exceeds the histogram keeps the direct pass."""
+    rs = np.random.RandomState(1)
+    cases = []
+    for atoms in (structures.icosahedron('Au', 3), structures.alloy_sphere(400, seed=3)):
+        ideal = atoms.copy()
+        atoms.positions = atoms.positions * 1.03 + rs.normal(0, 0.03, atoms.positions.shape)
+        cases.append((atoms, ideal))
+    sym = structures.icosahedron('Au', 4)
+    sym.positions *= 1.05
+    cases.append((sym, structures.icosahedron('Au', 4)))
+    for atoms, ideal in cases:
+        pos = atoms.get_positions()
+        be64, target = _fused_backend(atoms, ideal, 'fp64')
+        e64, s64, f64 = be64.energy_forces(pos, target, 'rw', 1.)[:3]
+        be, target = _fused_backend(atoms, ideal)
+        res = {}
+        for hist in (0, 1, 0, 1):
+            be.set_option('fused_hist', hist)
+            be.energy_forces(pos + 0.01, target, 'rw', 1.)  # another history each time
+            n0 = be.launch_count()
+            out = be.energy_forces(pos, target, 'rw', 1.)[:3]
+            assert be.launch_count() - n0 == 1
+            out = (out[0], out[1], np.array(out[2]))
+            if hist in res:
+                assert out[0] == res[hist][0] and out[1] == res[hist][1]
+                assert np.array_equal(out[2], res[hist][2])
+            res[hist] = out
+            assert abs(out[0] - e64) < 1e-6 * abs(e64) and abs(out[1] - s64) < 1e-6 * abs(s64)
+            assert nerr(out[2], f64) < TOL32
+        assert abs(res[1][0] - res[0][0]) < 1e-7 * abs(res[0][0])
+        assert nerr(res[1][2], res[0][2]) < 2e-6
+    # two clusters 1000 A apart: beyond the histogram either way, same bits
+    far = structures.icosahedron('Au', 2)
+    far.positions[30:] += [1000., 0., 0.]
+    be, target = _fused_backend(far, structures.icosahedron('Au', 2))
+    pos = far.get_positions()
+    out = {}
+    for hist in (0, 1):
+        be.set_option('fused_hist', hist)
+        out[hist] = be.energy_forces(pos, target, 'rw', 1.)[:3]
+    assert out[0][0] == out[1][0] and np.array_equal(np.array(out[0][2]), np.array(out[1][2]))
 
 
 def test_sq_iq_follow_the_reference_formulas():
@@ -1355,6 +1407,7 @@ def test_qspace_chain_rule_weights_equal_rspace(potential, precision):
     # launch's float64 radial table differs from it by the direct pass's own
     # rounding, checked below)
     be.set_option('fused_table', 0)
+    be.set_option('fused_hist', 0)  # (and the direct float32 F(Q) pass on both sides)
     for tg in targets:
         res = {}
         for q in (1, 0):
@@ -1371,3 +1424,4 @@ def test_qspace_chain_rule_weights_equal_rspace(potential, precision):
             be.set_option('fused_table', 0)
             assert e2 == e1 and s2 == s1 and nerr(f2, f1) < TOL32
     be.set_option('fused_table', 1)
+    be.set_option('fused_hist', 1)
