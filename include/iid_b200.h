@@ -102,6 +102,18 @@ int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
                       int64_t n_types, const double *ftable, int64_t nq,
                       double qbin);
 
+/* The same with a second table norm_table[n_types][nq] (NULL = ftable) for the
+ * normaliser: the pair sums use ftable, na uses norm_table.  For per-atom
+ * factors that multiply the pair term but not <f>^2 -- the Debye-Waller factor
+ * of isotropic atomic displacements, tau_ij(Q) = exp(-(u_i^2 + u_j^2) Q^2 / 2)
+ * = t_i t_j, in the reference's fq = norm * omega * tau
+ * (kernels/cpu_nxn.py:114-121 get_adp_fq, kernels/cpu_flat.py:156-174
+ * get_adp_grad_fq with grad_tau = 0): ftable rows = f t, norm_table rows = f,
+ * one row per (element, displacement) class. */
+int iid_set_structure_norm(iid_handle *h, int64_t n, const int32_t *type_index,
+                           int64_t n_types, const double *ftable,
+                           const double *norm_table, int64_t nq, double qbin);
+
 /* F(Q) -> G(r) as a dense real matrix T[nr][nq] (float64, host) reproducing
  * master_kernel.get_pdf_at_qmin :39-104 (zero below qmin, zero-pad, odd
  * extension, inverse FFT, linear re-binning onto rgrid, factor 2); the host

@@ -195,6 +195,69 @@ def wrap_fq_grad(positions, scatter, qbin, precision='fp32', na_mode=0,
     return rtn
 
 
+# --- atomic displacement parameters (the reference's unused kernels) ----------
+
+def pair_indices(n):
+    """(i, j), i > j, of the flattened pair list k = i (i - 1) / 2 + j
+    (kernels/__init__.py:15-19 k_to_ij)."""
+    i, j = np.tril_indices(n, -1)
+    return i, j
+
+
+def adp_tau(adps, nq, qbin, precision='fp32'):
+    """tau[K, Q] = exp(-(u_i^2 + u_j^2) Q^2 / 2) for isotropic mean-square
+    displacements adps[N] -- the Debye-Waller array the reference's
+    get_adp_fq / get_adp_grad_fq take as an INPUT (the reference itself builds
+    none: its wrappers pass adps = None, flat_multi_cpu_wrap.py:18-19)."""
+    dt = np.float32 if precision == 'fp32' else np.float64
+    u = np.asarray(adps, dtype=np.float64)
+    i, j = pair_indices(len(u))
+    sv = (dt(qbin) * np.arange(nq).astype(dt)).astype(np.float64)  # cpu_flat.py:93
+    return np.exp(-0.5 * (u[i] + u[j])[:, None] * sv[None, :] ** 2).astype(dt)
+
+
+def wrap_adp_fq(positions, scatter, adps, qbin, precision='fp32'):
+    """F(Q) with fq = norm * omega * tau (kernels/cpu_nxn.py:114-121 get_adp_fq),
+    summed and normalised as flat_serial_cpu_wrap.wrap_fq :52-69 (na from norm
+    alone).  numpy over all K pairs: small structures only."""
+    dt = np.float32 if precision == 'fp32' else np.float64
+    d, r, norm, omega = pair_internals(positions, scatter, qbin, precision)
+    tau = adp_tau(adps, norm.shape[1], qbin, precision)
+    fq = (norm * omega).astype(dt) * tau
+    final = fq.sum(axis=0, dtype=np.float64).astype(dt)
+    na = normaliser(scatter, precision, 0)
+    with np.errstate(all='ignore'):
+        final = np.nan_to_num(final / na)
+    return 2 * final
+
+
+def wrap_adp_grad_fq(positions, scatter, adps, qbin, precision='fp32'):
+    """grad F(Q) [N, 3, Q] with grad = norm * (tau * grad_omega + omega *
+    grad_tau) (kernels/cpu_flat.py:156-174 get_adp_grad_fq), grad_tau = 0 for
+    position-independent displacements; grad_omega as cpu_flat.py:117-131,
+    scatter-sum as cpu_experimental.py:8-15, / na as
+    flat_serial_cpu_wrap.py:129."""
+    dt = np.float32 if precision == 'fp32' else np.float64
+    d, r, norm, omega = pair_internals(positions, scatter, qbin, precision)
+    n, nq = np.asarray(scatter).shape
+    tau = adp_tau(adps, nq, qbin, precision)
+    sv = dt(qbin) * np.arange(nq).astype(dt)
+    with np.errstate(all='ignore'):
+        rr = r[:, None]
+        a = ((sv[None, :] * np.cos(sv[None, :] * rr).astype(dt)).astype(dt) - omega) / \
+            (rr * rr).astype(dt)
+    go = (a.astype(dt)[:, None, :] * d[:, :, None]).astype(dt)       # get_grad_omega
+    g = (norm[:, None, :] * (tau[:, None, :] * go).astype(dt)).astype(dt)  # grad_tau = 0
+    i, j = pair_indices(n)
+    rtn = np.zeros((n, 3, nq), dt)
+    np.subtract.at(rtn, i, g)
+    np.add.at(rtn, j, g)
+    na = normaliser(scatter, precision, 0)
+    with np.errstate(all='ignore'):
+        rtn = np.nan_to_num(rtn / na)
+    return rtn
+
+
 # --- float64 host stage: kernels/master_kernel.py ---------------------------
 
 def fft_gr_to_fq(g, rstep, rmin):

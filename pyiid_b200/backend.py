@@ -99,6 +99,25 @@ def element_table(scatter_array, numbers=None):
             np.ascontiguousarray(inv.reshape(-1), dtype=np.int32))
 
 
+ADP_CLASSES_MAX = 32
+
+
+def adp_tables(table, idx, adps, qbin):
+    """Per-(element, displacement) classes: pair table f(Q) exp(-u^2 Q^2 / 2),
+    normaliser table f(Q), class index per atom."""
+    nq = table.shape[1]
+    pairs = np.stack([idx.astype(np.float64), adps], axis=1)
+    classes, inv = np.unique(pairs, axis=0, return_inverse=True)
+    if len(classes) > ADP_CLASSES_MAX:
+        raise ValueError('%d distinct (element, displacement) classes; at most %d '
+                         '(atoms are tiled by class: quantise the displacements)'
+                         % (len(classes), ADP_CLASSES_MAX))
+    q = np.arange(nq, dtype=np.float64) * qbin
+    norm = np.ascontiguousarray(table[classes[:, 0].astype(int)], dtype=np.float64)
+    pair = np.ascontiguousarray(norm * np.exp(-0.5 * classes[:, 1:2] * q[None, :] ** 2))
+    return pair, norm, np.ascontiguousarray(inv.reshape(-1), dtype=np.int32)
+
+
 def visible_devices():
     """Number of CUDA devices the library sees (0 without a GPU)."""
     cnt = ctypes.c_int(0)
@@ -182,6 +201,7 @@ class Backend(object):
         self._last_scat = None
         self._last_qbin = None
         self._last_numbers = None
+        self._last_adps = None
         self._last_target = None
         self._target_key = None
         self._restraints = []
@@ -210,22 +230,42 @@ class Backend(object):
             self.rank, self.world = rank, world
 
     # -- cached state -------------------------------------------------------
-    def set_structure(self, scatter_array, numbers, qbin):
+    def set_structure(self, scatter_array, numbers, qbin, adps=None):
+        """``adps``: isotropic mean-square displacements <u^2> per atom (A^2) or
+        None.  Their Debye-Waller factor tau_ij(Q) = exp(-(u_i^2 + u_j^2) Q^2 / 2)
+        = t_i t_j multiplies the pair term, not the normaliser
+        (``get_adp_fq``, kernels/cpu_nxn.py:114-121): the pair sums get one table
+        row f t per (element, displacement) class, na the plain f."""
         scat = np.asarray(scatter_array)
+        if adps is not None:
+            adps = np.ascontiguousarray(adps, dtype=np.float64).reshape(-1)
+            if adps.shape[0] != scat.shape[0]:
+                raise ValueError('adps: one mean-square displacement per atom')
+            if not np.all(np.isfinite(adps)) or np.any(adps < 0):
+                raise ValueError('adps: mean-square displacements must be finite and >= 0')
+            if not np.any(adps):
+                adps = None
         # fast path: the very same (shared, read-only) table object as last time
         if scat is self._last_scat and float(qbin) == self._last_qbin and \
-                np.array_equal(numbers, self._last_numbers):
+                np.array_equal(numbers, self._last_numbers) and \
+                (adps is None) == (self._last_adps is None) and \
+                (adps is None or np.array_equal(adps, self._last_adps)):
             return
         table, idx = element_table(scat, numbers)
-        key = (scat.shape, float(qbin), idx.tobytes(), table.tobytes())
+        norm = None
+        if adps is not None:
+            table, norm, idx = adp_tables(table, idx, adps, float(qbin))
+        key = (scat.shape, float(qbin), idx.tobytes(), table.tobytes(),
+               None if norm is None else norm.tobytes())
         self._last_scat, self._last_qbin = scat, float(qbin)
         self._last_numbers = np.array(numbers)
+        self._last_adps = None if adps is None else adps.copy()
         if key == self._skey:
             return
         n, nq = scat.shape
-        check(self.lib.iid_set_structure(
-            self.h, n, idx.ctypes.data, table.shape[0], table.ctypes.data, nq,
-            float(qbin)))
+        check(self.lib.iid_set_structure_norm(
+            self.h, n, idx.ctypes.data, table.shape[0], table.ctypes.data,
+            None if norm is None else norm.ctypes.data, nq, float(qbin)))
         if nq != self.nq:
             self._tkey = None
             self.nr = 0

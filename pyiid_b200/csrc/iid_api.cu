@@ -240,7 +240,8 @@ static void chain_drain(iid_handle *h);
 static int multi_destroy(iid_handle *h);
 static int multi_need_subs(iid_handle *h, int count);
 static int multi_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
-                               int64_t n_types, const double *ftable, int64_t nq, double qbin);
+                               int64_t n_types, const double *ftable, const double *norm_table,
+                               int64_t nq, double qbin);
 static int multi_set_transform(iid_handle *h, int64_t nr, int64_t nq, const double *T);
 static int multi_fq_host(iid_handle *h, const double *pos_host, double *F_host, double *pdf_host);
 static int multi_grad_fq_host(iid_handle *h, const double *pos_host, void *G_host,
@@ -845,7 +846,20 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
                                  int64_t n_types, const double *ftable, int64_t nq,
                                  double qbin)
 {
-    if (MULTI(h)) return multi_set_structure(h, n, type_index, n_types, ftable, nq, qbin);
+    return iid_set_structure_norm(h, n, type_index, n_types, ftable, nullptr, nq, qbin);
+}
+
+// The pair sums take ftable, the normaliser na takes norm_table (null: ftable).  The
+// two differ when a per-atom factor multiplies the pair term but not <f>^2: the
+// Debye-Waller factor tau = t_i t_j of isotropic displacements in
+// fq = norm * omega * tau (kernels/cpu_nxn.py:114-121), with norm = f_i f_j alone
+// in na (flat_multi_cpu_wrap.py:52-55).
+extern "C" int iid_set_structure_norm(iid_handle *h, int64_t n, const int32_t *type_index,
+                                      int64_t n_types, const double *ftable,
+                                      const double *norm_table, int64_t nq, double qbin)
+{
+    if (MULTI(h))
+        return multi_set_structure(h, n, type_index, n_types, ftable, norm_table, nq, qbin);
     NEED(h);
     if (n < 1 || n_types < 1 || nq < 1 || !type_index || !ftable)
         return fail(IID_E_BADARG, "bad structure arguments");
@@ -868,7 +882,7 @@ extern "C" int iid_set_structure(iid_handle *h, int64_t n, const int32_t *type_i
     for (int64_t m = 0; m < nq; ++m) {
         double s1 = 0.0, s2 = 0.0;
         for (int64_t e = 0; e < n_types; ++e) {
-            const double f = ftable[e * nq + m];
+            const double f = (norm_table ? norm_table : ftable)[e * nq + m];
             s1 += (double)count[e] * f;
             s2 += (double)count[e] * f * f;
         }
@@ -3019,7 +3033,8 @@ static int multi_destroy(iid_handle *h)
 }
 
 static int multi_set_structure(iid_handle *h, int64_t n, const int32_t *type_index,
-                               int64_t n_types, const double *ftable, int64_t nq, double qbin)
+                               int64_t n_types, const double *ftable, const double *norm_table,
+                               int64_t nq, double qbin)
 {
     // small structures do not amortise the per-device launches and the host
     // hops: about 1500 atoms per device at least
@@ -3035,7 +3050,7 @@ static int multi_set_structure(iid_handle *h, int64_t n, const int32_t *type_ind
         iid_handle *sh = h->subs[d];
         sh->rank = d;  // before the structure: the row jobs are built once
         sh->world = active;
-        int rc = iid_set_structure(sh, n, type_index, n_types, ftable, nq, qbin);
+        int rc = iid_set_structure_norm(sh, n, type_index, n_types, ftable, norm_table, nq, qbin);
         if (rc) return rc;
     }
     if (nq != h->nq) h->nr = 0;

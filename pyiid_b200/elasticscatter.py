@@ -217,8 +217,34 @@ class ElasticScatter(object):
         scat = atoms.get_array(name, copy=False) if hasattr(atoms, 'arrays') \
             else atoms.get_array(name)
         be = self._be('fq' if sum_type == 'fq' else 'pdf')
-        be.set_structure(scat, atoms.numbers, qbin)
+        be.set_structure(scat, atoms.numbers, qbin, self._adps(atoms))
         return be
+
+    @staticmethod
+    def _adps(atoms):
+        """Isotropic atomic displacement parameters: ``atoms.set_array('adps',
+        u2)`` with the mean-square displacement <u^2> of every atom in A^2
+        (or ``None``).  The reference carries an ``adps`` slot through its
+        wrappers that is always ``None`` (``flat_multi_cpu_wrap.py:9-19``) and
+        two kernels nothing calls, ``get_adp_fq`` (``kernels/cpu_nxn.py:114-121``:
+        fq = norm * omega * tau) and ``get_adp_grad_fq``
+        (``kernels/cpu_flat.py:156-174``: norm * (tau * grad_omega + omega *
+        grad_tau)); it defines no tau.  Here tau_ij(Q) = exp(-(u_i^2 + u_j^2)
+        Q^2 / 2), the Debye-Waller factor of uncorrelated isotropic
+        displacements: independent of the positions (grad_tau = 0) and a product
+        t_i t_j, so it folds into the form-factor table of the pair sums while
+        the normaliser keeps the plain f."""
+        arrays = getattr(atoms, 'arrays', None)
+        if not arrays or 'adps' not in arrays:
+            return None
+        adps = np.asarray(arrays['adps'], dtype=np.float64)
+        if adps.ndim == 2 and adps.shape[1] == 1:
+            adps = adps[:, 0]
+        if adps.ndim != 1:
+            raise ValueError("'adps' must hold one isotropic mean-square displacement "
+                             "per atom (shape [N]); anisotropic displacements are not "
+                             "defined by the reference")
+        return adps
 
     def _wrap_fq(self, atoms, qbin=.1, sum_type='fq'):
         """``wrap_fq(atoms, qbin, sum_type) -> float32 [Qbins]``
