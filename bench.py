@@ -433,8 +433,9 @@ def config3_extra():
     roof['fq_hist_fp32'] = {'achieved': pairq / t, 'unit': UNIT, 'peak': None, 'frac': None,
                             'pairs_per_s': 0.5 * n * (n - 1) / t,
                             'note': 'the shipped F(Q) pass at this size: radial pair histogram, '
-                                    'O(N^2 + K Q) -- no pair*Q bound applies; it is bound by 24 '
-                                    '32-bit shared-memory atomics per pair (the atomic unit issues one per ~5 cycles per SM), '
+                                    'O(N^2 + K Q) -- no pair*Q bound applies; it is bound by 16 '
+                                    '32-bit shared-memory atomics per pair (8-point stencil on the fine grid; '
+                                    'the atomic unit issues one per ~6 cycles per SM), '
                                     '%.1f SM cycles per pair' % (t * sms * clk / (0.5 * n * (n - 1)))}
     t = out['fq_grad_kernel_ms_fp32'] * 1e-3
     roof['fq_grad_fp32'] = {'achieved': pairq / t, 'peak': sms * clk * 8, 'unit': UNIT,

@@ -124,9 +124,15 @@ int iid_set_transform(iid_handle *h, int64_t nr, int64_t nq, const double *T);
 /* Host-only: the Lagrange weights w[n_points] of the radial stencil for a
  * point u in [0, 1) past grid node k (node k - left + i gets w[i]) and the grid
  * step in units of 1/Q_max.  The fused evaluation's force table interpolates
- * with this stencil and the F(Q) pair histogram spreads with it; w must hold
- * at least 16 doubles. */
+ * with this stencil, its F(Q) phase and the F(Q) pair histogram of structures
+ * beyond the fine grid spread with it; w must hold at least 16 doubles. */
 int iid_stencil_weights(double u, double *w, int *n_points, int *left, double *qmax_h);
+
+/* Host-only: the same for the SHORTER stencil on a FINER grid with which the
+ * F(Q) pair histogram of a large structure spreads when the structure fits it
+ * (8 points, Q_max h = 0.157: the same 4e-10 bound with 16 instead of 24
+ * shared-memory atomics per pair; otherwise it uses the stencil above). */
+int iid_hist_stencil_weights(double u, double *w, int *n_points, int *left, double *qmax_h);
 
 /* Host-only (no device): the sharding plan iid_set_structure + iid_set_shard
  * would produce -- total work items, this rank's items and the (i, j) slots

@@ -153,7 +153,7 @@ struct iid_handle {
     // F(Q) pass through a radial pair histogram (iid_fq_hist.cuh): FP32 mode, large structures
     bool fq_hist = true;
     int64_t fq_hist_min_n = 1200;
-    double *hist_info = nullptr;            // [4] grid step, its inverse, nodes in use, gate
+    double *hist_info = nullptr;            // [8] grid step, its inverse, nodes in use, gate, stencil points
     unsigned long long *hist_C = nullptr;   // [element pairs][FH_CAP] fixed point, zero between passes
     int *hist_order = nullptr;              // [n_items_tri] item indices sorted by element pair
     double *hist_Spart = nullptr;           // [element pairs][chunks][qp] partial sums of the transform
@@ -273,6 +273,27 @@ extern "C" int iid_stencil_weights(double u, double *w, int *n_points, int *left
     if (n_points) *n_points = FT_PTS;
     if (left) *left = FT_LEFT;
     if (qmax_h) *qmax_h = FT_QH;
+    return 0;
+}
+// Host-only: the same for the fine-grid stencil of the F(Q) pair histogram
+// (FH_PTS_FINE points, Q_max h = FH_QH_FINE; iid_fq_hist.cuh).
+extern "C" int iid_hist_stencil_weights(double u, double *w, int *n_points, int *left,
+                                        double *qmax_h)
+{
+    if (!w) return fail(IID_E_BADARG, "null pointer");
+    constexpr int P = FH_PTS_FINE, LEFT = P / 2 - 1;
+    double d[P], pre[P];
+    for (int i = 0; i < P; ++i) d[i] = u - (double)(i - LEFT);
+    pre[0] = 1.0;
+    for (int i = 1; i < P; ++i) pre[i] = pre[i - 1] * d[i - 1];
+    double suf = 1.0;
+    for (int i = P - 1; i >= 0; --i) {
+        w[i] = lagrange_bary<P>(i) * pre[i] * suf;
+        suf *= d[i];
+    }
+    if (n_points) *n_points = P;
+    if (left) *left = LEFT;
+    if (qmax_h) *qmax_h = FH_QH_FINE;
     return 0;
 }
 extern "C" const char *iid_last_error(void) { return g_err.c_str(); }
@@ -1185,12 +1206,12 @@ static int fq_hist_prepare(iid_handle *h)
     const int ntp = (int)(h->ntypes * (h->ntypes + 1) / 2);
     constexpr int NCHUNK = FH_NCHUNK;
     if (!h->hist_info) {
-        if ((rc = dev_alloc(&h->hist_info, 4)) ||
+        if ((rc = dev_alloc(&h->hist_info, 8)) ||
             (rc = dev_alloc(&h->hist_C, (size_t)ntp * FH_CAP)) ||
             (rc = dev_alloc(&h->hist_Spart, (size_t)ntp * NCHUNK * h->qp)))
             return rc;
         CU(cudaMemset(h->hist_C, 0, (size_t)ntp * FH_CAP * sizeof(unsigned long long)));
-        CU(cudaMemset(h->hist_info, 0, 4 * sizeof(double)));
+        CU(cudaMemset(h->hist_info, 0, 8 * sizeof(double)));
         CU(cudaStreamSynchronize(0));
         static bool attr_done[64] = {false};
         if (!attr_done[h->device & 63]) {

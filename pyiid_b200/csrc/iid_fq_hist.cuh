@@ -12,13 +12,19 @@
 //                                                     each pair spreads its unit
 //                                                     weight over 12 grid nodes)
 //
-//   1. fq_hist_grid_kernel   bounding box -> number of nodes in use
-//   2. fq_hist_kernel        O(N^2): float64 distance, 12 float32 weights, 24
+//   1. fq_hist_grid_kernel   bounding box -> stencil, grid step, nodes in use
+//   2. fq_hist_kernel        O(N^2): float64 distance, P float32 weights, 2 P
 //                            shared-memory integer atomics per pair
 //   3. fq_hist_transform_kernel  O(K Q): S_ab from C_ab in float64, per-block
 //                            partial sums for reduce_spart_kernel (fixed order)
 //
-// instead of ~830 instructions per pair over 330 bins.  The histogram is FIXED
+// instead of ~830 instructions per pair over 330 bins.  The pass is bound by the
+// shared-memory atomic unit (one warp-wide atomic per ~5.7 cycles per SM), i.e. by
+// the NUMBER of stencil points: when the structure fits the shared-memory
+// histogram on the finer grid Q_max h = 0.157 (154 A at Q_max = 25: 140 000 atoms
+// of gold) it spreads with P = 8 points -- the same 4e-10 bound, 16 atomics per
+// pair -- else with the 12 points of the coarse grid Q_max h = 1/3 (327 A).
+// The histogram is FIXED
 // POINT (units of 2^-28): integer addition commutes, so F(Q) is bit-reproducible
 // whatever the order of the atomics; the only native shared-memory atomic add is
 // 32 bits wide, so a node is two words, high (units of 2^-12) and low (16 bits),
@@ -52,25 +58,27 @@ struct HistParams {
     int stride;
 };
 
-// One pair: its unit weight over the nodes k - FT_LEFT .. k + FT_PTS - 1 - FT_LEFT of
-// a two-word fixed-point histogram in shared memory (units of 2^-28; high word
-// 2^-12, low word 16 bits).  u in [0, 1) past node k.
+// One pair: its unit weight over the nodes k - P/2 + 1 .. k + P/2 of a two-word
+// fixed-point histogram in shared memory (units of 2^-28; high word 2^-12, low
+// word 16 bits) that stores P/2 nodes before r = 0.  u in [0, 1) past node k.
+template <int P>
 __device__ __forceinline__ void fq_hist_spread(int *hi_s, unsigned *lo_s, int k, float u)
 {
+    constexpr int LEFT = P / 2 - 1, PAD = P / 2;
     // Lagrange weights (barycentric form by prefix / suffix products; float32: 1e-7
     // of a unit weight)
-    float d[FT_PTS], pre[FT_PTS];
+    float d[P], pre[P];
 #pragma unroll
-    for (int i = 0; i < FT_PTS; ++i) d[i] = u - (float)(i - FT_LEFT);
+    for (int i = 0; i < P; ++i) d[i] = u - (float)(i - LEFT);
     pre[0] = 1.f;
 #pragma unroll
-    for (int i = 1; i < FT_PTS; ++i) pre[i] = pre[i - 1] * d[i - 1];
+    for (int i = 1; i < P; ++i) pre[i] = pre[i - 1] * d[i - 1];
     float suf = 1.f;
-    int *hp = hi_s + (k - FT_LEFT + FT_PAD);
-    unsigned *lp = lo_s + (k - FT_LEFT + FT_PAD);
+    int *hp = hi_s + (k - LEFT + PAD);
+    unsigned *lp = lo_s + (k - LEFT + PAD);
 #pragma unroll
-    for (int i = FT_PTS - 1; i >= 0; --i) {
-        const float w = (float)ft_bary(i) * 268435456.f * pre[i] * suf;  // 2^28
+    for (int i = P - 1; i >= 0; --i) {
+        const float w = (float)lagrange_bary<P>(i) * 268435456.f * pre[i] * suf;  // 2^28
         suf *= d[i];
         const int q = __float2int_rn(w);
         atomicAdd(hp + i, q >> 16);             // floor: q = hi 2^16 + lo
@@ -78,12 +86,14 @@ __device__ __forceinline__ void fq_hist_spread(int *hi_s, unsigned *lo_s, int k,
     }
 }
 
-// info[0] = h, info[1] = 1/h, info[2] = K (nodes r = 0 .. (K-1) h), info[3] = gate
+// info[0] = h, info[1] = 1/h, info[2] = K (nodes r = 0 .. (K-1) h), info[3] = gate,
+// info[4] = stencil points (FH_PTS_FINE on the fine grid when the structure fits it,
+// else FT_PTS on the grid of step h12)
 __global__ void __launch_bounds__(1024) fq_hist_grid_kernel(const double *__restrict__ x,
                                                             const double *__restrict__ y,
                                                             const double *__restrict__ z,
                                                             const float *__restrict__ valid,
-                                                            int np, double h, double *info)
+                                                            int np, double h12, double *info)
 {
     __shared__ double smin[3][32], smax[3][32];
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -128,19 +138,26 @@ __global__ void __launch_bounds__(1024) fq_hist_grid_kernel(const double *__rest
         double m = 0.0;
         for (int k = 0; k < (int)(blockDim.x >> 5); ++k) m = fmax(m, rad[k]);
         const double rmax = 2.0 * sqrt(m) * 1.0000001 + 1e-9;  // longest possible pair distance
-        const double K = ceil(rmax / h) + (double)(FT_PTS + 2);
+        // (a function of the positions alone: the same structure takes the same
+        // stencil, whatever was evaluated before)
+        const double h8 = h12 * (FH_QH_FINE / FT_QH);
+        const double K8 = ceil(rmax / h8) + (double)(FH_PTS_FINE + 2);
+        const double K12 = ceil(rmax / h12) + (double)(FT_PTS + 2);
+        const bool fine = K8 <= (double)(FH_CAP - FH_PTS_FINE);
+        const double h = fine ? h8 : h12, K = fine ? K8 : K12;
+        const double cap = (double)(FH_CAP - (fine ? FH_PTS_FINE : FT_PTS));
         info[0] = h;
         info[1] = 1.0 / h;
-        info[2] = fmin(K, (double)(FH_CAP - 2 * FT_PAD));
-        info[3] = K <= (double)(FH_CAP - 2 * FT_PAD) ? 1.0 : 0.0;
+        info[2] = fmin(K, cap);
+        info[3] = K <= cap ? 1.0 : 0.0;
+        info[4] = fine ? (double)FH_PTS_FINE : (double)FT_PTS;
     }
 }
 
-__global__ void __launch_bounds__(FH_THREADS, 1) fq_hist_kernel(const HistParams p)
+template <int P>
+__device__ __forceinline__ void fq_hist_body(const HistParams &p, unsigned char *smem_raw)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (p.info[3] == 0.0) return;  // the structure does not fit: the direct kernel runs
-    const int K = (int)p.info[2], Kp = K + 2 * FT_PAD;
+    const int K = (int)p.info[2], Kp = K + P;  // P/2 nodes before r = 0, P/2 past the last
     const double inv_h = p.info[1];
     int *hi_s = reinterpret_cast<int *>(smem_raw);      // [Kp] units of 2^-12
     unsigned *lo_s = reinterpret_cast<unsigned *>(hi_s + FH_CAP);  // [Kp] units of 2^-28, < 2^16 per add
@@ -199,7 +216,7 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fq_hist_kernel(const HistParams
                     const double tpos = r2 * y * inv_h;
                     const int k = (int)tpos;
                     const float u = (float)(tpos - (double)k);
-                    fq_hist_spread(hi_s, lo_s, k, u);
+                    fq_hist_spread<P>(hi_s, lo_s, k, u);
                 }
             }
             since_fold += (unsigned)blockDim.x;
@@ -215,6 +232,14 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fq_hist_kernel(const HistParams
         }
     }
     if (cur_pair >= 0) flush(cur_pair);
+}
+
+__global__ void __launch_bounds__(FH_THREADS, 1) fq_hist_kernel(const HistParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (p.info[3] == 0.0) return;  // the structure does not fit: the direct kernel runs
+    if (p.info[4] == (double)FH_PTS_FINE) fq_hist_body<FH_PTS_FINE>(p, smem_raw);
+    else fq_hist_body<FT_PTS>(p, smem_raw);
 }
 
 // S_ab[m] from C_ab: block (chunk, pair) sums its FHT_E nodes for every Q bin in
@@ -236,7 +261,8 @@ __global__ void __launch_bounds__(384) fq_hist_transform_kernel(
     double *out = Spart + ((size_t)pair * gridDim.x + blockIdx.x) * qp;
     const int m = threadIdx.x;
     const bool on = info[3] != 0.0;
-    const int Kp = (int)info[2] + 2 * FT_PAD;
+    const int pad = (int)info[4] / 2;  // nodes stored before r = 0
+    const int Kp = (int)info[2] + 2 * pad;
     const int e0 = blockIdx.x * FHT_E;
     if (!on || e0 >= Kp) {  // block-uniform
         if (m < qp) out[m] = 0.0;
@@ -249,7 +275,7 @@ __global__ void __launch_bounds__(384) fq_hist_transform_kernel(
         unsigned long long *c = C + (size_t)pair * stride + e0 + e;
         const long long v = (long long)*c;
         *c = 0ull;
-        const double r = fabs((double)(e0 + e - FT_PAD)) * h;  // the spread is even in r
+        const double r = fabs((double)(e0 + e - pad)) * h;  // the spread is even in r
         cs[e] = (double)v * (1.0 / 268435456.0) * (r > 0.0 ? 1.0 / r : 1.0);
         any |= v != 0;
     }
@@ -262,11 +288,11 @@ __global__ void __launch_bounds__(384) fq_hist_transform_kernel(
         const double turn = Q * h * 0.15915494309189533577;
         double sth, cth, s, c;
         sincospi(2.0 * (turn - rint(turn)), &sth, &cth);
-        const double t0 = turn * (double)(e0 - FT_PAD);
+        const double t0 = turn * (double)(e0 - pad);
         sincospi(2.0 * (t0 - rint(t0)), &s, &c);
         double sp = fma(s, cth, -(c * sth));  // node e0 - 1
         const double tc = cth + cth;
-        const int ezero = FT_PAD - e0;  // index of the r = 0 node in this chunk (if any)
+        const int ezero = pad - e0;  // index of the r = 0 node in this chunk (if any)
         for (int e = 0; e < ne; ++e) {
             // |r|: sin(Q |r|) = sign(r) sin(Q r)
             const double sv = (e < ezero) ? -s : s;

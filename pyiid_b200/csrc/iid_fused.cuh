@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(384, 1) fused_eval_kernel(const FusedParams q)
                         y = y * fma(-0.5 * r2, y * y, 1.5);  // second Newton step: 1e-15
                         const double tpos = r2 * y * inv_h;
                         const int k = (int)tpos;
-                        fq_hist_spread(hi_s, lo_s, k, (float)(tpos - (double)k));
+                        fq_hist_spread<FT_PTS>(hi_s, lo_s, k, (float)(tpos - (double)k));
                     }
                 }
             }

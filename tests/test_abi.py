@@ -100,25 +100,29 @@ def test_small_structures_get_a_single_wave_triangle_list():
         assert (total <= 148) == one_wave, (n, total)
 
 
-def test_radial_stencil_interpolates_band_limited_functions():
-    """The Lagrange stencil shared by the fused kernel's force table and the
-    F(Q) pair histogram (iid_stencil.cuh): the weights are a partition of unity,
-    reproduce polynomials, and interpolate sin(Q r)/r on a grid with
-    Q_max h = 1/3 to 4e-10 of its amplitude -- the figure DESIGN.md quotes."""
+@pytest.mark.parametrize('fn,points,lft0,qh0', [('iid_stencil_weights', 12, 5, 1. / 3.),
+                                                ('iid_hist_stencil_weights', 8, 3, 0.157)])
+def test_radial_stencil_interpolates_band_limited_functions(fn, points, lft0, qh0):
+    """The Lagrange stencils of iid_stencil.cuh -- 12 points on the grid
+    Q_max h = 1/3 (force table of the fused kernel, coarse-grid pair histogram)
+    and 8 points on the grid Q_max h = 0.157 (fine-grid pair histogram): the
+    weights are a partition of unity, reproduce polynomials, and interpolate
+    sin(Q r)/r to 4e-10 of its amplitude -- the figure DESIGN.md quotes."""
     lib = _lib.load()
+    weights = getattr(lib, fn)
     w = np.zeros(16)
     npts, left = ctypes.c_int(0), ctypes.c_int(0)
     qh = ctypes.c_double(0.)
-    assert lib.iid_stencil_weights(0.25, w.ctypes.data, ctypes.byref(npts), ctypes.byref(left),
-                                   ctypes.byref(qh)) == 0
+    assert weights(0.25, w.ctypes.data, ctypes.byref(npts), ctypes.byref(left),
+                   ctypes.byref(qh)) == 0
     n, lft, qmax_h = npts.value, left.value, qh.value
-    assert n == 12 and lft == 5 and abs(qmax_h - 1. / 3.) < 1e-15
+    assert n == points and lft == lft0 and abs(qmax_h - qh0) < 1e-15
     rs = np.random.RandomState(0)
     qmax, worst = 25., 0.
     h = qmax_h / qmax
     for _ in range(400):
         u, k = rs.rand(), rs.randint(0, 9000)
-        assert lib.iid_stencil_weights(u, w.ctypes.data, None, None, None) == 0
+        assert weights(u, w.ctypes.data, None, None, None) == 0
         ww = w[:n]
         assert abs(ww.sum() - 1.) < 1e-12
         nodes = (k - lft + np.arange(n)) * h
@@ -130,7 +134,7 @@ def test_radial_stencil_interpolates_band_limited_functions():
             worst = max(worst, abs(ww.dot(g) - exact) / q)
     assert worst < 4e-10, worst
     # at a node the stencil is the identity
-    assert lib.iid_stencil_weights(0., w.ctypes.data, None, None, None) == 0
+    assert weights(0., w.ctypes.data, None, None, None) == 0
     assert abs(w[lft] - 1.) < 1e-15 and np.abs(np.delete(w[:n], lft)).max() < 1e-15
 
 
