@@ -41,7 +41,7 @@
 
 namespace iid {
 
-constexpr int FH_THREADS = 512;
+constexpr int FH_THREADS = 1024;  // 32 warps per SM: the loads and weights of one warp hide behind the others' atomics
 constexpr int FH_CAP = 24576;  // nodes of the shared-memory histogram (2 x 4 B each)
 constexpr unsigned FH_FOLD_PAIRS = 49152;    // low word: 65 535 per add, 2^32 / 65 535 adds
 constexpr unsigned FH_FLUSH_PAIRS = 393216;  // high word: <= 4 916 per add (+ carries)
@@ -203,11 +203,27 @@ __device__ __forceinline__ void fq_hist_body(const HistParams &p, unsigned char 
         const int gi = it.itile * TILE_I + lane;
         const double xi = p.x[gi], yi = p.y[gi], zi = p.z[gi];
         const bool vi = p.valid[gi] != 0.f;
+        // the j atom of the NEXT trip is loaded before this trip's pair is spread: the
+        // load's latency (ncu: long-scoreboard stalls at the loop head, 29 % of the
+        // samples once the atomics were down to 16 per pair) hides behind the atomics
+        double xj = 0.0, yj = 0.0, zj = 0.0;
+        bool vj = false;
+        if (it.jbegin + warp < it.jend) {
+            const int g0 = it.jbegin + warp;
+            xj = p.x[g0]; yj = p.y[g0]; zj = p.z[g0];
+            vj = p.valid[g0] != 0.f;
+        }
         for (int j0 = it.jbegin; j0 < it.jend; j0 += nw) {
-            const int gj = j0 + warp;
+            const int gj = j0 + warp, gn = gj + nw;
+            double xn = 0.0, yn = 0.0, zn = 0.0;
+            bool vn = false;
+            if (gn < it.jend) {
+                xn = p.x[gn]; yn = p.y[gn]; zn = p.z[gn];
+                vn = p.valid[gn] != 0.f;
+            }
             // a diagonal item holds both orders of its pairs: count i > j
-            if (gj < it.jend && vi && p.valid[gj] != 0.f && (!diag || gj < gi)) {
-                const double dx = p.x[gj] - xi, dy = p.y[gj] - yi, dz = p.z[gj] - zi;
+            if (gj < it.jend && vi && vj && (!diag || gj < gi)) {
+                const double dx = xj - xi, dy = yj - yi, dz = zj - zi;
                 const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
                 if (r2 > 0.0) {
                     double y = (double)rsqrtf((float)r2);
@@ -219,6 +235,7 @@ __device__ __forceinline__ void fq_hist_body(const HistParams &p, unsigned char 
                     fq_hist_spread<P>(hi_s, lo_s, k, u);
                 }
             }
+            xj = xn; yj = yn; zj = zn; vj = vn;
             since_fold += (unsigned)blockDim.x;
             since_flush += (unsigned)blockDim.x;
             if (since_fold >= FH_FOLD_PAIRS) {
