@@ -128,11 +128,13 @@ int iid_set_transform(iid_handle *h, int64_t nr, int64_t nq, const double *T);
  * beyond the fine grid spread with it; w must hold at least 16 doubles. */
 int iid_stencil_weights(double u, double *w, int *n_points, int *left, double *qmax_h);
 
-/* Host-only: the same for the SHORTER stencil on a FINER grid with which the
- * F(Q) pair histogram of a large structure spreads when the structure fits it
- * (8 points, Q_max h = 0.157: the same 4e-10 bound with 16 instead of 24
- * shared-memory atomics per pair; otherwise it uses the stencil above). */
-int iid_hist_stencil_weights(double u, double *w, int *n_points, int *left, double *qmax_h);
+/* Host-only: the same for the stencils with which the F(Q) pair histogram of a
+ * large structure spreads -- the shortest stencil / finest grid the structure
+ * fits: tier 0 = 6 points, Q_max h = 0.0658; tier 1 = 8 points, Q_max h = 0.157;
+ * tier 2 = the 12 points above.  All three keep the 4e-10 bound; the pass costs
+ * two shared-memory atomics per point and pair. */
+int iid_hist_stencil_weights(int tier, double u, double *w, int *n_points, int *left,
+                             double *qmax_h);
 
 /* Host-only (no device): the sharding plan iid_set_structure + iid_set_shard
  * would produce -- total work items, this rank's items and the (i, j) slots

@@ -41,7 +41,7 @@ SIGNATURES = {
     'iid_set_structure_norm': [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _dbl],
     'iid_set_transform': [_vp, _i64, _i64, _vp],
     'iid_stencil_weights': [_dbl, _vp, _vp, _vp, _vp],
-    'iid_hist_stencil_weights': [_dbl, _vp, _vp, _vp, _vp],
+    'iid_hist_stencil_weights': [_int, _dbl, _vp, _vp, _vp, _vp],
     'iid_plan_shard': [_i64, _vp, _i64, _int, _int, _int, _int, _pi64, _pi64,
                        _pi64, _pi64],
     'iid_plan_rows': [_i64, _vp, _i64, _int, _int, _int, _int, _pi64, _pi64, _pi64,

@@ -275,13 +275,13 @@ extern "C" int iid_stencil_weights(double u, double *w, int *n_points, int *left
     if (qmax_h) *qmax_h = FT_QH;
     return 0;
 }
-// Host-only: the same for the fine-grid stencil of the F(Q) pair histogram
-// (FH_PTS_FINE points, Q_max h = FH_QH_FINE; iid_fq_hist.cuh).
-extern "C" int iid_hist_stencil_weights(double u, double *w, int *n_points, int *left,
-                                        double *qmax_h)
+// Host-only: the same for the stencils of the F(Q) pair histogram (iid_fq_hist.cuh):
+// tier 0 = the finest grid (FH_PTS_FINEST points), 1 = the fine grid (FH_PTS_FINE),
+// 2 = the coarse grid (FT_PTS points, the stencil above).
+template <int P>
+static void hist_stencil(double u, double *w)
 {
-    if (!w) return fail(IID_E_BADARG, "null pointer");
-    constexpr int P = FH_PTS_FINE, LEFT = P / 2 - 1;
+    constexpr int LEFT = P / 2 - 1;
     double d[P], pre[P];
     for (int i = 0; i < P; ++i) d[i] = u - (double)(i - LEFT);
     pre[0] = 1.0;
@@ -291,9 +291,18 @@ extern "C" int iid_hist_stencil_weights(double u, double *w, int *n_points, int 
         w[i] = lagrange_bary<P>(i) * pre[i] * suf;
         suf *= d[i];
     }
-    if (n_points) *n_points = P;
-    if (left) *left = LEFT;
-    if (qmax_h) *qmax_h = FH_QH_FINE;
+}
+extern "C" int iid_hist_stencil_weights(int tier, double u, double *w, int *n_points, int *left,
+                                        double *qmax_h)
+{
+    if (!w || tier < 0 || tier > 2) return fail(IID_E_BADARG, "null pointer or unknown tier");
+    const int pts = tier == 0 ? FH_PTS_FINEST : tier == 1 ? FH_PTS_FINE : FT_PTS;
+    if (tier == 0) hist_stencil<FH_PTS_FINEST>(u, w);
+    else if (tier == 1) hist_stencil<FH_PTS_FINE>(u, w);
+    else hist_stencil<FT_PTS>(u, w);
+    if (n_points) *n_points = pts;
+    if (left) *left = pts / 2 - 1;
+    if (qmax_h) *qmax_h = tier == 0 ? FH_QH_FINEST : tier == 1 ? FH_QH_FINE : FT_QH;
     return 0;
 }
 extern "C" const char *iid_last_error(void) { return g_err.c_str(); }

@@ -20,10 +20,10 @@
 //
 // instead of ~830 instructions per pair over 330 bins.  The pass is bound by the
 // shared-memory atomic unit (one warp-wide atomic per ~5.7 cycles per SM), i.e. by
-// the NUMBER of stencil points: when the structure fits the shared-memory
-// histogram on the finer grid Q_max h = 0.157 (154 A at Q_max = 25: 140 000 atoms
-// of gold) it spreads with P = 8 points -- the same 4e-10 bound, 16 atomics per
-// pair -- else with the 12 points of the coarse grid Q_max h = 1/3 (327 A).
+// the NUMBER of stencil points: the pass takes the shortest stencil of
+// iid_stencil.cuh whose grid fits the shared-memory histogram -- 6 points up to
+// 75 A at Q_max = 25, 8 points up to 182 A, the 12 points of the coarse grid up to
+// 327 A; all three keep the 4e-10 bound.
 // The histogram is FIXED
 // POINT (units of 2^-28): integer addition commutes, so F(Q) is bit-reproducible
 // whatever the order of the atomics; the only native shared-memory atomic add is
@@ -42,7 +42,7 @@
 namespace iid {
 
 constexpr int FH_THREADS = 1024;  // 32 warps per SM: the loads and weights of one warp hide behind the others' atomics
-constexpr int FH_CAP = 24576;  // nodes of the shared-memory histogram (2 x 4 B each)
+constexpr int FH_CAP = 28672;  // nodes of the shared-memory histogram (2 x 4 B each: 224 KB)
 constexpr unsigned FH_FOLD_PAIRS = 49152;    // low word: 65 535 per add, 2^32 / 65 535 adds
 constexpr unsigned FH_FLUSH_PAIRS = 393216;  // high word: <= 4 916 per add (+ carries)
 
@@ -87,8 +87,8 @@ __device__ __forceinline__ void fq_hist_spread(int *hi_s, unsigned *lo_s, int k,
 }
 
 // info[0] = h, info[1] = 1/h, info[2] = K (nodes r = 0 .. (K-1) h), info[3] = gate,
-// info[4] = stencil points (FH_PTS_FINE on the fine grid when the structure fits it,
-// else FT_PTS on the grid of step h12)
+// info[4] = stencil points: the shortest stencil / finest grid of iid_stencil.cuh the
+// structure fits (6, 8 or 12 points)
 __global__ void __launch_bounds__(1024) fq_hist_grid_kernel(const double *__restrict__ x,
                                                             const double *__restrict__ y,
                                                             const double *__restrict__ z,
@@ -140,17 +140,17 @@ __global__ void __launch_bounds__(1024) fq_hist_grid_kernel(const double *__rest
         const double rmax = 2.0 * sqrt(m) * 1.0000001 + 1e-9;  // longest possible pair distance
         // (a function of the positions alone: the same structure takes the same
         // stencil, whatever was evaluated before)
-        const double h8 = h12 * (FH_QH_FINE / FT_QH);
-        const double K8 = ceil(rmax / h8) + (double)(FH_PTS_FINE + 2);
-        const double K12 = ceil(rmax / h12) + (double)(FT_PTS + 2);
-        const bool fine = K8 <= (double)(FH_CAP - FH_PTS_FINE);
-        const double h = fine ? h8 : h12, K = fine ? K8 : K12;
-        const double cap = (double)(FH_CAP - (fine ? FH_PTS_FINE : FT_PTS));
+        const double hs[3] = {h12 * (FH_QH_FINEST / FT_QH), h12 * (FH_QH_FINE / FT_QH), h12};
+        const int pts[3] = {FH_PTS_FINEST, FH_PTS_FINE, FT_PTS};
+        int t = 0;  // the finest grid the structure fits (the last one decides the gate)
+        while (t < 2 && ceil(rmax / hs[t]) + (double)(pts[t] + 2) > (double)(FH_CAP - pts[t])) ++t;
+        const double h = hs[t], K = ceil(rmax / h) + (double)(pts[t] + 2);
+        const double cap = (double)(FH_CAP - pts[t]);
         info[0] = h;
         info[1] = 1.0 / h;
         info[2] = fmin(K, cap);
         info[3] = K <= cap ? 1.0 : 0.0;
-        info[4] = fine ? (double)FH_PTS_FINE : (double)FT_PTS;
+        info[4] = (double)pts[t];
     }
 }
 
@@ -255,7 +255,9 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fq_hist_kernel(const HistParams
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (p.info[3] == 0.0) return;  // the structure does not fit: the direct kernel runs
-    if (p.info[4] == (double)FH_PTS_FINE) fq_hist_body<FH_PTS_FINE>(p, smem_raw);
+    const int pts = (int)p.info[4];  // block-uniform
+    if (pts == FH_PTS_FINEST) fq_hist_body<FH_PTS_FINEST>(p, smem_raw);
+    else if (pts == FH_PTS_FINE) fq_hist_body<FH_PTS_FINE>(p, smem_raw);
     else fq_hist_body<FT_PTS>(p, smem_raw);
 }
 

@@ -28,10 +28,15 @@ __host__ __device__ constexpr double ft_bary(int i) { return lagrange_bary<FT_PT
 
 // The F(Q) pair histogram of large structures spreads with a SHORTER stencil on a
 // FINER grid when the structure fits it: its cost is the shared-memory atomics per
-// pair (two per node), and the same error bound, max |prod (u - j)| / 8! *
-// (Q_max h)^8 = 1.07e-3 * 0.157^8 = 4e-10, holds for 8 points with Q_max h = 0.157
-// -- 16 atomics per pair instead of 24 on 2.1 times as many nodes.
+// pair (two per node), and the same error bound max |prod (u - j)| / P! *
+// (Q_max h)^P = 4e-10 holds for
+//   12 points, Q_max h = 1/3     (2.2e-4 * 3^-12),
+//    8 points, Q_max h = 0.157   (1.07e-3 * 0.157^8),
+//    6 points, Q_max h = 0.0658  (4.88e-3 * 0.0658^6)
+// -- 24, 16 or 12 atomics per pair on 1, 2.1 or 5.1 times as many nodes.
 constexpr int FH_PTS_FINE = 8;
 constexpr double FH_QH_FINE = 0.157;
+constexpr int FH_PTS_FINEST = 6;
+constexpr double FH_QH_FINEST = 0.0658;
 
 }  // namespace iid

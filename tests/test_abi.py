@@ -100,16 +100,21 @@ def test_small_structures_get_a_single_wave_triangle_list():
         assert (total <= 148) == one_wave, (n, total)
 
 
-@pytest.mark.parametrize('fn,points,lft0,qh0', [('iid_stencil_weights', 12, 5, 1. / 3.),
-                                                ('iid_hist_stencil_weights', 8, 3, 0.157)])
-def test_radial_stencil_interpolates_band_limited_functions(fn, points, lft0, qh0):
+@pytest.mark.parametrize('tier,points,lft0,qh0', [(None, 12, 5, 1. / 3.), (2, 12, 5, 1. / 3.),
+                                                  (1, 8, 3, 0.157), (0, 6, 2, 0.0658)])
+def test_radial_stencil_interpolates_band_limited_functions(tier, points, lft0, qh0):
     """The Lagrange stencils of iid_stencil.cuh -- 12 points on the grid
-    Q_max h = 1/3 (force table of the fused kernel, coarse-grid pair histogram)
-    and 8 points on the grid Q_max h = 0.157 (fine-grid pair histogram): the
-    weights are a partition of unity, reproduce polynomials, and interpolate
-    sin(Q r)/r to 4e-10 of its amplitude -- the figure DESIGN.md quotes."""
+    Q_max h = 1/3 (force table of the fused kernel, coarse-grid pair histogram),
+    8 points on Q_max h = 0.157 and 6 points on Q_max h = 0.0658 (fine-grid pair
+    histograms): the weights are a partition of unity, reproduce polynomials,
+    and interpolate sin(Q r)/r to 4e-10 of its amplitude -- the figure DESIGN.md
+    quotes."""
     lib = _lib.load()
-    weights = getattr(lib, fn)
+    if tier is None:
+        weights = lib.iid_stencil_weights
+    else:
+        def weights(*a):
+            return lib.iid_hist_stencil_weights(tier, *a)
     w = np.zeros(16)
     npts, left = ctypes.c_int(0), ctypes.c_int(0)
     qh = ctypes.c_double(0.)
@@ -121,7 +126,7 @@ def test_radial_stencil_interpolates_band_limited_functions(fn, points, lft0, qh
     qmax, worst = 25., 0.
     h = qmax_h / qmax
     for _ in range(400):
-        u, k = rs.rand(), rs.randint(0, 9000)
+        u, k = rs.rand(), rs.randint(0, 9000 * 12 // points)
         assert weights(u, w.ctypes.data, None, None, None) == 0
         ww = w[:n]
         assert abs(ww.sum() - 1.) < 1e-12

@@ -598,22 +598,24 @@ def test_fq_through_the_pair_histogram():
         assert lib.iid_fq_finish(h, s_tot.data_ptr(), f.data_ptr(), None) == 0
         f_sum = f.cpu().numpy()
     assert nerr(f_sum, f_ref) < 1e-12
-    # two clusters 200 A apart: beyond the fine grid (8 points, 154 A), within the
-    # coarse one (12 points, 327 A) -- the same F(Q) as the direct pass and float64
-    mid = structures.fcc_sphere('Au', 1300)
-    mid.positions[650:] += [200., 0., 0.]
-    scat = ElasticScatter()
-    scat._ensure_wrapped(mid)
-    be = scat._load(mid, scat.exp['qbin'], 'fq')
-    pos = mid.get_positions()
-    f_hist = be.fq(pos)
-    assert np.array_equal(be.fq(pos), f_hist)
-    be.set_option('fq_hist', 0)
-    f_direct = be.fq(pos)
-    be.set_option('fq_hist', 1)
-    ref = oracle.experiment_fq(pos.astype(np.float32), mid.get_array('F(Q) scatter'),
-                               dict(scat.exp), 'fp64', nthreads=8)
-    assert nerr(f_hist, f_direct) < 5e-7 and nerr(f_hist, ref) < 2e-6
+    # the compact structures above take the finest grid (6 points, up to 75 A); two
+    # clusters 100 A apart the fine one (8 points, up to 182 A), 200 A apart the
+    # coarse one (12 points, up to 327 A) -- the same F(Q) as the direct pass and float64
+    for gap in (100., 200.):
+        mid = structures.fcc_sphere('Au', 1300)
+        mid.positions[650:] += [gap, 0., 0.]
+        scat = ElasticScatter()
+        scat._ensure_wrapped(mid)
+        be = scat._load(mid, scat.exp['qbin'], 'fq')
+        pos = mid.get_positions()
+        f_hist = be.fq(pos)
+        assert np.array_equal(be.fq(pos), f_hist)
+        be.set_option('fq_hist', 0)
+        f_direct = be.fq(pos)
+        be.set_option('fq_hist', 1)
+        ref = oracle.experiment_fq(pos.astype(np.float32), mid.get_array('F(Q) scatter'),
+                                   dict(scat.exp), 'fp64', nthreads=8)
+        assert nerr(f_hist, f_direct) < 5e-7 and nerr(f_hist, ref) < 2e-6, gap
     # a structure that does not fit the histogram: the gated direct kernel runs
     far = structures.fcc_sphere('Au', 1300)
     far.positions[650:] += [800., 0., 0.]
