@@ -22,18 +22,17 @@
 // shared-memory atomic unit (one warp-wide atomic per ~5.7 cycles per SM), i.e. by
 // the NUMBER of stencil points: the pass takes the shortest stencil of
 // iid_stencil.cuh whose grid fits the shared-memory histogram -- 6 points up to
-// 75 A at Q_max = 25, 8 points up to 182 A, the 12 points of the coarse grid up to
-// 327 A; all three keep the 4e-10 bound.
-// The histogram is FIXED
-// POINT (units of 2^-28): integer addition commutes, so F(Q) is bit-reproducible
-// whatever the order of the atomics; the only native shared-memory atomic add is
+// 75 A at Q_max = 25, 8 points up to 180 A, the 12 points of the coarse grid up to
+// 382 A; all three keep the 4e-10 bound.  The histogram is FIXED POINT (units of
+// 2^-28): integer addition commutes, so F(Q) is bit-reproducible whatever the
+// order of the atomics; the only native shared-memory atomic add is
 // 32 bits wide, so a node is two words, high (units of 2^-12) and low (16 bits),
 // with the carries folded every 49 152 pairs and the block's histogram flushed
 // to the 64-bit global one every 393 216 pairs.  Pair distances carry the
 // float32 rounding of the positions (FP32 mode) and nothing else: this pass is
 // more accurate than the float32 recurrences it replaces.  A structure whose
 // diameter (twice the radius about its bounding-box centre) does not fit the
-// shared-memory histogram (327 A at Q_max = 25) keeps the direct kernel (the
+// shared-memory histogram (382 A at Q_max = 25) keeps the direct kernel (the
 // gate word below).
 #pragma once
 #include "iid_debye.cuh"

@@ -599,8 +599,8 @@ def test_fq_through_the_pair_histogram():
         f_sum = f.cpu().numpy()
     assert nerr(f_sum, f_ref) < 1e-12
     # the compact structures above take the finest grid (6 points, up to 75 A); two
-    # clusters 100 A apart the fine one (8 points, up to 182 A), 200 A apart the
-    # coarse one (12 points, up to 327 A) -- the same F(Q) as the direct pass and float64
+    # clusters 100 A apart the fine one (8 points, up to 180 A), 200 A apart the
+    # coarse one (12 points, up to 382 A) -- the same F(Q) as the direct pass and float64
     for gap in (100., 200.):
         mid = structures.fcc_sphere('Au', 1300)
         mid.positions[650:] += [gap, 0., 0.]
