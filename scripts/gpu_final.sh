@@ -1,3 +1,6 @@
+#!/bin/bash
+# The records of a round's last state (one GPU): parity tests, ncu capture of the
+# histogram F(Q) pass, configs[4] on one GPU, the bench line of both arms.
 mkdir -p gpurun_out
 ( time python -m pytest tests -m gpu -q --timeout 900 ) > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
 bash scripts/gpu_ncu_fqhist.sh
